@@ -1,0 +1,153 @@
+// dbt_internal.cuh -- shared internals of libdbt_b200 (sm_100a only, no other back end).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include "../../include/dbt_b200.h"
+
+namespace dbt {
+
+// ---- on-disk layout in 32-bit words (reference: dbtproj.h:16-38) -------------
+constexpr uint32_t kBlockWords = 3504;   // 14016 / 4
+constexpr uint32_t kRecWords = 35;       // 140 / 4
+constexpr uint32_t kRpb = 100;           // MAX_RECORDS_PER_BLOCK
+constexpr uint32_t kEntriesWord = 2;     // entries start at byte 8
+constexpr uint32_t kStrWord = 2;         // str starts at byte 8 of a record
+constexpr uint32_t kStrWords = 30;       // 120 / 4
+constexpr uint32_t kTrailerWord = 3502;  // valid/misc/pad word, then dummy at 3503
+constexpr uint32_t kBlockVec4 = 876;     // 14016 / 16
+
+// word offset of slot s (slot = block*100 + entry) inside an image
+__host__ __device__ __forceinline__ uint64_t slot_word(uint64_t slot) {
+    uint64_t b = slot / kRpb;
+    uint32_t e = (uint32_t)(slot - b * kRpb);
+    return b * kBlockWords + kEntriesWord + (uint64_t)e * kRecWords;
+}
+
+// ---- error plumbing ---------------------------------------------------------------------
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define DBT_CUDA(expr)                                                         \
+    do {                                                                       \
+        cudaError_t e__ = (expr);                                              \
+        if (e__ != cudaSuccess) return ::dbt::cuda_fail(e__, #expr, __FILE__, __LINE__); \
+    } while (0)
+#define DBT_TRY(expr)                  \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__ != 0) return rc__;    \
+    } while (0)
+#define DBT_KERNEL_CHECK() DBT_CUDA(cudaGetLastError())
+
+// ---- stage timing ---------------------------------------------------------------------------
+enum Stage {
+    ST_HEADERS = 0,
+    ST_EXTRACT,
+    ST_HIST,
+    ST_ONESWEEP,
+    ST_WORD_GATHER,
+    ST_UNIQUE,
+    ST_GATHER,
+    ST_HASH_BUILD,
+    ST_HASH_PROBE,
+    ST_COMPACT,
+    ST_INTERSECT,
+    ST_MISC,
+    ST_H2D,
+    ST_D2H,
+    ST_COUNT
+};
+void count_launch(int n = 1);
+struct StageScope { // records events around a stage when timing is enabled
+    StageScope(int stage, cudaStream_t s);
+    ~StageScope();
+    int stage;
+    cudaStream_t stream;
+    int slot;
+};
+void stage_resolve(); // call after a stream sync: folds pending event pairs into the totals
+
+// ---- workspace bump allocator (no hidden device allocation on the device-scope path) -------
+struct Arena {
+    char *base;
+    size_t cap, off;
+    Arena(void *p, size_t bytes) : base((char *)p), cap(bytes), off(0) {}
+    template <typename T> T *take(size_t count) {
+        size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+        if (off + bytes > cap) return nullptr;
+        T *r = (T *)(base + off);
+        off += bytes;
+        return r;
+    }
+    size_t mark() const { return off; }
+    void release(size_t m) { off = m; }
+};
+inline size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+// ---- key description ------------------------------------------------------------------------
+// A key is a few big-endian-comparable u32 words per row, most significant first:
+//   field '0': recid                   -> w0                (column array)
+//   field '1': num                     -> w0
+//   field '2': str, NUL-normalised     -> str[kw]           (AoS array, kw = 8 or 30 words)
+//   field '3': num then str            -> w0, str[kw]
+struct KeyCols {
+    uint32_t *w0;     // [n] most significant word for fields 0/1/3 (nullptr for field 2)
+    uint32_t *str;    // [n][kw] AoS big-endian words (nullptr for fields 0/1)
+    uint32_t kw;      // words per str key
+    uint32_t *recid;  // [n] recid column (tie-break word when recids are not monotone in file order)
+    uint64_t n;
+    // host copies of the OR/AND statistics gathered during extraction
+    uint32_t vary_w0, vary_recid, vary_str[30];
+    int recid_unsorted;
+};
+
+// ---- launchers implemented in the .cu files --------------------------------------------------
+// headers / extraction (kernels_extract.cu)
+struct ImageInfo {
+    uint64_t nrows;      // live rows
+    int prefix_full;     // every block except the last is full => slot == row
+};
+int image_info(const void *d_image, uint64_t nblocks, uint32_t **d_row_slot_out, Arena &ws, cudaStream_t st,
+               ImageInfo *info);
+struct ExtractStats { // device-side
+    uint32_t or_w0, and_w0, or_recid, and_recid, recid_unsorted, str_overflow, pad[2];
+    uint32_t str_or[32], str_and[32];
+};
+int extract_keys(const void *d_image, uint64_t nrows, const uint32_t *d_row_slot, int field, uint32_t kw,
+                 uint32_t *d_w0, uint32_t *d_str, uint32_t *d_recid, ExtractStats *d_stats, cudaStream_t st);
+
+// radix sort (kernels_sort.cu)
+size_t sort_ws_bytes(uint64_t n);
+// sorts pairs over the key bits set in `varying_mask` (digits covering only constant bits are skipped)
+int sort_pairs_masked(uint32_t *&keys, uint32_t *&keys_alt, uint32_t *&vals, uint32_t *&vals_alt, uint64_t n,
+                      uint32_t varying_mask, bool iota_vals, Arena &ws, cudaStream_t st);
+int or_and_reduce(const uint32_t *d_words, uint64_t n, uint32_t *d_or_and /*2 words*/, cudaStream_t st);
+int gather_word(const uint32_t *d_src, uint32_t stride, uint32_t word, const uint32_t *d_perm, uint32_t *d_out,
+                uint64_t n, cudaStream_t st);
+int iota_u32(uint32_t *d, uint64_t n, cudaStream_t st);
+
+// unique / compaction / gather (kernels_gather.cu)
+int unique_rows(const KeyCols &k, int field, const uint32_t *d_perm, const uint32_t *d_sorted_w0, uint64_t n,
+                uint32_t *d_uperm, uint32_t *d_ukeys, uint64_t *d_count /*device u64*/, Arena &ws, cudaStream_t st);
+// out = values[i] (or i when values == nullptr) repeated counts[i] times, ascending i; *d_total = sum(counts)
+int compact_select(const uint32_t *d_counts, const uint32_t *d_values, uint64_t n, uint32_t *d_out, uint64_t out_cap,
+                   uint64_t *d_total, Arena &ws, cudaStream_t st);
+int gather_records(const void *d_in, const uint32_t *d_rows, const uint32_t *d_row_slot, uint64_t nrows_out,
+                   void *d_out, cudaStream_t st);
+
+// joins (kernels_join.cu)
+size_t hash_table_slots(uint64_t nr);
+int hash_join_counts(const KeyCols &r, const KeyCols &s, int field, uint32_t *d_counts /*[s.n]*/, Arena &ws,
+                     cudaStream_t st);
+// sorted unique row lists of R and S -> per-R-unique-row 0/1 match flags, and the reference walk's read count
+int intersect_sorted(const KeyCols &r, const uint32_t *d_ur, const uint32_t *d_urkeys, uint64_t nur, const KeyCols &s,
+                     const uint32_t *d_us, const uint32_t *d_uskeys, uint64_t nus, int field, uint32_t *d_flags,
+                     uint64_t *d_later_reads, cudaStream_t st);
+
+// generator (kernels_gen.cu)
+int gen_syn(uint64_t seed, uint64_t n_total, uint64_t U, int kind, uint64_t row0, uint64_t nrows, uint32_t recid0,
+            void *d_image, cudaStream_t st);
+
+} // namespace dbt

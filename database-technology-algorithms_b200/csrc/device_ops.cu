@@ -1,0 +1,316 @@
+// device_ops.cu -- device-scope operators: block image in HBM -> block image in HBM.
+//
+// These are the GPU bodies of the four dbtproj.h operators (reference DatabaseProject.cpp:94-647).
+// Pipeline shared by all of them:
+//   headers -> key extraction (AoS -> columns) -> [LSD radix sort of (key word, row) pairs, one
+//   word at a time from least to most significant, constant digits skipped] -> [unique | hash
+//   build/probe | intersection] -> compaction -> ONE record gather into the output image.
+#include "dbt_internal.cuh"
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace dbt {
+
+struct Prepared {
+    ImageInfo info;
+    uint32_t *row_slot; // nullptr when slot == row
+    KeyCols keys;
+};
+
+static bool field_ok(int f) { return f >= '0' && f <= '3'; }
+
+static int prepare(const void *d_img, uint64_t nblocks, int field, Arena &ws, cudaStream_t st, Prepared *out) {
+    memset(out, 0, sizeof *out);
+    DBT_TRY(image_info(d_img, nblocks, &out->row_slot, ws, st, &out->info));
+    const uint64_t n = out->info.nrows;
+    KeyCols &k = out->keys;
+    k.n = n;
+    k.kw = 8;
+    if (n == 0) return 0;
+    const bool has_w0 = field != '2', has_str = field >= '2';
+    ExtractStats *d_stats = ws.take<ExtractStats>(1);
+    k.recid = ws.take<uint32_t>(n);
+    k.w0 = has_w0 ? ws.take<uint32_t>(n) : nullptr;
+    k.str = has_str ? ws.take<uint32_t>(n * k.kw) : nullptr;
+    if (!d_stats || !k.recid || (has_w0 && !k.w0) || (has_str && !k.str)) {
+        set_error("prepare: workspace too small");
+        return DBT_ERR_WORKSPACE;
+    }
+    ExtractStats h;
+    DBT_TRY(extract_keys(d_img, n, out->row_slot, field, k.kw, k.w0, k.str, k.recid, d_stats, st));
+    DBT_CUDA(cudaMemcpyAsync(&h, d_stats, sizeof h, cudaMemcpyDeviceToHost, st));
+    DBT_CUDA(cudaStreamSynchronize(st));
+    if (has_str && h.str_overflow) {
+        // some str has no NUL in its first 32 bytes: fall back to the full 120-byte key
+        k.kw = kStrWords;
+        k.str = ws.take<uint32_t>(n * k.kw);
+        if (!k.str) {
+            set_error("prepare: workspace too small for 120-byte string keys (size it with dbt_dev_ws_bytes_kw(..., 30))");
+            return DBT_ERR_WORKSPACE;
+        }
+        DBT_TRY(extract_keys(d_img, n, out->row_slot, field, k.kw, k.w0, k.str, k.recid, d_stats, st));
+        DBT_CUDA(cudaMemcpyAsync(&h, d_stats, sizeof h, cudaMemcpyDeviceToHost, st));
+        DBT_CUDA(cudaStreamSynchronize(st));
+    }
+    k.vary_w0 = has_w0 ? (h.or_w0 ^ h.and_w0) : 0;
+    k.vary_recid = h.or_recid ^ h.and_recid;
+    for (uint32_t j = 0; j < 30; ++j) k.vary_str[j] = (has_str && j < k.kw) ? (h.str_or[j] ^ h.str_and[j]) : 0;
+    k.recid_unsorted = (int)h.recid_unsorted;
+    return 0;
+}
+
+// Order the rows by (key(field), recid); ties beyond that keep file order (LSD passes are stable).
+// Returns the row permutation and, for 1-word keys, the sorted key column.
+static int sort_rows_by_key(KeyCols &k, int field, Arena &ws, cudaStream_t st, uint32_t **perm_out,
+                            uint32_t **sorted_w0_out) {
+    const uint64_t n = k.n;
+    *perm_out = nullptr;
+    *sorted_w0_out = nullptr;
+    if (n == 0) return 0;
+    struct Word {
+        const uint32_t *src;
+        uint32_t stride, idx, vary;
+    };
+    std::vector<Word> words; // least significant first
+    if (field != '0' && k.recid_unsorted && k.vary_recid) words.push_back({k.recid, 1, 0, k.vary_recid});
+    if (field >= '2')
+        for (int j = (int)k.kw - 1; j >= 0; --j)
+            if (k.vary_str[j]) words.push_back({k.str, k.kw, (uint32_t)j, k.vary_str[j]});
+    const bool w0_is_key = field != '2';
+    // field '0' with recids already ascending in file order: the file is sorted (stable) as it is
+    const bool w0_sorted_already = (field == '0' && !k.recid_unsorted);
+    if (w0_is_key && k.vary_w0 && !w0_sorted_already) words.push_back({k.w0, 1, 0, k.vary_w0});
+
+    uint32_t *ka = nullptr, *kb = ws.take<uint32_t>(n), *va = ws.take<uint32_t>(n), *vb = ws.take<uint32_t>(n);
+    const bool single_col = (words.size() == 1 && words[0].src == k.w0); // sort the column in place (clobbers it)
+    if (!single_col) ka = ws.take<uint32_t>(n);
+    else ka = k.w0;
+    if (!ka || !kb || !va || !vb) {
+        set_error("sort: workspace too small");
+        return DBT_ERR_WORKSPACE;
+    }
+    uint32_t *kk = ka, *kk_alt = kb, *vv = va, *vv_alt = vb;
+    bool first = true;
+    for (const Word &w : words) {
+        if (!(first && single_col)) {
+            StageScope sc(ST_WORD_GATHER, st);
+            DBT_TRY(gather_word(w.src, w.stride, w.idx, first ? nullptr : vv, kk, n, st));
+        }
+        DBT_TRY(sort_pairs_masked(kk, kk_alt, vv, vv_alt, n, w.vary, first, ws, st));
+        first = false;
+    }
+    if (first) DBT_TRY(iota_u32(vv, n, st)); // nothing varied: identity order
+    *perm_out = vv;
+    if (field == '0' || field == '1') {
+        if (!words.empty() && words.back().src == k.w0) *sorted_w0_out = kk;
+        else *sorted_w0_out = k.w0; // constant column, or already ascending: the column is its own sorted copy
+    }
+    return 0;
+}
+
+static int read_u64(const uint64_t *d, uint64_t *h, int count, cudaStream_t st) {
+    DBT_CUDA(cudaMemcpyAsync(h, d, 8 * count, cudaMemcpyDeviceToHost, st));
+    DBT_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+static int finish(cudaStream_t st) {
+    DBT_CUDA(cudaStreamSynchronize(st));
+    stage_resolve();
+    return 0;
+}
+
+// ---- workspace bound ----------------------------------------------------------------------
+static size_t rel_bytes(uint64_t nb, int field, uint32_t kw, bool sorted) {
+    uint64_t n = nb * kRpb;
+    size_t b = 0;
+    b += pad256(4 * nb) + 512;                       // nreserved + header stats
+    b += pad256(4 * n);                              // ragged slot list
+    b += 512 + pad256(4 * n);                        // stats + recid
+    if (field != '2') b += pad256(4 * n);            // w0
+    if (field >= '2') b += pad256(4 * n * 8) + (kw > 8 ? pad256(4 * n * kw) : 0);
+    if (sorted) b += 4 * pad256(4 * n) + sort_ws_bytes(n) + 4096; // ping/pong keys+rows, look-back state
+    return b;
+}
+
+} // namespace dbt
+
+using namespace dbt;
+
+extern "C" size_t dbt_dev_ws_bytes_kw(int op, uint64_t nbr, uint64_t nbs, int field, uint32_t kw) {
+    uint64_t nr = nbr * kRpb, ns = nbs * kRpb;
+    size_t scan = pad256(8 * ((std::max(nr, ns) + 2047) / 2048 + 1)) + 1024;
+    size_t b = 1 << 20;
+    switch (op) {
+    case DBT_OP_SORT: b += rel_bytes(nbr, field, kw, true); break;
+    case DBT_OP_DEDUP: b += rel_bytes(nbr, field, kw, true) + 2 * pad256(4 * nr) + scan + 512; break;
+    case DBT_OP_MERGEJOIN:
+        b += rel_bytes(nbr, field, kw, true) + rel_bytes(nbs, field, kw, true) + 2 * pad256(4 * nr) + 2 * pad256(4 * ns) +
+             2 * pad256(4 * nr) + scan + 4096;
+        break;
+    case DBT_OP_HASHJOIN:
+        b += rel_bytes(nbr, field, kw, false) + rel_bytes(nbs, field, kw, false) + 2 * pad256(4 * hash_table_slots(nr)) +
+             2 * pad256(4 * ns) + scan + 4096;
+        break;
+    default: return 0;
+    }
+    return b + b / 16;
+}
+extern "C" size_t dbt_dev_ws_bytes(int op, uint64_t nbr, uint64_t nbs, int field) {
+    return dbt_dev_ws_bytes_kw(op, nbr, nbs, field, 8);
+}
+
+#define DBT_CHECK_ARGS(cond, msg)  \
+    do {                           \
+        if (!(cond)) {             \
+            set_error(msg);        \
+            return DBT_ERR_ARG;    \
+        }                          \
+    } while (0)
+
+extern "C" int dbt_dev_mergesort(const void *d_in, uint64_t nblocks, int field, void *d_out, void *d_ws, size_t ws_bytes,
+                                 void *stream, uint64_t *nrows) {
+    DBT_CHECK_ARGS(field_ok(field), "Wrong field! Please give a field between 0 and 3!");
+    DBT_CHECK_ARGS((d_in && d_out && d_ws) || nblocks == 0, "dbt_dev_mergesort: NULL buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    Arena ws(d_ws, ws_bytes);
+    Prepared p;
+    DBT_TRY(prepare(d_in, nblocks, field, ws, st, &p));
+    uint32_t *perm, *sorted;
+    DBT_TRY(sort_rows_by_key(p.keys, field, ws, st, &perm, &sorted));
+    DBT_TRY(gather_records(d_in, perm, p.row_slot, p.info.nrows, d_out, st));
+    if (nrows) *nrows = p.info.nrows;
+    return finish(st);
+}
+
+extern "C" int dbt_dev_dedup(const void *d_in, uint64_t nblocks, int field, void *d_out, void *d_ws, size_t ws_bytes,
+                             void *stream, uint64_t *nrows, uint64_t *nunique) {
+    DBT_CHECK_ARGS(field_ok(field), "Wrong field! Please give a field between 0 and 3!");
+    DBT_CHECK_ARGS((d_in && d_out && d_ws) || nblocks == 0, "dbt_dev_dedup: NULL buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    Arena ws(d_ws, ws_bytes);
+    Prepared p;
+    DBT_TRY(prepare(d_in, nblocks, field, ws, st, &p));
+    const uint64_t n = p.info.nrows;
+    uint64_t u = 0;
+    if (n) {
+        uint32_t *perm, *sorted;
+        DBT_TRY(sort_rows_by_key(p.keys, field, ws, st, &perm, &sorted));
+        uint32_t *uperm = ws.take<uint32_t>(n);
+        uint64_t *d_cnt = ws.take<uint64_t>(8);
+        if (!uperm || !d_cnt) {
+            set_error("dedup: workspace too small");
+            return DBT_ERR_WORKSPACE;
+        }
+        DBT_TRY(unique_rows(p.keys, field, perm, sorted, n, uperm, nullptr, d_cnt, ws, st));
+        DBT_TRY(read_u64(d_cnt, &u, 1, st));
+        DBT_TRY(gather_records(d_in, uperm, p.row_slot, u, d_out, st));
+    }
+    if (nrows) *nrows = n;
+    if (nunique) *nunique = u;
+    return finish(st);
+}
+
+// sort + unique of one relation; leaves the unique row list (and unique key column for 1-word keys)
+static int dedup_rel(const void *d_in, uint64_t nblocks, int field, Arena &ws, cudaStream_t st, Prepared *p,
+                     uint32_t **urows, uint32_t **ukeys, uint64_t *nu) {
+    DBT_TRY(prepare(d_in, nblocks, field, ws, st, p));
+    const uint64_t n = p->info.nrows;
+    *urows = *ukeys = nullptr;
+    *nu = 0;
+    if (!n) return 0;
+    uint32_t *perm, *sorted;
+    DBT_TRY(sort_rows_by_key(p->keys, field, ws, st, &perm, &sorted));
+    *urows = ws.take<uint32_t>(n);
+    const bool one = (field == '0' || field == '1');
+    *ukeys = one ? ws.take<uint32_t>(n) : nullptr;
+    uint64_t *d_cnt = ws.take<uint64_t>(8);
+    if (!*urows || (one && !*ukeys) || !d_cnt) {
+        set_error("mergejoin: workspace too small");
+        return DBT_ERR_WORKSPACE;
+    }
+    DBT_TRY(unique_rows(p->keys, field, perm, sorted, n, *urows, *ukeys, d_cnt, ws, st));
+    DBT_TRY(read_u64(d_cnt, nu, 1, st));
+    return 0;
+}
+
+extern "C" int dbt_dev_mergejoin(const void *d_in_r, uint64_t nbr, const void *d_in_s, uint64_t nbs, int field,
+                                 void *d_out_ur, void *d_out_us, void *d_out, void *d_ws, size_t ws_bytes, void *stream,
+                                 uint64_t *res) {
+    DBT_CHECK_ARGS(field_ok(field), "Wrong field! Please give a field between 0 and 3!");
+    DBT_CHECK_ARGS(d_ws && res, "dbt_dev_mergejoin: NULL buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    Arena ws(d_ws, ws_bytes);
+    Prepared pr, ps;
+    uint32_t *ur, *urk, *us, *usk;
+    uint64_t nur, nus;
+    DBT_TRY(dedup_rel(d_in_r, nbr, field, ws, st, &pr, &ur, &urk, &nur));
+    DBT_TRY(dedup_rel(d_in_s, nbs, field, ws, st, &ps, &us, &usk, &nus));
+    // the side files "1outfile.bin" / "2outfile.bin" (DatabaseProject.cpp:385-394)
+    if (d_out_ur) DBT_TRY(gather_records(d_in_r, ur, pr.row_slot, nur, d_out_ur, st));
+    if (d_out_us) DBT_TRY(gather_records(d_in_s, us, ps.row_slot, nus, d_out_us, st));
+    uint64_t nres = 0, reads = 0;
+    if (nur && nus) {
+        uint32_t *flags = ws.take<uint32_t>(nur);
+        uint32_t *mrows = ws.take<uint32_t>(nur);
+        uint64_t *d_res = ws.take<uint64_t>(8);
+        if (!flags || !mrows || !d_res) {
+            set_error("mergejoin: workspace too small");
+            return DBT_ERR_WORKSPACE;
+        }
+        DBT_TRY(intersect_sorted(pr.keys, ur, urk, nur, ps.keys, us, usk, nus, field, flags, d_res + 1, st));
+        DBT_TRY(compact_select(flags, ur, nur, mrows, nur, d_res, ws, st));
+        uint64_t h[2];
+        DBT_TRY(read_u64(d_res, h, 2, st));
+        nres = h[0];
+        reads = h[1];
+        if (d_out) DBT_TRY(gather_records(d_in_r, mrows, pr.row_slot, nres, d_out, st));
+    }
+    res[0] = nres;
+    res[1] = nur;
+    res[2] = nus;
+    res[3] = reads;
+    return finish(st);
+}
+
+extern "C" int dbt_dev_hashjoin(const void *d_in_r, uint64_t nbr, const void *d_in_s, uint64_t nbs, int field,
+                                void *d_out, uint64_t out_capacity_blocks, void *d_ws, size_t ws_bytes, void *stream,
+                                uint64_t *nres) {
+    DBT_CHECK_ARGS(field_ok(field), "Wrong field! Please give a field between 0 and 3!");
+    DBT_CHECK_ARGS(d_ws && nres, "dbt_dev_hashjoin: NULL buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    Arena ws(d_ws, ws_bytes);
+    Prepared pr, ps;
+    DBT_TRY(prepare(d_in_r, nbr, field, ws, st, &pr));
+    DBT_TRY(prepare(d_in_s, nbs, field, ws, st, &ps));
+    *nres = 0;
+    const uint64_t ns = ps.info.nrows;
+    if (ns && pr.info.nrows) {
+        if (field >= '2' && pr.keys.kw != ps.keys.kw) {
+            // one side needed 120-byte keys, the other did not: widen the short side so the shapes agree
+            set_error("hashjoin: mixed string key widths are not supported yet");
+            return DBT_ERR_UNSUPPORTED;
+        }
+        uint32_t *counts = ws.take<uint32_t>(ns);
+        uint64_t cap = out_capacity_blocks * kRpb;
+        uint32_t *rows = ws.take<uint32_t>(std::max<uint64_t>(std::min<uint64_t>(cap, (field == '3') ? cap : ns), 1));
+        uint64_t *d_total = ws.take<uint64_t>(8);
+        if (!counts || !rows || !d_total) {
+            set_error("hashjoin: workspace too small");
+            return DBT_ERR_WORKSPACE;
+        }
+        uint64_t rows_cap = std::max<uint64_t>(std::min<uint64_t>(cap, (field == '3') ? cap : ns), 1);
+        DBT_TRY(hash_join_counts(pr.keys, ps.keys, field, counts, ws, st));
+        DBT_TRY(compact_select(counts, nullptr, ns, rows, rows_cap, d_total, ws, st));
+        uint64_t total = 0;
+        DBT_TRY(read_u64(d_total, &total, 1, st));
+        *nres = total;
+        if (total > cap || total > rows_cap) {
+            set_error("hashjoin: output capacity too small (nres returned)");
+            return DBT_ERR_WORKSPACE;
+        }
+        DBT_TRY(gather_records(d_in_s, rows, ps.row_slot, total, d_out, st));
+    }
+    return finish(st);
+}

@@ -1,0 +1,239 @@
+// kernels_extract.cu -- block headers and AoS -> columnar key extraction.
+//
+// The reference walks entries[0..nreserved) of every block and compares records through
+// compareID/NUM/STR/NUMSTR (DatabaseProject.cpp:44-92,198-205).  Here the keys are pulled out
+// once into order-preserving u32 words: recid / num as they are, str as NUL-normalised
+// big-endian words (strcmp order == unsigned word order), so every later stage works on
+// integers only.
+#include "dbt_internal.cuh"
+
+namespace dbt {
+
+// ---------------------------------------------------------------------------------------------
+// Headers: live rows per block.
+// ---------------------------------------------------------------------------------------------
+struct HeaderStats {
+    unsigned long long nrows;
+    uint32_t ragged; // some block before the last is not full
+    uint32_t pad;
+};
+
+__global__ void __launch_bounds__(256) header_kernel(const uint32_t *__restrict__ img, uint64_t nblocks,
+                                                     uint32_t *__restrict__ nres_out, HeaderStats *stats) {
+    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t r = 0, ragged = 0;
+    if (b < nblocks) {
+        r = img[b * kBlockWords + 1];
+        if (r > kRpb) r = kRpb;
+        if (b + 1 < nblocks && r != kRpb) ragged = 1;
+        if (nres_out) nres_out[b] = r;
+    }
+    uint32_t sum = __reduce_add_sync(0xFFFFFFFFu, r);
+    uint32_t rg = __reduce_or_sync(0xFFFFFFFFu, ragged);
+    if ((threadIdx.x & 31) == 0) {
+        if (sum) atomicAdd(&stats->nrows, (unsigned long long)sum);
+        if (rg) atomicOr(&stats->ragged, 1u);
+    }
+}
+
+// ragged images only (rare): serial-per-CTA scan of nreserved, then slot list.  One CTA, chunked.
+__global__ void __launch_bounds__(1024) ragged_slots_kernel(const uint32_t *__restrict__ nres, uint64_t nblocks,
+                                                            uint32_t *__restrict__ row_slot) {
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint64_t b0 = 0; b0 < nblocks; b0 += 1024) {
+        uint64_t b = b0 + threadIdx.x;
+        uint32_t v = b < nblocks ? nres[b] : 0, x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += t;
+        }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        uint32_t pre = carry;
+        for (int w = 0; w < warp; ++w) pre += wsum[w];
+        uint32_t off = pre + x - v;
+        for (uint32_t i = 0; i < v; ++i) row_slot[off + i] = (uint32_t)(b * kRpb + i);
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = pre + x;
+        __syncthreads();
+    }
+}
+
+int image_info(const void *d_image, uint64_t nblocks, uint32_t **d_row_slot_out, Arena &ws, cudaStream_t st,
+               ImageInfo *info) {
+    StageScope sc(ST_HEADERS, st);
+    *d_row_slot_out = nullptr;
+    info->nrows = 0;
+    info->prefix_full = 1;
+    if (nblocks == 0) return 0;
+    HeaderStats *d_stats = ws.take<HeaderStats>(1);
+    uint32_t *d_nres = ws.take<uint32_t>(nblocks);
+    if (!d_stats || !d_nres) {
+        set_error("image_info: workspace too small");
+        return DBT_ERR_WORKSPACE;
+    }
+    DBT_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(HeaderStats), st));
+    int grid = (int)((nblocks + 255) / 256);
+    header_kernel<<<grid, 256, 0, st>>>((const uint32_t *)d_image, nblocks, d_nres, d_stats);
+    count_launch();
+    DBT_KERNEL_CHECK();
+    HeaderStats h;
+    DBT_CUDA(cudaMemcpyAsync(&h, d_stats, sizeof h, cudaMemcpyDeviceToHost, st));
+    DBT_CUDA(cudaStreamSynchronize(st));
+    info->nrows = h.nrows;
+    info->prefix_full = h.ragged ? 0 : 1;
+    if (h.nrows >= (1ull << 30)) {
+        set_error("image has >= 2^30 live rows; shard it across GPUs");
+        return DBT_ERR_UNSUPPORTED;
+    }
+    if (h.ragged) {
+        uint32_t *slots = ws.take<uint32_t>(h.nrows ? h.nrows : 1);
+        if (!slots) {
+            set_error("image_info: workspace too small (ragged slot list)");
+            return DBT_ERR_WORKSPACE;
+        }
+        ragged_slots_kernel<<<1, 1024, 0, st>>>(d_nres, nblocks, slots);
+        count_launch();
+        DBT_KERNEL_CHECK();
+        *d_row_slot_out = slots;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Key extraction.
+// ---------------------------------------------------------------------------------------------
+__global__ void init_stats_kernel(ExtractStats *s) {
+    int t = threadIdx.x;
+    uint32_t *w = reinterpret_cast<uint32_t *>(s);
+    if (t < (int)(sizeof(ExtractStats) / 4)) w[t] = 0;
+    __syncthreads();
+    if (t == 0) {
+        s->and_w0 = 0xFFFFFFFFu;
+        s->and_recid = 0xFFFFFFFFu;
+    }
+    if (t < 32) s->str_and[t] = 0xFFFFFFFFu;
+}
+
+// NUL-normalise one little-endian word of a C string and make it big-endian-comparable.
+// `ended` carries "a NUL was seen in an earlier word".  strcmp semantics of the reference
+// comparators (DatabaseProject.cpp:57-68): bytes after the first NUL never matter.
+__device__ __forceinline__ uint32_t norm_word(uint32_t w, bool &ended) {
+    if (ended) return 0;
+    uint32_t z = (w - 0x01010101u) & ~w & 0x80808080u; // lowest flagged byte is a true zero byte
+    if (z) {
+        int pos = (__ffs(z) - 1) >> 3; // index of the first NUL byte (byte 0 = lowest address)
+        w &= (pos == 0) ? 0u : (0xFFFFFFFFu >> (32 - 8 * pos));
+        ended = true;
+    }
+    return __byte_perm(w, 0, 0x0123);
+}
+
+template <int FIELD> // 0,1,2,3 (numeric, not ASCII)
+__global__ void __launch_bounds__(256)
+extract_kernel(const uint32_t *__restrict__ img, uint64_t nrows, const uint32_t *__restrict__ row_slot, uint32_t kw,
+               uint32_t *__restrict__ out_w0, uint32_t *__restrict__ out_str, uint32_t *__restrict__ out_recid,
+               ExtractStats *stats) {
+    __shared__ uint32_t s_or[34], s_and[34]; // [0]=w0 [1]=recid [2..]=str words
+    __shared__ uint32_t s_flags[2];
+    const bool HAS_STR = (FIELD >= 2);
+    for (int i = threadIdx.x; i < 34; i += blockDim.x) {
+        s_or[i] = 0;
+        s_and[i] = 0xFFFFFFFFu;
+    }
+    if (threadIdx.x < 2) s_flags[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = r < nrows;
+    uint32_t recid = 0, w0 = 0, unsorted = 0, overflow = 0;
+    uint64_t base = 0;
+    if (live) {
+        uint64_t slot = row_slot ? row_slot[r] : r;
+        base = slot_word(slot);
+        recid = img[base];
+        w0 = (FIELD == 0) ? recid : ((FIELD == 2) ? 0u : img[base + 1]);
+        out_recid[r] = recid;
+        if (FIELD != 2) out_w0[r] = w0;
+    }
+    // recid monotone in file order?  (then a stable sort on the key alone already breaks ties by recid)
+    uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, recid, 1);
+    if (live && r > 0) {
+        if (lane == 0) {
+            uint64_t pslot = row_slot ? row_slot[r - 1] : r - 1;
+            prev = img[slot_word(pslot)];
+        }
+        unsorted = recid < prev;
+    }
+    uint32_t o = __reduce_or_sync(0xFFFFFFFFu, live ? w0 : 0u);
+    uint32_t a = __reduce_and_sync(0xFFFFFFFFu, live ? w0 : 0xFFFFFFFFu);
+    uint32_t o2 = __reduce_or_sync(0xFFFFFFFFu, live ? recid : 0u);
+    uint32_t a2 = __reduce_and_sync(0xFFFFFFFFu, live ? recid : 0xFFFFFFFFu);
+    uint32_t un = __reduce_or_sync(0xFFFFFFFFu, unsorted);
+    if (lane == 0) {
+        atomicOr(&s_or[0], o);
+        atomicAnd(&s_and[0], a);
+        atomicOr(&s_or[1], o2);
+        atomicAnd(&s_and[1], a2);
+        if (un) s_flags[0] = 1;
+    }
+    if (HAS_STR) {
+        bool ended = false;
+        for (uint32_t j = 0; j < kw; ++j) {
+            uint32_t w = 0;
+            if (live) {
+                w = norm_word(img[base + kStrWord + j], ended);
+                out_str[r * kw + j] = w;
+            }
+            uint32_t so = __reduce_or_sync(0xFFFFFFFFu, live ? w : 0u);
+            uint32_t sa = __reduce_and_sync(0xFFFFFFFFu, live ? w : 0xFFFFFFFFu);
+            if (lane == 0) {
+                atomicOr(&s_or[2 + j], so);
+                atomicAnd(&s_and[2 + j], sa);
+            }
+        }
+        overflow = live && !ended && kw < kStrWords;
+        if (__any_sync(0xFFFFFFFFu, overflow) && lane == 0) s_flags[1] = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicOr(&stats->or_w0, s_or[0]);
+        atomicAnd(&stats->and_w0, s_and[0]);
+        atomicOr(&stats->or_recid, s_or[1]);
+        atomicAnd(&stats->and_recid, s_and[1]);
+        if (s_flags[0]) atomicOr(&stats->recid_unsorted, 1u);
+        if (s_flags[1]) atomicOr(&stats->str_overflow, 1u);
+    }
+    if (HAS_STR && threadIdx.x < kw) {
+        atomicOr(&stats->str_or[threadIdx.x], s_or[2 + threadIdx.x]);
+        atomicAnd(&stats->str_and[threadIdx.x], s_and[2 + threadIdx.x]);
+    }
+}
+
+int extract_keys(const void *d_image, uint64_t nrows, const uint32_t *d_row_slot, int field, uint32_t kw,
+                 uint32_t *d_w0, uint32_t *d_str, uint32_t *d_recid, ExtractStats *d_stats, cudaStream_t st) {
+    StageScope sc(ST_EXTRACT, st);
+    init_stats_kernel<<<1, 128, 0, st>>>(d_stats);
+    count_launch();
+    if (nrows) {
+        int grid = (int)((nrows + 255) / 256);
+        const uint32_t *img = (const uint32_t *)d_image;
+        switch (field) {
+        case '0': extract_kernel<0><<<grid, 256, 0, st>>>(img, nrows, d_row_slot, kw, d_w0, d_str, d_recid, d_stats); break;
+        case '1': extract_kernel<1><<<grid, 256, 0, st>>>(img, nrows, d_row_slot, kw, d_w0, d_str, d_recid, d_stats); break;
+        case '2': extract_kernel<2><<<grid, 256, 0, st>>>(img, nrows, d_row_slot, kw, d_w0, d_str, d_recid, d_stats); break;
+        case '3': extract_kernel<3><<<grid, 256, 0, st>>>(img, nrows, d_row_slot, kw, d_w0, d_str, d_recid, d_stats); break;
+        default: set_error("bad field"); return DBT_ERR_ARG;
+        }
+        count_launch();
+    }
+    DBT_KERNEL_CHECK();
+    return 0;
+}
+
+} // namespace dbt

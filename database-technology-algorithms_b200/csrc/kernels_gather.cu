@@ -1,0 +1,265 @@
+// kernels_gather.cu -- adjacent-difference unique, count compaction (single-pass decoupled
+// look-back scans) and the final record gather / block packer.
+//
+//  * unique_rows   replaces the reference's previous-record compare loop in EliminateDuplicates
+//                  (DatabaseProject.cpp:121-162);
+//  * compact_by_count turns per-row match counts into the list of rows to emit, in file order
+//                  (the reference appends matches one by one, DatabaseProject.cpp:584-629);
+//  * gather_records is the only place 140-byte records move (the reference copies every record
+//                  in every pass, DatabaseProject.cpp:202,223,303,338).
+#include "dbt_internal.cuh"
+
+namespace dbt {
+
+// ---------------------------------------------------------------------------------------------
+// Single-pass scan skeleton: each CTA takes a tile (dynamic id), sums its counts, resolves its
+// exclusive prefix by decoupled look-back over 64-bit tile states, then emits.
+// ---------------------------------------------------------------------------------------------
+constexpr uint64_t kSfAgg = 1ull << 62, kSfInc = 2ull << 62, kSvMask = (1ull << 62) - 1;
+
+__device__ __forceinline__ uint64_t ld_volatile64(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_volatile64(uint64_t *p, uint64_t v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v));
+}
+
+struct ScanWs {
+    uint64_t *state; // [ntiles] zeroed
+    uint32_t *ctr;   // zeroed
+};
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+// CountFn: uint32_t operator()(uint64_t i) const           -- how many outputs row i produces
+// EmitFn : void operator()(uint64_t i, uint64_t off, uint32_t c) const -- write them at [off, off+c)
+template <class CountFn, class EmitFn>
+__global__ void __launch_bounds__(kScanThreads)
+scan_emit_kernel(uint64_t n, CountFn cnt, EmitFn emit, ScanWs ws, unsigned long long *total_out) {
+    __shared__ uint64_t s_wsum[kScanThreads / 32];
+    __shared__ uint64_t s_prefix;
+    __shared__ uint32_t s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ws.ctr, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t i0 = (uint64_t)tile * kScanTile + (uint64_t)tid * kScanItems; // blocked arrangement
+    uint32_t c[kScanItems];
+    uint64_t local = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        c[k] = (i0 + k < n) ? cnt(i0 + k) : 0u;
+        local += c[k];
+    }
+    uint64_t x = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint64_t t = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= o) x += t;
+    }
+    if (lane == 31) s_wsum[warp] = x;
+    __syncthreads();
+    uint64_t pre = 0, agg = 0;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; ++w) {
+        uint64_t t = s_wsum[w];
+        if (w < warp) pre += t;
+        agg += t;
+    }
+    if (tid == 0) {
+        uint64_t excl = 0;
+        if (tile == 0) {
+            st_volatile64(&ws.state[0], kSfInc | agg);
+        } else {
+            st_volatile64(&ws.state[tile], kSfAgg | agg);
+            int64_t p = (int64_t)tile - 1;
+            while (true) {
+                uint64_t s;
+                do {
+                    s = ld_volatile64(&ws.state[p]);
+                } while ((s >> 62) == 0);
+                excl += s & kSvMask;
+                if (s & kSfInc) break;
+                --p;
+            }
+            st_volatile64(&ws.state[tile], kSfInc | (excl + agg));
+        }
+        s_prefix = excl;
+        if ((uint64_t)(tile + 1) * kScanTile >= n) *total_out = excl + agg; // last tile
+    }
+    __syncthreads();
+    uint64_t off = s_prefix + pre + x - local;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (c[k]) emit(i0 + k, off, c[k]);
+        off += c[k];
+    }
+}
+
+template <class CountFn, class EmitFn>
+static int run_scan_emit(uint64_t n, CountFn cnt, EmitFn emit, uint64_t *d_total, Arena &ws, cudaStream_t st) {
+    if (n == 0) {
+        DBT_CUDA(cudaMemsetAsync(d_total, 0, 8, st));
+        return 0;
+    }
+    size_t m = ws.mark();
+    uint64_t ntiles = (n + kScanTile - 1) / kScanTile;
+    ScanWs sw;
+    sw.state = ws.take<uint64_t>(ntiles);
+    sw.ctr = ws.take<uint32_t>(64);
+    if (!sw.state || !sw.ctr) {
+        set_error("scan: workspace too small");
+        return DBT_ERR_WORKSPACE;
+    }
+    DBT_CUDA(cudaMemsetAsync(sw.state, 0, ntiles * 8, st));
+    DBT_CUDA(cudaMemsetAsync(sw.ctr, 0, 4, st));
+    scan_emit_kernel<<<(unsigned)ntiles, kScanThreads, 0, st>>>(n, cnt, emit, sw, (unsigned long long *)d_total);
+    count_launch();
+    DBT_KERNEL_CHECK();
+    ws.release(m);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// unique: keep sorted position i iff its key differs from position i-1's key.
+// ---------------------------------------------------------------------------------------------
+struct RowKeyEq { // full-key equality of two rows through the key columns
+    const uint32_t *w0;
+    const uint32_t *str;
+    uint32_t kw;
+    __device__ bool operator()(uint32_t a, uint32_t b) const {
+        if (w0 && w0[a] != w0[b]) return false;
+        if (str) {
+            const uint32_t *pa = str + (uint64_t)a * kw, *pb = str + (uint64_t)b * kw;
+            for (uint32_t j = 0; j < kw; ++j)
+                if (pa[j] != pb[j]) return false;
+        }
+        return true;
+    }
+};
+
+struct UniqueCountSorted { // 1-word keys: the sorted key column is at hand
+    const uint32_t *sorted;
+    __device__ uint32_t operator()(uint64_t i) const { return (i == 0 || sorted[i] != sorted[i - 1]) ? 1u : 0u; }
+};
+struct UniqueCountRows {
+    const uint32_t *perm;
+    RowKeyEq eq;
+    __device__ uint32_t operator()(uint64_t i) const { return (i == 0 || !eq(perm[i - 1], perm[i])) ? 1u : 0u; }
+};
+struct EmitPerm {
+    const uint32_t *perm;
+    uint32_t *out;
+    uint32_t *out_key;         // optional: compacted sorted key column
+    const uint32_t *sorted;
+    __device__ void operator()(uint64_t i, uint64_t off, uint32_t) const {
+        out[off] = perm[i];
+        if (out_key) out_key[off] = sorted[i];
+    }
+};
+
+int unique_rows(const KeyCols &k, int field, const uint32_t *d_perm, const uint32_t *d_sorted_w0, uint64_t n,
+                uint32_t *d_uperm, uint32_t *d_ukeys, uint64_t *d_count, Arena &ws, cudaStream_t st) {
+    StageScope sc(ST_UNIQUE, st);
+    EmitPerm emit{d_perm, d_uperm, d_ukeys, d_sorted_w0};
+    if ((field == '0' || field == '1') && d_sorted_w0) {
+        return run_scan_emit(n, UniqueCountSorted{d_sorted_w0}, emit, d_count, ws, st);
+    }
+    emit.out_key = nullptr;
+    RowKeyEq eq{(field == '2') ? nullptr : k.w0, (field >= '2') ? k.str : nullptr, k.kw};
+    return run_scan_emit(n, UniqueCountRows{d_perm, eq}, emit, d_count, ws, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// compaction of per-row counts into a row list (row i repeated counts[i] times, ascending i)
+// ---------------------------------------------------------------------------------------------
+struct CountFromArray {
+    const uint32_t *c;
+    __device__ uint32_t operator()(uint64_t i) const { return c[i]; }
+};
+struct EmitRowRepeated {
+    uint32_t *out;
+    const uint32_t *values; // optional: emit values[i] instead of i
+    uint64_t cap;
+    __device__ void operator()(uint64_t i, uint64_t off, uint32_t c) const {
+        uint32_t v = values ? values[i] : (uint32_t)i;
+        for (uint32_t t = 0; t < c; ++t)
+            if (off + t < cap) out[off + t] = v;
+    }
+};
+int compact_select(const uint32_t *d_counts, const uint32_t *d_values, uint64_t n, uint32_t *d_out, uint64_t out_cap,
+                   uint64_t *d_total, Arena &ws, cudaStream_t st) {
+    StageScope sc(ST_COMPACT, st);
+    return run_scan_emit(n, CountFromArray{d_counts}, EmitRowRepeated{d_out, d_values, out_cap}, d_total, ws, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Record gather + block packer.  One CTA builds one 14016-byte output block in shared memory
+// from 4-byte gathered words (records are only 4-byte aligned) and stores it with
+// 16-byte vectors; 100 independent 140-byte random reads per block are in flight per CTA.
+// ---------------------------------------------------------------------------------------------
+constexpr int kGatherThreads = 256;
+
+__global__ void __launch_bounds__(kGatherThreads)
+gather_kernel(const uint32_t *__restrict__ in, const uint32_t *__restrict__ rows, const uint32_t *__restrict__ row_slot,
+              uint64_t nrows_out, uint4 *__restrict__ out, uint64_t nblocks_out) {
+    __shared__ __align__(16) uint32_t stage[kBlockWords];
+    __shared__ uint64_t src[kRpb];
+    const int tid = threadIdx.x;
+    for (uint64_t ob = blockIdx.x; ob < nblocks_out; ob += gridDim.x) {
+        const uint64_t r0 = ob * kRpb;
+        const uint32_t cnt = (uint32_t)min((uint64_t)kRpb, nrows_out - r0);
+        if (tid < (int)cnt) {
+            uint32_t row = rows ? rows[r0 + tid] : (uint32_t)(r0 + tid);
+            uint64_t slot = row_slot ? row_slot[row] : row;
+            src[tid] = slot_word(slot);
+        }
+        if (tid == 0) {
+            stage[0] = (uint32_t)ob; // blockid
+            stage[1] = cnt;          // nreserved
+            stage[kTrailerWord] = 1; // valid=1, misc=0, padding 0
+            stage[kTrailerWord + 1] = cnt; // dummy
+        }
+        __syncthreads();
+        const uint32_t nwords = cnt * kRecWords;
+#pragma unroll 4
+        for (uint32_t idx = tid; idx < kRpb * kRecWords; idx += kGatherThreads) {
+            uint32_t rec = idx / kRecWords;
+            uint32_t w = idx - rec * kRecWords;
+            stage[kEntriesWord + idx] = (idx < nwords) ? in[src[rec] + w] : 0u;
+        }
+        __syncthreads();
+        const uint4 *sv = reinterpret_cast<const uint4 *>(stage);
+        uint4 *dst = out + ob * kBlockVec4;
+        for (uint32_t i = tid; i < kBlockVec4; i += kGatherThreads) dst[i] = sv[i];
+        __syncthreads();
+    }
+}
+
+int gather_records(const void *d_in, const uint32_t *d_rows, const uint32_t *d_row_slot, uint64_t nrows_out, void *d_out,
+                   cudaStream_t st) {
+    StageScope sc(ST_GATHER, st);
+    if (nrows_out == 0) return 0;
+    uint64_t nb = (nrows_out + kRpb - 1) / kRpb;
+    int grid = (int)std::min<uint64_t>(nb, 148 * 8 * 4);
+    gather_kernel<<<grid, kGatherThreads, 0, st>>>((const uint32_t *)d_in, d_rows, d_row_slot, nrows_out, (uint4 *)d_out,
+                                                   nb);
+    count_launch();
+    DBT_KERNEL_CHECK();
+    return 0;
+}
+
+} // namespace dbt
+
+extern "C" int dbt_gather_records(const void *d_in_image, const uint32_t *d_rows, const uint32_t *d_row_slot,
+                                  uint64_t nrows_out, void *d_out_image, void *stream) {
+    if (!d_in_image || !d_out_image) {
+        dbt::set_error("dbt_gather_records: NULL image");
+        return DBT_ERR_ARG;
+    }
+    return dbt::gather_records(d_in_image, d_rows, d_row_slot, nrows_out, d_out_image, (cudaStream_t)stream);
+}

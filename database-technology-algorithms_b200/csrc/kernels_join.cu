@@ -1,0 +1,304 @@
+// kernels_join.cu -- hash build/probe and sorted-list intersection.
+//
+//  * hash_join_counts replaces the reference's unordered_map / unordered_multimap build and
+//    find/equal_range probe (DatabaseProject.cpp:510-547, 584-629): a linear-probing
+//    open-addressing table in HBM keyed by the u32 key (fields '0'/'1') or by row id with full-key
+//    compare (fields '2'/'3').  The result is, per S row, how many times the reference would emit
+//    it: 0/1 for the set semantics of fields '0'..'2', the number of matching R rows for '3'.
+//  * intersect_sorted replaces MergeJoin's two-pointer walk over the two deduplicated files
+//    (DatabaseProject.cpp:414-482) and reproduces the number of block reads that walk performs.
+#include "dbt_internal.cuh"
+
+namespace dbt {
+
+constexpr uint32_t kEmptyKey = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t hash_u32(uint32_t k) {
+    k ^= k >> 16;
+    k *= 0x7FEB352Du;
+    k ^= k >> 15;
+    k *= 0x846CA68Bu;
+    k ^= k >> 16;
+    return k;
+}
+
+struct KeyView { // device view of KeyCols
+    const uint32_t *w0;
+    const uint32_t *str;
+    uint32_t kw;
+};
+__device__ __forceinline__ uint32_t hash_row(const KeyView &k, uint32_t row) {
+    uint32_t h = k.w0 ? hash_u32(k.w0[row]) : 0x9E3779B9u;
+    if (k.str) {
+        const uint32_t *p = k.str + (uint64_t)row * k.kw;
+        for (uint32_t j = 0; j < k.kw; ++j) h = hash_u32(h ^ p[j]) + j;
+    }
+    return h;
+}
+__device__ __forceinline__ bool rows_equal(const KeyView &a, uint32_t ra, const KeyView &b, uint32_t rb) {
+    if (a.w0 && a.w0[ra] != b.w0[rb]) return false;
+    if (a.str) {
+        const uint32_t *pa = a.str + (uint64_t)ra * a.kw, *pb = b.str + (uint64_t)rb * b.kw;
+        for (uint32_t j = 0; j < a.kw; ++j)
+            if (pa[j] != pb[j]) return false;
+    }
+    return true;
+}
+// three-way compare of row ra of a against row rb of b (both key sets have the same shape)
+__device__ __forceinline__ int rows_cmp(const KeyView &a, uint32_t ra, const KeyView &b, uint32_t rb) {
+    if (a.w0) {
+        uint32_t x = a.w0[ra], y = b.w0[rb];
+        if (x != y) return x < y ? -1 : 1;
+    }
+    if (a.str) {
+        const uint32_t *pa = a.str + (uint64_t)ra * a.kw, *pb = b.str + (uint64_t)rb * b.kw;
+        for (uint32_t j = 0; j < a.kw; ++j)
+            if (pa[j] != pb[j]) return pa[j] < pb[j] ? -1 : 1;
+    }
+    return 0;
+}
+
+// ---- u32 keys: the table stores the keys themselves ---------------------------------------
+__global__ void __launch_bounds__(256)
+build_u32_kernel(const uint32_t *__restrict__ keys, uint64_t n, uint32_t *table, uint32_t mask, uint32_t *has_max) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t k = keys[i];
+        if (k == kEmptyKey) { // the sentinel value itself: remembered on the side
+            *has_max = 1;
+            continue;
+        }
+        uint32_t h = hash_u32(k) & mask;
+        while (true) {
+            uint32_t cur = table[h];
+            if (cur == k) break;
+            if (cur == kEmptyKey) {
+                uint32_t old = atomicCAS(&table[h], kEmptyKey, k);
+                if (old == kEmptyKey || old == k) break;
+            }
+            h = (h + 1) & mask;
+        }
+    }
+}
+__global__ void __launch_bounds__(256)
+probe_u32_kernel(const uint32_t *__restrict__ keys, uint64_t n, const uint32_t *__restrict__ table, uint32_t mask,
+                 const uint32_t *__restrict__ has_max, uint32_t *__restrict__ counts) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t hm = *has_max;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t k = keys[i];
+        uint32_t found = 0;
+        if (k == kEmptyKey) {
+            found = hm;
+        } else {
+            uint32_t h = hash_u32(k) & mask;
+            while (true) {
+                uint32_t cur = table[h];
+                if (cur == k) {
+                    found = 1;
+                    break;
+                }
+                if (cur == kEmptyKey) break;
+                h = (h + 1) & mask;
+            }
+        }
+        counts[i] = found;
+    }
+}
+
+// ---- multi-word keys: the table stores (R row + 1); equality goes through the key columns ---
+template <bool MULTI>
+__global__ void __launch_bounds__(256)
+build_rows_kernel(KeyView r, uint64_t n, uint32_t *table, uint32_t *mult, uint32_t mask) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t row = (uint32_t)i;
+        uint32_t h = hash_row(r, row) & mask;
+        while (true) {
+            uint32_t cur = table[h];
+            if (cur == 0) {
+                cur = atomicCAS(&table[h], 0u, row + 1);
+                if (cur == 0) cur = row + 1;
+            }
+            if (cur == row + 1 || rows_equal(r, cur - 1, r, row)) {
+                if (MULTI) atomicAdd(&mult[h], 1u);
+                break;
+            }
+            h = (h + 1) & mask;
+        }
+    }
+}
+template <bool MULTI>
+__global__ void __launch_bounds__(256)
+probe_rows_kernel(KeyView r, KeyView s, uint64_t n, const uint32_t *__restrict__ table,
+                  const uint32_t *__restrict__ mult, uint32_t mask, uint32_t *__restrict__ counts) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t row = (uint32_t)i;
+        uint32_t h = hash_row(s, row) & mask;
+        uint32_t c = 0;
+        while (true) {
+            uint32_t cur = table[h];
+            if (cur == 0) break;
+            if (rows_equal(r, cur - 1, s, row)) {
+                c = MULTI ? mult[h] : 1u;
+                break;
+            }
+            h = (h + 1) & mask;
+        }
+        counts[i] = c;
+    }
+}
+
+size_t hash_table_slots(uint64_t nr) {
+    uint64_t want = nr * 2 + 64, cap = 1024;
+    while (cap < want) cap <<= 1;
+    return cap;
+}
+
+int hash_join_counts(const KeyCols &r, const KeyCols &s, int field, uint32_t *d_counts, Arena &ws, cudaStream_t st) {
+    if (s.n == 0) return 0;
+    size_t slots = hash_table_slots(r.n);
+    if (slots > (1ull << 32)) {
+        set_error("hash table too large");
+        return DBT_ERR_UNSUPPORTED;
+    }
+    uint32_t mask = (uint32_t)(slots - 1);
+    uint32_t *table = ws.take<uint32_t>(slots);
+    uint32_t *aux = ws.take<uint32_t>(64);
+    if (!table || !aux) {
+        set_error("hash join: workspace too small");
+        return DBT_ERR_WORKSPACE;
+    }
+    int gb = (int)std::min<uint64_t>((r.n + 255) / 256 + 1, 148 * 16);
+    int gp = (int)std::min<uint64_t>((s.n + 255) / 256 + 1, 148 * 16);
+    if (field == '0' || field == '1') {
+        {
+            StageScope sc(ST_HASH_BUILD, st);
+            DBT_CUDA(cudaMemsetAsync(table, 0xFF, slots * 4, st));
+            DBT_CUDA(cudaMemsetAsync(aux, 0, 4, st));
+            if (r.n) {
+                build_u32_kernel<<<gb, 256, 0, st>>>(r.w0, r.n, table, mask, aux);
+                count_launch();
+            }
+            DBT_KERNEL_CHECK();
+        }
+        StageScope sc(ST_HASH_PROBE, st);
+        probe_u32_kernel<<<gp, 256, 0, st>>>(s.w0, s.n, table, mask, aux, d_counts);
+        count_launch();
+        DBT_KERNEL_CHECK();
+        return 0;
+    }
+    KeyView rv{field == '2' ? nullptr : r.w0, r.str, r.kw};
+    KeyView sv{field == '2' ? nullptr : s.w0, s.str, s.kw};
+    const bool multi = (field == '3');
+    uint32_t *mult = nullptr;
+    if (multi) {
+        mult = ws.take<uint32_t>(slots);
+        if (!mult) {
+            set_error("hash join: workspace too small");
+            return DBT_ERR_WORKSPACE;
+        }
+    }
+    {
+        StageScope sc(ST_HASH_BUILD, st);
+        DBT_CUDA(cudaMemsetAsync(table, 0, slots * 4, st));
+        if (multi) DBT_CUDA(cudaMemsetAsync(mult, 0, slots * 4, st));
+        if (r.n) {
+            if (multi) build_rows_kernel<true><<<gb, 256, 0, st>>>(rv, r.n, table, mult, mask);
+            else build_rows_kernel<false><<<gb, 256, 0, st>>>(rv, r.n, table, mult, mask);
+            count_launch();
+        }
+        DBT_KERNEL_CHECK();
+    }
+    StageScope sc(ST_HASH_PROBE, st);
+    if (multi) probe_rows_kernel<true><<<gp, 256, 0, st>>>(rv, sv, s.n, table, mult, mask, d_counts);
+    else probe_rows_kernel<false><<<gp, 256, 0, st>>>(rv, sv, s.n, table, mult, mask, d_counts);
+    count_launch();
+    DBT_KERNEL_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Intersection of two sorted unique lists.
+// ---------------------------------------------------------------------------------------------
+struct SortedList { // i-th smallest key of a relation: either a sorted u32 column or rows + key columns
+    const uint32_t *keys; // sorted unique u32 keys (1-word keys) or nullptr
+    const uint32_t *rows; // sorted unique row ids
+    KeyView kv;
+    uint64_t n;
+};
+__device__ __forceinline__ int list_cmp(const SortedList &a, uint64_t i, const SortedList &b, uint64_t j) {
+    if (a.keys) {
+        uint32_t x = a.keys[i], y = b.keys[j];
+        return x < y ? -1 : (x > y ? 1 : 0);
+    }
+    return rows_cmp(a.kv, a.rows[i], b.kv, b.rows[j]);
+}
+// first j in [0, b.n) with b[j] >= a[i]
+__device__ __forceinline__ uint64_t lower_bound(const SortedList &a, uint64_t i, const SortedList &b) {
+    uint64_t lo = 0, hi = b.n;
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (list_cmp(b, mid, a, i) < 0) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) intersect_kernel(SortedList a, SortedList b, uint32_t *__restrict__ flags) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+        uint64_t j = lower_bound(a, i, b);
+        flags[i] = (j < b.n && list_cmp(a, i, b, j) == 0) ? 1u : 0u;
+    }
+}
+
+// Number of block reads after the first two that the reference's two-pointer walk performs
+// (DatabaseProject.cpp:414-482): the walk stops at the first exhausted list; R is tested before S.
+// Closed form derived in DESIGN.md ("MergeJoin nios").
+__global__ void walk_reads_kernel(SortedList r, SortedList s, unsigned long long *out) {
+    if (threadIdx.x || blockIdx.x) return;
+    uint64_t nr = r.n, ns = s.n, reads = 0;
+    if (nr && ns) {
+        int c = list_cmp(r, nr - 1, s, ns - 1);
+        uint64_t a, b;
+        bool inc_b;
+        if (c <= 0) { // R runs out first (or both together): the empty R read ends the walk
+            a = nr;
+            uint64_t lb = lower_bound(r, nr - 1, s);
+            bool match = lb < ns && list_cmp(r, nr - 1, s, lb) == 0;
+            b = lb + (match ? 1 : 0);
+            inc_b = match;
+            uint64_t ymax = b - (inc_b ? 1 : 0);
+            reads = (nr + kRpb - 1) / kRpb + ymax / kRpb;
+        } else { // S runs out first
+            b = ns;
+            uint64_t lb = lower_bound(s, ns - 1, r);
+            bool match = lb < nr && list_cmp(s, ns - 1, r, lb) == 0;
+            a = lb + (match ? 1 : 0);
+            reads = a / kRpb + (ns + kRpb - 1) / kRpb;
+        }
+    }
+    *out = reads;
+}
+
+int intersect_sorted(const KeyCols &r, const uint32_t *d_ur, const uint32_t *d_urkeys, uint64_t nur, const KeyCols &s,
+                     const uint32_t *d_us, const uint32_t *d_uskeys, uint64_t nus, int field, uint32_t *d_flags,
+                     uint64_t *d_later_reads, cudaStream_t st) {
+    StageScope sc(ST_INTERSECT, st);
+    const bool one = (field == '0' || field == '1');
+    SortedList a{one ? d_urkeys : nullptr, d_ur, KeyView{field == '2' ? nullptr : r.w0, r.str, r.kw}, nur};
+    SortedList b{one ? d_uskeys : nullptr, d_us, KeyView{field == '2' ? nullptr : s.w0, s.str, s.kw}, nus};
+    if (nur) {
+        int grid = (int)std::min<uint64_t>((nur + 255) / 256, 148 * 16);
+        intersect_kernel<<<grid, 256, 0, st>>>(a, b, d_flags);
+        count_launch();
+    }
+    walk_reads_kernel<<<1, 1, 0, st>>>(a, b, (unsigned long long *)d_later_reads);
+    count_launch();
+    DBT_KERNEL_CHECK();
+    return 0;
+}
+
+} // namespace dbt

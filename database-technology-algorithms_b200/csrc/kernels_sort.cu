@@ -1,0 +1,473 @@
+// kernels_sort.cu -- LSD "onesweep" radix sort of (u32 key, u32 row) pairs, hand-written for sm_100a.
+//
+// Replaces the reference's run generation (qsort of 140-byte records, DatabaseProject.cpp:207-214)
+// and its priority_queue k-way merge (DatabaseProject.cpp:245-369): the sort happens on 8-byte
+// (key, row) pairs, records move once at the end (kernels_gather.cu).
+//
+// One pass = one kernel: every CTA takes a tile (dynamic tile id), ranks its keys on an 8-bit digit
+// with warp match-any, publishes its per-digit counts in a decoupled look-back chain, stages the
+// tile sorted-by-digit in shared memory and writes digit runs coalesced.  Per pass the DRAM
+// traffic is 8 B read + 8 B written per pair (keys+rows) -- the kernel is HBM-bound.
+#include "dbt_internal.cuh"
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace dbt {
+
+constexpr int kRadix = 256;
+constexpr uint32_t kFlagAgg = 0x40000000u; // tile aggregate available
+constexpr uint32_t kFlagInc = 0x80000000u; // inclusive prefix available
+constexpr uint32_t kValMask = 0x3FFFFFFFu;
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+__device__ __forceinline__ uint32_t ld_volatile(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_volatile(uint32_t *p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v));
+}
+
+// ---------------------------------------------------------------------------------------------
+// OR / AND reduction of a word column: the bits where OR and AND differ are the only bits a sort
+// has to look at (constant bits cannot change the order).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) or_and_kernel(const uint32_t *__restrict__ w, uint64_t n, uint32_t *out) {
+    uint32_t o = 0, a = 0xFFFFFFFFu;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t v = w[i];
+        o |= v;
+        a &= v;
+    }
+    o = __reduce_or_sync(0xFFFFFFFFu, o);
+    a = __reduce_and_sync(0xFFFFFFFFu, a);
+    if ((threadIdx.x & 31) == 0) {
+        atomicOr(&out[0], o);
+        atomicAnd(&out[1], a);
+    }
+}
+__global__ void init_or_and_kernel(uint32_t *out) {
+    out[0] = 0;
+    out[1] = 0xFFFFFFFFu;
+}
+int or_and_reduce(const uint32_t *d_words, uint64_t n, uint32_t *d_or_and, cudaStream_t st) {
+    init_or_and_kernel<<<1, 1, 0, st>>>(d_or_and);
+    count_launch();
+    if (n) {
+        int grid = (int)std::min<uint64_t>((n + 255) / 256, 148 * 8);
+        or_and_kernel<<<grid, 256, 0, st>>>(d_words, n, d_or_and);
+        count_launch();
+    }
+    DBT_KERNEL_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Histogram of up to 4 digit positions in one read of the keys, then per-digit exclusive scan.
+// ---------------------------------------------------------------------------------------------
+struct DigitPlan {
+    int npass;
+    int shift[4];
+};
+
+__global__ void __launch_bounds__(512) hist_kernel(const uint32_t *__restrict__ keys, uint64_t n, DigitPlan plan,
+                                                   uint32_t *__restrict__ ghist /*[4][256]*/) {
+    __shared__ uint32_t sh[4][kRadix];
+    for (int i = threadIdx.x; i < 4 * kRadix; i += blockDim.x) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    uint64_t nvec = n / 4;
+    const uint4 *kv = reinterpret_cast<const uint4 *>(keys);
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        uint4 v = kv[i];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            if (p < plan.npass) {
+                int s = plan.shift[p];
+                atomicAdd(&sh[p][(v.x >> s) & 0xFF], 1u);
+                atomicAdd(&sh[p][(v.y >> s) & 0xFF], 1u);
+                atomicAdd(&sh[p][(v.z >> s) & 0xFF], 1u);
+                atomicAdd(&sh[p][(v.w >> s) & 0xFF], 1u);
+            }
+        }
+    }
+    // tail (n % 4) by the first threads of block 0
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        uint32_t k = keys[nvec * 4 + threadIdx.x];
+        for (int p = 0; p < plan.npass; ++p) atomicAdd(&sh[p][(k >> plan.shift[p]) & 0xFF], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < plan.npass * kRadix; i += blockDim.x) {
+        uint32_t c = (&sh[0][0])[i];
+        if (c) atomicAdd(&ghist[i], c);
+    }
+}
+
+// in-place exclusive scan of each 256-bin histogram (one CTA per digit position)
+__global__ void __launch_bounds__(kRadix) hist_scan_kernel(uint32_t *ghist) {
+    __shared__ uint32_t wsum[8];
+    uint32_t *h = ghist + blockIdx.x * kRadix;
+    uint32_t v = h[threadIdx.x], x = v;
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= o) x += t;
+    }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    uint32_t pre = 0;
+    for (int w = 0; w < warp; ++w) pre += wsum[w];
+    h[threadIdx.x] = pre + x - v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The onesweep pass.
+// ---------------------------------------------------------------------------------------------
+template <int THREADS, int ITEMS>
+struct OnesweepSmem {
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int TILE = THREADS * ITEMS;
+    uint32_t hist[WARPS][kRadix]; // per-warp digit counters, later exclusive-over-warps offsets
+    uint32_t excl[kRadix];        // tile-local exclusive digit offsets
+    uint32_t goff[kRadix];        // global offset of the digit run minus excl[d]
+    uint32_t wsum[8];
+    uint32_t tile;
+    uint32_t keys[TILE];
+    uint32_t vals[TILE];
+};
+
+template <int THREADS, int ITEMS, bool HAS_VALS, bool IOTA_VALS>
+__global__ void __launch_bounds__(THREADS)
+onesweep_kernel(const uint32_t *__restrict__ kin, uint32_t *__restrict__ kout, const uint32_t *__restrict__ vin,
+                uint32_t *__restrict__ vout, uint32_t n, int shift, const uint32_t *__restrict__ digit_base,
+                uint32_t *state /*[ntiles][256], zeroed*/, uint32_t *tile_ctr /*zeroed*/) {
+    using Smem = OnesweepSmem<THREADS, ITEMS>;
+    constexpr int WARPS = Smem::WARPS;
+    constexpr int TILE = Smem::TILE;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sm.tile = atomicAdd(tile_ctr, 1u); // dynamic tile id => every predecessor tile is resident or done
+    for (int i = tid; i < WARPS * kRadix; i += THREADS) (&sm.hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = sm.tile;
+    const uint32_t base = tile * (uint32_t)TILE;
+    const bool full = base + (uint32_t)TILE <= n;
+    const uint32_t idx0 = base + warp * (ITEMS * 32) + lane; // warp-striped arrangement
+
+    uint32_t key[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        uint32_t idx = idx0 + j * 32;
+        key[j] = (full || idx < n) ? kin[idx] : 0xFFFFFFFFu;
+    }
+
+    // ---- rank inside the warp: match-any gives the lanes with my digit; the group leader bumps the
+    // warp's counter once for the whole group (no shared-memory atomics)
+    uint32_t rank[ITEMS];
+    const uint32_t lt = lanemask_lt();
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const bool valid = full || (idx0 + j * 32 < n);
+        const uint32_t d = (key[j] >> shift) & 0xFFu;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, valid ? d : 0x100u);
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (lane == leader && valid) {
+            old = sm.hist[warp][d];
+            sm.hist[warp][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xFFFFFFFFu, old, leader);
+        rank[j] = old + __popc(peers & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per digit: exclusive over warps, tile count, publish the aggregate at once
+    uint32_t count_d = 0, incl = 0;
+    if (tid < kRadix) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            uint32_t t = sm.hist[w][tid];
+            sm.hist[w][tid] = acc;
+            acc += t;
+        }
+        count_d = acc;
+        st_volatile(&state[(size_t)tile * kRadix + tid], (tile == 0 ? kFlagInc : kFlagAgg) | count_d);
+        // exclusive scan of the 256 counts (8 warps)
+        incl = count_d;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) sm.wsum[warp] = incl;
+    }
+    __syncthreads();
+    if (tid < kRadix) {
+        uint32_t pre = 0;
+        for (int w = 0; w < warp; ++w) pre += sm.wsum[w];
+        sm.excl[tid] = pre + incl - count_d;
+    }
+    __syncthreads();
+
+    // ---- stage the tile in shared memory ordered by digit (look-back latency hides behind this)
+    uint32_t pos[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const uint32_t d = (key[j] >> shift) & 0xFFu;
+        pos[j] = sm.excl[d] + sm.hist[warp][d] + rank[j];
+        if (full || (idx0 + j * 32 < n)) sm.keys[pos[j]] = key[j];
+    }
+    if (HAS_VALS) {
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            uint32_t idx = idx0 + j * 32;
+            if (full || idx < n) sm.vals[pos[j]] = IOTA_VALS ? idx : vin[idx];
+        }
+    }
+
+    // ---- decoupled look-back, one thread per digit
+    if (tid < kRadix) {
+        uint32_t excl_prefix = 0;
+        if (tile > 0) {
+            int p = (int)tile - 1;
+            while (true) {
+                uint32_t s;
+                do {
+                    s = ld_volatile(&state[(size_t)p * kRadix + tid]);
+                } while ((s & (kFlagAgg | kFlagInc)) == 0);
+                excl_prefix += s & kValMask;
+                if (s & kFlagInc) break;
+                --p;
+            }
+            st_volatile(&state[(size_t)tile * kRadix + tid], kFlagInc | (excl_prefix + count_d));
+        }
+        sm.goff[tid] = digit_base[tid] + excl_prefix - sm.excl[tid];
+    }
+    __syncthreads();
+
+    // ---- coalesced writes of the digit runs
+    const uint32_t nvalid = full ? (uint32_t)TILE : n - base;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        uint32_t i = tid + j * THREADS;
+        if (i < nvalid) {
+            uint32_t k = sm.keys[i];
+            uint32_t dst = sm.goff[(k >> shift) & 0xFFu] + i;
+            kout[dst] = k;
+            if (HAS_VALS) vout[dst] = sm.vals[i];
+        }
+    }
+}
+
+// ---- launch plumbing ----------------------------------------------------------------------
+struct OnesweepCfg {
+    int threads, items;
+};
+static OnesweepCfg current_cfg() {
+    static OnesweepCfg cfg = [] {
+        OnesweepCfg c{256, 16};
+        if (const char *e = getenv("DBT_ONESWEEP_CFG")) { // tuning hook: "<threads>x<items>"
+            int t = 0, i = 0;
+            if (sscanf(e, "%dx%d", &t, &i) == 2) c = OnesweepCfg{t, i};
+        }
+        return c;
+    }();
+    return cfg;
+}
+
+template <int THREADS, int ITEMS>
+static int launch_onesweep_t(const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, uint32_t n,
+                             int shift, const uint32_t *digit_base, uint32_t *state, uint32_t *ctr, bool has_vals,
+                             bool iota, cudaStream_t st) {
+    using Smem = OnesweepSmem<THREADS, ITEMS>;
+    size_t smem = sizeof(Smem);
+    uint32_t ntiles = (n + Smem::TILE - 1) / Smem::TILE;
+#define DBT_LAUNCH_OS(HV, IO)                                                                                     \
+    do {                                                                                                          \
+        auto kfn = onesweep_kernel<THREADS, ITEMS, HV, IO>;                                                       \
+        static bool attr_done = false;                                                                            \
+        if (!attr_done) {                                                                                         \
+            DBT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+            attr_done = true;                                                                                     \
+        }                                                                                                         \
+        kfn<<<ntiles, THREADS, smem, st>>>(kin, kout, vin, vout, n, shift, digit_base, state, ctr);               \
+    } while (0)
+    if (!has_vals) DBT_LAUNCH_OS(false, false);
+    else if (iota) DBT_LAUNCH_OS(true, true);
+    else DBT_LAUNCH_OS(true, false);
+#undef DBT_LAUNCH_OS
+    count_launch();
+    DBT_KERNEL_CHECK();
+    return 0;
+}
+
+static int tile_items() {
+    OnesweepCfg c = current_cfg();
+    return c.threads * c.items;
+}
+
+static int launch_onesweep(const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, uint32_t n,
+                           int shift, const uint32_t *digit_base, uint32_t *state, uint32_t *ctr, bool has_vals,
+                           bool iota, cudaStream_t st) {
+    OnesweepCfg c = current_cfg();
+#define DBT_CFG(T, I)                \
+    if (c.threads == T && c.items == I) \
+        return launch_onesweep_t<T, I>(kin, kout, vin, vout, n, shift, digit_base, state, ctr, has_vals, iota, st);
+    DBT_CFG(256, 16)
+    DBT_CFG(256, 12)
+    DBT_CFG(256, 20)
+    DBT_CFG(384, 12)
+    DBT_CFG(384, 16)
+    DBT_CFG(512, 8)
+    DBT_CFG(512, 12)
+    DBT_CFG(512, 16)
+#undef DBT_CFG
+    set_error("unsupported DBT_ONESWEEP_CFG");
+    return DBT_ERR_ARG;
+}
+
+size_t sort_ws_bytes(uint64_t n) {
+    uint64_t ntiles = (n + 2048 - 1) / 2048 + 1; // bound for the smallest tile any config uses (256x12 = 3072)
+    return pad256(ntiles * kRadix * 4) + pad256(4 * kRadix * 4) + 4 * 256 + 4096;
+}
+
+static DigitPlan plan_digits(uint32_t varying) {
+    DigitPlan p{};
+    uint32_t m = varying;
+    while (m) {
+        int s = __builtin_ctz(m);
+        p.shift[p.npass++] = s;
+        uint64_t window = ((uint64_t)0xFF) << s;
+        m &= ~(uint32_t)window;
+    }
+    return p;
+}
+
+// Sort pairs over the varying bits only.  keys/vals: ping buffers (input), *_alt: pong buffers.
+// iota_vals: the input values are implicitly the element indices (content of `vals` ignored; the
+// first pass synthesises them, saving one read and one write of the row column).
+// On return keys/vals point at the buffers holding the result (swapped as needed).
+int sort_pairs_masked(uint32_t *&keys, uint32_t *&keys_alt, uint32_t *&vals, uint32_t *&vals_alt, uint64_t n,
+                      uint32_t varying_mask, bool iota_vals, Arena &ws, cudaStream_t st) {
+    if (n >= (1ull << 30)) {
+        set_error("sort_pairs: n must be < 2^30 per call");
+        return DBT_ERR_UNSUPPORTED;
+    }
+    DigitPlan plan = plan_digits(varying_mask);
+    if (n == 0 || plan.npass == 0) {
+        if (iota_vals && n) DBT_TRY(iota_u32(vals, n, st)); // nothing to sort but the caller expects a row list
+        return 0;
+    }
+    size_t m0 = ws.mark();
+    uint32_t ntiles = (uint32_t)((n + tile_items() - 1) / tile_items());
+    uint32_t *ghist = ws.take<uint32_t>(4 * kRadix);
+    uint32_t *ctr = ws.take<uint32_t>(64);
+    uint32_t *state = ws.take<uint32_t>((size_t)ntiles * kRadix);
+    if (!ghist || !ctr || !state) {
+        set_error("sort_pairs: workspace too small");
+        return DBT_ERR_WORKSPACE;
+    }
+    {
+        StageScope sc(ST_HIST, st);
+        DBT_CUDA(cudaMemsetAsync(ghist, 0, 4 * kRadix * 4, st));
+        int grid = (int)std::min<uint64_t>((n / 4 + 511) / 512 + 1, 148 * 4);
+        hist_kernel<<<grid, 512, 0, st>>>(keys, n, plan, ghist);
+        hist_scan_kernel<<<plan.npass, kRadix, 0, st>>>(ghist);
+        count_launch(2);
+        DBT_KERNEL_CHECK();
+    }
+    for (int p = 0; p < plan.npass; ++p) {
+        StageScope sc(ST_ONESWEEP, st);
+        DBT_CUDA(cudaMemsetAsync(state, 0, (size_t)ntiles * kRadix * 4, st));
+        DBT_CUDA(cudaMemsetAsync(ctr, 0, 4, st));
+        DBT_TRY(launch_onesweep(keys, keys_alt, vals, vals_alt, (uint32_t)n, plan.shift[p], ghist + p * kRadix, state,
+                                ctr, true, iota_vals && p == 0, st));
+        std::swap(keys, keys_alt);
+        std::swap(vals, vals_alt);
+    }
+    ws.release(m0);
+    return 0;
+}
+
+__global__ void iota_kernel(uint32_t *d, uint64_t n) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) d[i] = (uint32_t)i;
+}
+int iota_u32(uint32_t *d, uint64_t n, cudaStream_t st) {
+    if (!n) return 0;
+    int grid = (int)std::min<uint64_t>((n + 255) / 256, 148 * 16);
+    iota_kernel<<<grid, 256, 0, st>>>(d, n);
+    count_launch();
+    DBT_KERNEL_CHECK();
+    return 0;
+}
+
+// curkey[i] = src[perm[i] * stride + word]  (perm == nullptr => identity)
+__global__ void __launch_bounds__(256)
+gather_word_kernel(const uint32_t *__restrict__ src, uint32_t stride, uint32_t word, const uint32_t *__restrict__ perm,
+                   uint32_t *__restrict__ out, uint64_t n) {
+    uint64_t gstride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gstride) {
+        uint64_t r = perm ? perm[i] : i;
+        out[i] = src[r * stride + word];
+    }
+}
+int gather_word(const uint32_t *d_src, uint32_t stride, uint32_t word, const uint32_t *d_perm, uint32_t *d_out,
+                uint64_t n, cudaStream_t st) {
+    if (!n) return 0;
+    int grid = (int)std::min<uint64_t>((n + 255) / 256, 148 * 16);
+    gather_word_kernel<<<grid, 256, 0, st>>>(d_src, stride, word, d_perm, d_out, n);
+    count_launch();
+    DBT_KERNEL_CHECK();
+    return 0;
+}
+
+} // namespace dbt
+
+using namespace dbt;
+
+extern "C" size_t dbt_sort_pairs_ws_bytes(uint64_t n) { return sort_ws_bytes(n) + 256; }
+
+extern "C" int dbt_sort_pairs_u32(uint32_t *d_keys, uint32_t *d_keys_alt, uint32_t *d_vals, uint32_t *d_vals_alt,
+                                  uint64_t n, int begin_bit, int end_bit, void *d_ws, size_t ws_bytes, void *stream,
+                                  int *result_in_alt) {
+    if (!d_keys || !d_keys_alt || !d_vals || !d_vals_alt || begin_bit < 0 || end_bit > 32 || begin_bit > end_bit) {
+        set_error("dbt_sort_pairs_u32: bad arguments");
+        return DBT_ERR_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    Arena ws(d_ws, ws_bytes);
+    uint32_t *oa = ws.take<uint32_t>(64);
+    if (!oa) {
+        set_error("dbt_sort_pairs_u32: workspace too small");
+        return DBT_ERR_WORKSPACE;
+    }
+    uint32_t h[2] = {0, 0};
+    if (n) {
+        StageScope sc(ST_MISC, st);
+        DBT_TRY(or_and_reduce(d_keys, n, oa, st));
+        DBT_CUDA(cudaMemcpyAsync(h, oa, 8, cudaMemcpyDeviceToHost, st));
+        DBT_CUDA(cudaStreamSynchronize(st));
+    }
+    uint32_t range = (end_bit - begin_bit >= 32) ? 0xFFFFFFFFu
+                                                 : (uint32_t)((((uint64_t)1 << (end_bit - begin_bit)) - 1) << begin_bit);
+    uint32_t varying = (h[0] ^ h[1]) & range;
+    uint32_t *k = d_keys, *ka = d_keys_alt, *v = d_vals, *va = d_vals_alt;
+    DBT_TRY(sort_pairs_masked(k, ka, v, va, n, varying, false, ws, st));
+    DBT_CUDA(cudaStreamSynchronize(st));
+    stage_resolve();
+    if (result_in_alt) *result_in_alt = (k == d_keys_alt) ? 1 : 0;
+    return 0;
+}

@@ -1,0 +1,160 @@
+// runtime.cu -- error plumbing, stage timing, launch accounting, counter formulae.
+#include "dbt_internal.cuh"
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace dbt {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d in `%s`", (int)e, cudaGetErrorString(e), file, line, what);
+    g_err = buf;
+    return DBT_ERR_CUDA;
+}
+
+// ---- stage timing ---------------------------------------------------------------------------
+static const char *kStageNames[ST_COUNT] = {"headers",   "extract_keys", "histogram", "onesweep_pass", "word_gather",
+                                            "unique",    "record_gather", "hash_build", "hash_probe",   "compact",
+                                            "intersect", "misc",         "h2d",        "d2h"};
+static bool g_timing = false;
+static double g_ms[ST_COUNT];
+static uint64_t g_launches[ST_COUNT];
+static uint64_t g_total_launches = 0;
+struct Pending {
+    int stage;
+    cudaEvent_t a, b;
+};
+static std::vector<Pending> g_pending;
+static std::vector<cudaEvent_t> g_pool;
+static std::mutex g_mu;
+static thread_local int g_cur_stage = ST_MISC;
+
+static cudaEvent_t get_event() {
+    if (!g_pool.empty()) {
+        cudaEvent_t e = g_pool.back();
+        g_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void count_launch(int n) {
+    g_total_launches += n;
+    g_launches[g_cur_stage] += n;
+}
+
+StageScope::StageScope(int stage_, cudaStream_t s) : stage(stage_), stream(s), slot(-1) {
+    g_cur_stage = stage_;
+    if (!g_timing) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    Pending p;
+    p.stage = stage_;
+    p.a = get_event();
+    p.b = get_event();
+    cudaEventRecord(p.a, s);
+    g_pending.push_back(p);
+    slot = (int)g_pending.size() - 1;
+}
+StageScope::~StageScope() {
+    g_cur_stage = ST_MISC;
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    cudaEventRecord(g_pending[slot].b, stream);
+}
+void stage_resolve() {
+    if (!g_timing) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto &p : g_pending) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess)
+            g_ms[p.stage] += ms;
+        g_pool.push_back(p.a);
+        g_pool.push_back(p.b);
+    }
+    g_pending.clear();
+}
+
+} // namespace dbt
+
+using namespace dbt;
+
+extern "C" {
+
+const char *dbt_last_error(void) { return g_err.c_str(); }
+int dbt_abi_version(void) { return 1; }
+int dbt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void dbt_stage_timing_enable(int on) { g_timing = on != 0; }
+void dbt_stage_timing_reset(void) {
+    stage_resolve();
+    memset(g_ms, 0, sizeof g_ms);
+    memset(g_launches, 0, sizeof g_launches);
+}
+int dbt_stage_count(void) { return ST_COUNT; }
+const char *dbt_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : ""; }
+double dbt_stage_ms(int i) {
+    stage_resolve();
+    return (i >= 0 && i < ST_COUNT) ? g_ms[i] : 0.0;
+}
+uint64_t dbt_stage_launches(int i) { return (i >= 0 && i < ST_COUNT) ? g_launches[i] : 0; }
+uint64_t dbt_kernel_launches(void) { return g_total_launches; }
+
+// ---- counters (reference DatabaseProject.cpp:191-233,245-376) ---------
+int dbt_sort_counters(uint64_t B, uint32_t M, uint64_t *segs, uint64_t *passes, uint64_t *nios) {
+    if (M <= 2) {
+        set_error("nmem_blocks must be > 2");
+        return DBT_ERR_ARG;
+    }
+    uint64_t F = M - 1;
+    uint64_t R = (B + M - 1) / M; // runs produced by pass 0, each written as exactly M blocks
+    uint64_t f = R, total = R, phases = 0;
+    do { // the merge loop always runs at least one phase, and stops when a phase produces one file
+        f = (f + F - 1) / F;
+        total += f;
+        ++phases;
+    } while (f > 1);
+    if (segs) *segs = total;
+    if (passes) *passes = 1 + phases;
+    if (nios) *nios = R * M + phases * B; // block writes only
+    return 0;
+}
+uint64_t dbt_dedup_nios(uint64_t B, uint32_t M, uint64_t nunique) {
+    uint64_t io = 0;
+    if (dbt_sort_counters(B, M, nullptr, nullptr, &io)) return 0;
+    return io + (nunique + kRpb - 1) / kRpb;
+}
+uint64_t dbt_hashjoin_nios(uint64_t BR, uint64_t BS, uint32_t M, uint64_t nres) {
+    if (M < 2) return 0;
+    uint64_t F = M - 1;
+    // one count per bulk read of F blocks plus the final short/empty read of each input, plus output blocks
+    return (BR / F + 1) + (BS / F + 1) + (nres + kRpb - 1) / kRpb;
+}
+
+uint64_t dbt_mergejoin_nios(uint64_t BR, uint64_t BS, uint32_t M, const uint64_t *res) {
+    // both dedups + the 2 first block reads + later reads of the two-pointer walk + output blocks
+    // (reference: DatabaseProject.cpp:395,405,441,465,475,491)
+    return dbt_dedup_nios(BR, M, res[1]) + dbt_dedup_nios(BS, M, res[2]) + 2 + res[3] + (res[0] + kRpb - 1) / kRpb;
+}
+
+int dbt_host_alloc(void **p, size_t bytes) {
+    DBT_CUDA(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault));
+    return 0;
+}
+int dbt_host_free(void *p) {
+    DBT_CUDA(cudaFreeHost(p));
+    return 0;
+}
+}

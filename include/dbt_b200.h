@@ -1,0 +1,162 @@
+/*
+ * dbt_b200.h -- the thin extern "C" layer of the B200-native tuple operators.
+ *
+ * This is the drop-in boundary beneath the four dbtproj.h entry points (include/dbtproj.h):
+ * plain pointers and sizes, int status, no C++ or torch types, no exceptions, and no hidden
+ * device allocation on the device-scope path (the caller owns every buffer, including the
+ * workspace).  Each group cites the part of the reference it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative dbt_status on failure;
+ *     dbt_last_error() gives a human-readable message for the calling thread;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream);
+ *   - "image" = a block file in memory: a flat array of 14016-byte block_t (dbtproj.h);
+ *   - `field` is the ASCII selector '0'..'3' of the reference (DatabaseProject.cpp:23-40);
+ *   - device-scope operators (dbt_dev_*) take device pointers, enqueue on `stream` and
+ *     synchronise that stream before returning (they hand row counts back to the host);
+ *   - host-scope operators (dbt_host_*) take host pointers and do the host<->device copies
+ *     themselves (pinned staging when the caller's memory is pageable);
+ *   - there is NO CPU fallback anywhere: without a CUDA device every entry fails with
+ *     DBT_ERR_CUDA.
+ */
+#ifndef DBT_B200_H
+#define DBT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBT_BLOCK_BYTES 14016u
+#define DBT_RECORD_BYTES 140u
+#define DBT_RECORDS_PER_BLOCK 100u
+
+typedef enum dbt_status {
+    DBT_OK = 0,
+    DBT_ERR_ARG = -1,       /* bad argument (field, sizes, NULL pointers) */
+    DBT_ERR_CUDA = -2,      /* CUDA runtime error, incl. "no device" */
+    DBT_ERR_WORKSPACE = -3, /* workspace / output capacity too small */
+    DBT_ERR_IO = -4,        /* file open/read/write failure */
+    DBT_ERR_UNSUPPORTED = -5
+} dbt_status;
+
+const char *dbt_last_error(void);
+int dbt_abi_version(void);
+/* number of visible CUDA devices (0 => every other call fails loudly) */
+int dbt_device_count(void);
+
+/* ----------------------------------------------------------------------------------------------
+ * Counters of the external merge sort the reference would have run.
+ * Replaces the bookkeeping in reference DatabaseProject.cpp:216,227,298,334,346,364-376 and
+ * :522,565,579,639 (HashJoin) / :395,405,441,465,475,491 (MergeJoin).  Pure host arithmetic.
+ * ---------------------------------------------------------------------------------------------- */
+int dbt_sort_counters(uint64_t nblocks, uint32_t nmem_blocks, uint64_t *nsorted_segs, uint64_t *npasses,
+                      uint64_t *nios);
+uint64_t dbt_dedup_nios(uint64_t nblocks, uint32_t nmem_blocks, uint64_t nunique);
+uint64_t dbt_hashjoin_nios(uint64_t nblocks_r, uint64_t nblocks_s, uint32_t nmem_blocks, uint64_t nres);
+/* res = the 4 values dbt_dev_mergejoin returns (nres, nunique_R, nunique_S, later block reads) */
+uint64_t dbt_mergejoin_nios(uint64_t nblocks_r, uint64_t nblocks_s, uint32_t nmem_blocks, const uint64_t *res);
+
+/* ----------------------------------------------------------------------------------------------
+ * Building-block kernels (device scope).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* LSD onesweep radix sort of (u32 key, u32 value) pairs over key bits [begin_bit, end_bit).
+ * Replaces qsort run generation + priority_queue k-way merge (DatabaseProject.cpp:207-214,
+ * 255-343) at the pair level.  keys/vals are double buffers of n elements each; on return
+ * *result_in_alt is 1 when the sorted data sits in the *_alt buffers.  Stable.
+ * Digit positions where all keys agree are skipped.  n < 2^30. */
+size_t dbt_sort_pairs_ws_bytes(uint64_t n);
+int dbt_sort_pairs_u32(uint32_t *d_keys, uint32_t *d_keys_alt, uint32_t *d_vals, uint32_t *d_vals_alt, uint64_t n,
+                       int begin_bit, int end_bit, void *d_ws, size_t ws_bytes, void *stream, int *result_in_alt);
+
+/* Record gather + block packer: out image block k receives rows d_rows[100k .. 100k+99] of the
+ * input image (row = index into the live rows of the input in file order), with CANON headers
+ * (blockid=k, nreserved, valid=1, misc=0, dummy=nreserved; unused slots zero).
+ * Replaces the 140-byte memcpy per record per pass (DatabaseProject.cpp:202,223,303,338).
+ * d_row_slot may be NULL when every input block except the last is full (slot == row). */
+int dbt_gather_records(const void *d_in_image, const uint32_t *d_rows, const uint32_t *d_row_slot, uint64_t nrows_out,
+                       void *d_out_image, void *stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * Device-scope operators: image in HBM -> image in HBM.  `d_out` must hold
+ * ceil(rows/100) blocks where rows is the worst case for the operator (input rows for sort /
+ * dedup, min side for mergejoin, dbt_dev_hashjoin's own capacity argument).
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum dbt_op { DBT_OP_SORT = 0, DBT_OP_DEDUP = 1, DBT_OP_MERGEJOIN = 2, DBT_OP_HASHJOIN = 3 } dbt_op;
+
+/* upper bound of the workspace an operator needs for inputs of these sizes (blocks) */
+size_t dbt_dev_ws_bytes(int op, uint64_t nblocks_r, uint64_t nblocks_s, int field);
+/* same, for string keys of `kw` 32-bit words: 8 (strings shorter than 32 bytes, the default) or 30
+ * (full 120-byte keys; an operator that meets a longer string with the small workspace fails with
+ * DBT_ERR_WORKSPACE and a message naming this function) */
+size_t dbt_dev_ws_bytes_kw(int op, uint64_t nblocks_r, uint64_t nblocks_s, int field, uint32_t kw);
+
+/* MergeSort (DatabaseProject.cpp:172-381): every live row once, ordered by (key(field), recid). */
+int dbt_dev_mergesort(const void *d_in, uint64_t nblocks, int field, void *d_out, void *d_ws, size_t ws_bytes,
+                      void *stream, uint64_t *nrows);
+
+/* EliminateDuplicates (DatabaseProject.cpp:94-170): the min-recid row of every distinct key,
+ * ordered by key. */
+int dbt_dev_dedup(const void *d_in, uint64_t nblocks, int field, void *d_out, void *d_ws, size_t ws_bytes,
+                  void *stream, uint64_t *nrows, uint64_t *nunique);
+
+/* MergeJoin (DatabaseProject.cpp:384-502): dedup(R), dedup(S) into d_out_ur / d_out_us (the
+ * "1outfile.bin"/"2outfile.bin" side files), then R's row for every key present in both.
+ * res[0]=nres res[1]=nunique_R res[2]=nunique_S res[3]=later block reads of the reference's
+ * two-pointer walk (for nios). */
+int dbt_dev_mergejoin(const void *d_in_r, uint64_t nblocks_r, const void *d_in_s, uint64_t nblocks_s, int field,
+                      void *d_out_ur, void *d_out_us, void *d_out, void *d_ws, size_t ws_bytes, void *stream,
+                      uint64_t *res);
+
+/* HashJoin (DatabaseProject.cpp:504-647): S's rows, in S file order, whose key is in keys(R);
+ * field '3': once per matching R row.  out_capacity_blocks bounds d_out; when the result needs
+ * more, the call fails with DBT_ERR_WORKSPACE and *nres holds the required row count. */
+int dbt_dev_hashjoin(const void *d_in_r, uint64_t nblocks_r, const void *d_in_s, uint64_t nblocks_s, int field,
+                     void *d_out, uint64_t out_capacity_blocks, void *d_ws, size_t ws_bytes, void *stream,
+                     uint64_t *nres);
+
+/* ----------------------------------------------------------------------------------------------
+ * Host-scope operators: image in host memory -> image in host memory, copies included.
+ * These are what the file-based dbtproj entry points call after reading the block files into
+ * pinned staging.  `device` is the CUDA device index.  h_out sized like the device-scope case.
+ * ---------------------------------------------------------------------------------------------- */
+int dbt_host_mergesort(const void *h_in, uint64_t nblocks, int field, void *h_out, int device, uint64_t *nrows);
+int dbt_host_dedup(const void *h_in, uint64_t nblocks, int field, void *h_out, int device, uint64_t *nrows,
+                   uint64_t *nunique);
+int dbt_host_mergejoin(const void *h_in_r, uint64_t nblocks_r, const void *h_in_s, uint64_t nblocks_s, int field,
+                       void *h_out_ur, void *h_out_us, void *h_out, int device, uint64_t *res);
+int dbt_host_hashjoin(const void *h_in_r, uint64_t nblocks_r, const void *h_in_s, uint64_t nblocks_s, int field,
+                      void *h_out, uint64_t out_capacity_blocks, int device, uint64_t *nres);
+
+/* pinned host memory helpers for callers that want zero-staging copies */
+int dbt_host_alloc(void **p, size_t bytes);
+int dbt_host_free(void *p);
+
+/* ----------------------------------------------------------------------------------------------
+ * Synthetic inputs generated directly in HBM (SURVEY.md 8d "G_syn"; the distribution follows
+ * the reference generator main.cpp:41-77: 100 live rows per block, recid = row index, 5-letter
+ * strings, "Hola" at row 1 of every block).  kind: 0 = exactly U distinct num keys over n rows,
+ * 1 = uniform over [0,U), 2 = heavy-head power law over [0,U).  Same arithmetic as
+ * oracle/dbt_oracle.c orc_gen_syn so any sub-range can be reproduced on the CPU.
+ * ---------------------------------------------------------------------------------------------- */
+int dbt_gen_syn(uint64_t seed, uint64_t n_total, uint64_t U, int kind, uint64_t row0, uint64_t nrows, uint32_t recid0,
+                void *d_image, void *stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * Stage timing (CUDA events on the operator's stream, resolved at the operator's final sync).
+ * ---------------------------------------------------------------------------------------------- */
+void dbt_stage_timing_enable(int on);
+void dbt_stage_timing_reset(void);
+int dbt_stage_count(void);
+const char *dbt_stage_name(int i);
+double dbt_stage_ms(int i);    /* accumulated milliseconds since the last reset */
+uint64_t dbt_stage_launches(int i);
+uint64_t dbt_kernel_launches(void); /* kernels launched by this library since process start */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DBT_B200_H */

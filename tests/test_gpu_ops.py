@@ -1,0 +1,164 @@
+"""-m gpu parity tests: the CUDA path through the C-ABI vs the CANON oracle, bit-exact."""
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ["0", "1", "2", "3"]
+
+
+@pytest.fixture(scope="module")
+def files(orc):
+    f1, f2 = orc.gen_ref(42, 300)          # 30,000 rows, reference generator (main.cpp:41-77)
+    g1, g2 = orc.gen_ref(7, 120, tail_mode=1)  # junk after the NUL / in dummies, as the reference leaves it
+    return {"f1": f1, "f2": f2, "g1": g1, "g2": g2}
+
+
+@pytest.mark.parametrize("field", FIELDS)
+@pytest.mark.parametrize("name", ["f1", "g2"])
+def test_mergesort_matches_canon(dbt, orc, files, field, name):
+    src = files[name]
+    got, n = H.dev_sort(dbt, orc, src, field)
+    want = orc.sort(src, field)
+    assert n == orc.count_rows(src)
+    assert H.same_image(got, want), H.first_diff(got, want)
+
+
+@pytest.mark.parametrize("field", FIELDS)
+def test_dedup_matches_canon(dbt, orc, files, field):
+    src = files["f1"]
+    got, n, u = H.dev_dedup(dbt, orc, src, field)
+    want = orc.dedup(src, field)
+    assert u == orc.count_rows(want)
+    assert H.same_image(got, want), H.first_diff(got, want)
+
+
+@pytest.mark.parametrize("field", FIELDS)
+def test_hashjoin_matches_canon(dbt, orc, files, field):
+    r, s = files["f1"], files["f2"]
+    got, n = H.dev_hashjoin(dbt, orc, r, s, field)
+    want = orc.hashjoin(r, s, field)
+    assert n == orc.count_rows(want)
+    assert H.same_image(got, want), H.first_diff(got, want)
+
+
+def test_hashjoin_field3_multiplicity(dbt, orc):
+    # small num domain => many (num,str) duplicates in R ("Hola" rows): S rows are emitted once per matching R row
+    r, s = orc.gen_ref(3, 40, num_mod=3)
+    want = orc.hashjoin(r, s, "3")
+    nres = orc.count_rows(want)
+    assert nres > orc.count_rows(s) // 100  # really has multiplicities
+    got, n = H.dev_hashjoin(dbt, orc, r, s, "3", cap_blocks=H.nb(nres))
+    assert n == nres
+    assert H.same_image(got, want), H.first_diff(got, want)
+    # capacity too small: loud error carrying the needed size
+    with pytest.raises(dbt.DbtError):
+        H.dev_hashjoin(dbt, orc, r, s, "3", cap_blocks=1)
+
+
+@pytest.mark.parametrize("field", FIELDS)
+def test_mergejoin_matches_canon(dbt, orc, files, field):
+    r, s = files["f1"], files["f2"]
+    got, ur, us, info = H.dev_mergejoin(dbt, orc, r, s, field)
+    want, wur, wus, winfo = orc.mergejoin(r, s, field)
+    assert info == winfo
+    assert H.same_image(ur, wur), H.first_diff(ur, wur)
+    assert H.same_image(us, wus), H.first_diff(us, wus)
+    assert H.same_image(got, want), H.first_diff(got, want)
+
+
+def test_config1_sort_1m_rows(dbt, orc):
+    # BASELINE config[0]: 1M records, field num (nmem_blocks only affects the counters)
+    f1 = orc.gen_ref(42, 10000, two=False)
+    got, n = H.dev_sort(dbt, orc, f1, "1")
+    want = orc.sort(f1, "1")
+    assert n == 1_000_000
+    assert H.same_image(got, want), H.first_diff(got, want)
+
+
+def test_ragged_and_empty_inputs(dbt, orc):
+    f1 = orc.gen_ref(11, 50, two=False)
+    rag = f1.copy()
+    rng = np.random.default_rng(5)
+    rag["nreserved"] = rng.integers(0, 101, size=len(rag)).astype(np.uint32)  # partial blocks anywhere, some empty
+    for field in FIELDS:
+        got, n = H.dev_sort(dbt, orc, rag, field)
+        want = orc.sort(rag, field)
+        assert n == orc.count_rows(rag)
+        assert H.same_image(got, want), (field, H.first_diff(got, want))
+    got, n, u = H.dev_dedup(dbt, orc, rag, "1")
+    assert H.same_image(got, orc.dedup(rag, "1"))
+    # zero blocks, and blocks with zero rows
+    empty = orc.new_blocks(0)
+    got, n = H.dev_sort(dbt, orc, empty, "1")
+    assert n == 0 and len(got) == 0
+    hollow = f1[:3].copy()
+    hollow["nreserved"] = 0
+    got, n, u = H.dev_dedup(dbt, orc, hollow, "2")
+    assert (n, u, len(got)) == (0, 0, 0)
+    got, n = H.dev_hashjoin(dbt, orc, hollow, f1, "1")
+    assert n == 0
+    got, n = H.dev_hashjoin(dbt, orc, f1, hollow, "1")
+    assert n == 0
+
+
+def test_ties_canonicalised_by_recid_when_file_order_is_not(dbt, orc):
+    f1 = orc.gen_ref(13, 60, two=False, num_mod=50)  # heavy key duplication
+    rows = f1["entries"].reshape(-1)
+    rng = np.random.default_rng(1)
+    rows[:] = rows[rng.permutation(len(rows))]       # recids no longer ascending in file order
+    for field in FIELDS:
+        got, n = H.dev_sort(dbt, orc, f1, field)
+        want = orc.sort(f1, field)
+        assert H.same_image(got, want), (field, H.first_diff(got, want))
+        got, n, u = H.dev_dedup(dbt, orc, f1, field)
+        assert H.same_image(got, orc.dedup(f1, field)), field
+
+
+def test_long_strings_use_full_120_byte_keys(dbt, orc):
+    f1 = orc.gen_ref(17, 20, two=False)
+    rows = f1["entries"].reshape(-1)
+    rng = np.random.default_rng(2)
+    s = np.zeros((len(rows), 120), dtype=np.uint8)
+    lens = rng.integers(0, 120, size=len(rows))
+    for i, L in enumerate(lens):   # common 40-byte prefix so that the order is decided past byte 32
+        s[i, :L] = np.concatenate([np.full(40, ord("x")), rng.integers(97, 123, size=80)]).astype(np.uint8)[:L]
+    rows["str"] = s.view("V120").reshape(-1)
+    for field in ["2", "3"]:
+        d_in = H.to_dev(f1)
+        d_out = H.dev_alloc(len(f1) * H.BLOCK_BYTES)
+        wsb = dbt.dev_ws_bytes(dbt.OP_DEDUP, len(f1), 0, field, 30)
+        ws = H.dev_alloc(wsb)
+        n, u = dbt.dev_dedup(d_in.data_ptr(), len(f1), field, d_out.data_ptr(), ws.data_ptr(), wsb, H.stream())
+        got = H.to_host(d_out, H.nb(u), orc)
+        want = orc.dedup(f1, field)
+        assert H.same_image(got, want), (field, H.first_diff(got, want))
+
+
+def test_wrong_field_is_an_error(dbt, orc):
+    f1 = orc.gen_ref(1, 2, two=False)
+    with pytest.raises(dbt.DbtError):
+        H.dev_sort(dbt, orc, f1, "7")
+
+
+def test_sort_pairs_u32_full_range(dbt):
+    import ctypes as C
+    import torch
+
+    n = 3_000_017
+    g = torch.Generator(device="cuda").manual_seed(3)
+    keys = torch.randint(0, 2**32, (n,), dtype=torch.int64, device="cuda", generator=g).to(torch.uint32)
+    vals = torch.arange(n, dtype=torch.int32, device="cuda")
+    k1, v1 = keys.clone(), vals.clone()
+    k2, v2 = torch.empty_like(k1), torch.empty_like(v1)
+    wsb = dbt.lib().dbt_sort_pairs_ws_bytes(n)
+    ws = H.dev_alloc(wsb)
+    alt = C.c_int()
+    dbt.check(dbt.lib().dbt_sort_pairs_u32(k1.data_ptr(), k2.data_ptr(), v1.data_ptr(), v2.data_ptr(), n, 0, 32,
+                                           ws.data_ptr(), wsb, H.stream(), C.byref(alt)))
+    ko, vo = (k2, v2) if alt.value else (k1, v1)
+    ref_k, ref_i = torch.sort(keys.to(torch.int64), stable=True)
+    assert torch.equal(ko.to(torch.int64), ref_k)
+    assert torch.equal(vo.to(torch.int64), ref_i)
