@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native tuple operators.
+
+Workload (N=1): BASELINE.json configs[1] -- EliminateDuplicates field=num over 100M records with 10%
+duplicate rows (90M distinct 32-bit keys), one B200.  A "step" is one whole operator pass over the
+14.016 GB block image: headers -> key extraction -> 4-pass onesweep radix sort of (num, row) pairs ->
+adjacent-difference unique -> one record gather into the output image.
+
+  value  records/s, input image already resident in HBM, timed with CUDA events on the operator's
+         stream (dbt_dev_dedup through the C-ABI);
+  e2e    the same operator through the host-buffer C-ABI call (dbt_host_dedup): pinned host image in,
+         pinned host image out, H2D and D2H copies inside the timed region;
+  roofline  the dominant kernel's algorithmic bytes / its CUDA-event time, against MEASURED_PEAKS.json;
+  cpu_baseline  the untouched reference (oracle/_ref/ref_runner) on a bounded sample, 1 thread.
+
+`--impl reference` times the reference's own CPU implementation instead (rank 0 only).
+N>1 (torchrun): every rank holds its own 100M-row shard of one global relation; sample-sort splitters,
+one all-to-all of (key, row) pairs and one of the surviving records (see dist_ops.py).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BLOCK_BYTES = 14016
+RPB = 100
+FIELD = "1"
+NMEM = 64
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the untouched reference through oracle/_ref/ref_runner
+# ---------------------------------------------------------------------------------------------
+def ref_dedup_sample(sample_rows: int, seed: int = 42):
+    """One timed run of the reference EliminateDuplicates on a sample with the bench distribution."""
+    from oracle import pyoracle as orc  # baseline leg: the one place bench.py may execute oracle/
+
+    orc.build()
+    if not orc.ref_available():
+        return None
+    blocks = orc.gen_syn(seed, sample_rows, (sample_rows * 9) // 10, 0)
+    info, out, _ = orc.run_ref("dedup", FIELD, NMEM, blocks)
+    return {"seconds": info["seconds"], "rows": sample_rows, "nunique": info["a"]}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    rows = args.ref_rows
+    times = []
+    for i in range(args.warmup + args.steps):
+        r = ref_dedup_sample(rows)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_runner not built"}))
+            return 0
+        if i >= args.warmup:
+            times.append(r["seconds"])
+    sec = sum(times) / len(times)
+    value = rows / sec
+    sample = f"EliminateDuplicates field=num nmem_blocks={NMEM} on a {rows}-record sample of the same distribution (10% duplicate rows), files in tmpfs"
+    line = {
+        "impl": "reference", "metric": "records_per_second", "value": value, "unit": "records/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": "records/s", "cores": 1, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"EliminateDuplicates field=num, {args.rows} records per GPU, 10% duplicate rows (BASELINE configs[1]: 100M records, 1 B200)",
+        "rows_per_gpu": args.rows, "distinct_keys_per_gpu": (args.rows * 9) // 10, "nmem_blocks": NMEM,
+        "key_bits": 32, "record_bytes": 140, "cache": "input image (14 GB at 100M rows) is far larger than the 126 MB L2; no flush needed",
+        "parallelism": "1 GPU" if world == 1 else f"{world} GPUs, sample-sort range partition + all-to-all",
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=100_000_000, help="records per GPU")
+    ap.add_argument("--ref-rows", type=int, default=4_000_000, help="sample size of the CPU reference runs")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    if args.warmup < 3:
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+
+    import torch
+
+    dbt = importlib.import_module("database-technology-algorithms_b200")
+    L = dbt.lib()
+    if not torch.cuda.is_available() or L.dbt_device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device visible -- the product has no CPU fallback")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+        import dist_ops
+
+        return dist_ops.bench_main(args, dbt, rank, world, local_rank)
+
+    peak, peak_src = load_peaks()
+    n = args.rows
+    U = (n * 9) // 10
+    nblocks = (n + RPB - 1) // RPB
+    img_bytes = nblocks * BLOCK_BYTES
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+
+    d_in = torch.empty(img_bytes, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(img_bytes, dtype=torch.uint8, device=dev)
+    wsb = dbt.dev_ws_bytes(dbt.OP_DEDUP, nblocks, 0, FIELD)
+    d_ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    dbt.check(L.dbt_gen_syn(42, n, U, 0, 0, n, 0, d_in.data_ptr(), sp))
+    torch.cuda.synchronize()
+
+    def step():
+        return dbt.dev_dedup(d_in.data_ptr(), nblocks, FIELD, d_out.data_ptr(), d_ws.data_ptr(), wsb, sp)
+
+    for _ in range(args.warmup):
+        rows, uniq = step()
+    assert rows == n and uniq == U, f"wrong result: rows={rows} nunique={uniq}, expected {n}/{U}"
+
+    # ---- timed region: exactly K steps, CUDA events on the operator's stream ------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    L.dbt_stage_timing_enable(1)
+    L.dbt_stage_timing_reset()
+    launches0 = L.dbt_kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    launches = int(L.dbt_kernel_launches() - launches0)
+    stages = dbt.stage_report()
+    L.dbt_stage_timing_enable(0)
+    clocks = sampler.stop()
+    ms_step = ms_total / args.steps
+    value = n / (ms_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (live CUDA-event stage timing) -------------------------
+    alg_bytes = {  # algorithmic bytes per launch (DESIGN.md "Kernels")
+        "record_gather": 280.0 * U,       # 140 B read + 140 B written per surviving record
+        "onesweep_pass": 16.0 * n,        # 8 B read + 8 B written per (key,row) pair
+        "extract_keys": 12.0 * n,         # 4 B key read (sector-granular in practice) + key + recid columns written
+        "histogram": 4.0 * n,
+        "unique": 8.0 * n + 4.0 * U,
+    }
+    dom = max(stages.items(), key=lambda kv: kv[1][0])[0] if stages else None
+    roofline = None
+    if dom in alg_bytes:
+        ms_dom, _ = stages[dom]
+        kernel_launches = {"onesweep_pass": 4 * args.steps}.get(dom, args.steps)
+        avg_ms = ms_dom / kernel_launches
+        achieved = alg_bytes[dom] / (avg_ms * 1e-3) / 1e9
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": load_traffic(dom), "peak_source": peak_src,
+                    "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes[dom]}
+    stage_ms = {k: round(v[0] / args.steps, 4) for k, v in stages.items()}
+    per_stage_frac = {}
+    for k, b in alg_bytes.items():
+        if k in stages and stages[k][0] > 0:
+            launches_k = {"onesweep_pass": 4}.get(k, 1)
+            per_stage_frac[k] = round(b * launches_k / (stages[k][0] / args.steps * 1e-3) / 1e9 / peak, 4)
+
+    # ---- e2e: host buffers through dbt_host_dedup, copies inside the timed region ----------------
+    e2e = None
+    if not args.no_e2e:
+        import ctypes as C
+
+        h_in, h_out = C.c_void_p(), C.c_void_p()
+        dbt.check(L.dbt_host_alloc(C.byref(h_in), img_bytes))
+        dbt.check(L.dbt_host_alloc(C.byref(h_out), img_bytes))
+        torch.cuda.synchronize()
+        # fill the pinned host image from the device copy (setup, untimed)
+        host_t = torch.frombuffer((C.c_uint8 * img_bytes).from_address(h_in.value), dtype=torch.uint8)
+        host_t.copy_(d_in)
+        nr, nu = C.c_uint64(), C.c_uint64()
+
+        def e2e_step():
+            dbt.check(L.dbt_host_dedup(h_in, nblocks, ord(FIELD), h_out, local_rank, C.byref(nr), C.byref(nu)))
+
+        for _ in range(2):
+            e2e_step()
+        assert nu.value == U
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        sec = (time.perf_counter() - t0) / args.steps
+        out_bytes = ((U + RPB - 1) // RPB) * BLOCK_BYTES
+        e2e = {"value": n / sec, "unit": "records/s", "h2d_bytes_per_step": img_bytes, "d2h_bytes_per_step": out_bytes,
+               "ms_per_step": sec * 1e3, "api": "dbt_host_dedup (C-ABI, pinned host image in/out)"}
+        # spot check of the host result: first block header + record count
+        out_t = torch.frombuffer((C.c_uint8 * out_bytes).from_address(h_out.value), dtype=torch.uint8)
+        assert int(out_t[4:8].view(torch.int32)[0]) == 100
+        del host_t, out_t
+        L.dbt_host_free(h_in)
+        L.dbt_host_free(h_out)
+
+    # ---- cpu baseline: the reference itself on a bounded sample ------------------------------------
+    cpu = None
+    if not args.no_cpu:
+        r = ref_dedup_sample(args.ref_rows)
+        if r is not None:
+            cpu = {"value": r["rows"] / r["seconds"], "unit": "records/s", "cores": 1, "kind": "reference",
+                   "sample": f"reference EliminateDuplicates (oracle/_ref/ref_runner, single-threaded as shipped) on a "
+                             f"{r['rows']}-record sample of the same distribution, nmem_blocks={NMEM}, files in tmpfs; "
+                             f"host has {os.cpu_count()} cores"}
+
+    extra = {}
+    if not args.no_extra:
+        del d_out, d_ws, d_in
+        torch.cuda.empty_cache()
+        extra = extra_measurements(dbt, torch, dev, peak)
+
+    line = {
+        "metric": "records_per_second", "value": value, "unit": "records/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "gpu_launches": launches,
+        "stage_ms_per_step": stage_ms, "stage_hbm_frac": per_stage_frac, "extra": extra,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def load_traffic(kernel: str):
+    """dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(kernel)
+    return None
+
+
+def extra_measurements(dbt, torch, dev, peak):
+    """north_star side targets, reported next to the headline (not the headline itself)."""
+    import ctypes as C
+
+    L = dbt.lib()
+    out = {}
+    sp = torch.cuda.current_stream().cuda_stream
+    # 1B-record num-key pair sort on one B200 (records cannot be resident: 140 GB)
+    try:
+        n = 1_000_000_000
+        g = torch.Generator(device=dev).manual_seed(1)
+        keys = torch.randint(-2**31, 2**31, (n,), dtype=torch.int32, device=dev, generator=g)
+        k1, k2 = torch.empty_like(keys), torch.empty_like(keys)
+        v1, v2 = torch.empty_like(keys), torch.empty_like(keys)
+        wsb = L.dbt_sort_pairs_ws_bytes(n)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        alt = C.c_int()
+        times = []
+        for it in range(4):
+            k1.copy_(keys)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dbt.check(L.dbt_sort_pairs_u32(k1.data_ptr(), k2.data_ptr(), v1.data_ptr(), v2.data_ptr(), n, 0, 32,
+                                           ws.data_ptr(), wsb, sp, C.byref(alt)))
+            e1.record()
+            torch.cuda.synchronize()
+            if it:
+                times.append(e0.elapsed_time(e1))
+        ms = sum(times) / len(times)
+        ko = k2 if alt.value else k1
+        ok = True
+        for lo in range(0, n, 100_000_000):  # sortedness as unsigned 32-bit, chunk by chunk
+            c = ko[lo:min(n, lo + 100_000_001)].to(torch.int64) & 0xFFFFFFFF
+            ok = ok and bool((c[1:] >= c[:-1]).all().item())
+        assert ok, "1B pair sort produced an unsorted result"
+        out["pair_sort_1B_u32"] = {"records_per_s": n / (ms * 1e-3), "ms": ms,
+                                   "hbm_frac_of_measured_at_72B_per_record": 72.0 * n / (ms * 1e-3) / 1e9 / peak,
+                                   "note": "keys+values already in HBM; includes the OR/AND pre-scan (4 B), histogram (4 B) and 4 passes x 16 B"}
+        del keys, k1, k2, v1, v2, ws
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        out["pair_sort_1B_u32"] = {"error": str(e)[:200]}
+    return out
+
+
+if __name__ == "__main__":
+    sys.exit(main())

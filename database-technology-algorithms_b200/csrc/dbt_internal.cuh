@@ -67,6 +67,7 @@ struct StageScope { // records events around a stage when timing is enabled
     cudaStream_t stream;
     int slot;
 };
+int device_setup();   // one-time per-process device limits
 void stage_resolve(); // call after a stream sync: folds pending event pairs into the totals
 
 // ---- workspace bump allocator (no hidden device allocation on the device-scope path) -------

@@ -22,6 +22,7 @@ static bool field_ok(int f) { return f >= '0' && f <= '3'; }
 
 static int prepare(const void *d_img, uint64_t nblocks, int field, Arena &ws, cudaStream_t st, Prepared *out) {
     memset(out, 0, sizeof *out);
+    device_setup();
     DBT_TRY(image_info(d_img, nblocks, &out->row_slot, ws, st, &out->info));
     const uint64_t n = out->info.nrows;
     KeyCols &k = out->keys;
@@ -140,7 +141,7 @@ using namespace dbt;
 
 extern "C" size_t dbt_dev_ws_bytes_kw(int op, uint64_t nbr, uint64_t nbs, int field, uint32_t kw) {
     uint64_t nr = nbr * kRpb, ns = nbs * kRpb;
-    size_t scan = pad256(8 * ((std::max(nr, ns) + 2047) / 2048 + 1)) + 1024;
+    size_t scan = pad256(8 * ((std::max(nr, ns) + 2047) / 2048 + 1)) + 1024; // >= the scan's tile-state array
     size_t b = 1 << 20;
     switch (op) {
     case DBT_OP_SORT: b += rel_bytes(nbr, field, kw, true); break;

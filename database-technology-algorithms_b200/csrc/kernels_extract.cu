@@ -6,6 +6,8 @@
 // big-endian words (strcmp order == unsigned word order), so every later stage works on
 // integers only.
 #include "dbt_internal.cuh"
+#include <algorithm>
+#include <cstdlib>
 
 namespace dbt {
 
@@ -215,12 +217,169 @@ extract_kernel(const uint32_t *__restrict__ img, uint64_t nrows, const uint32_t 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Streaming extraction for block-dense images (every block but the last full => row == slot).
+// ncu (profiles/r01_notes.md): DRAM serves 128-byte lines here, and rows are 140 bytes apart, so the
+// strided kernel above already pulls ~the whole image from DRAM (132 B per row) -- but as scattered
+// sector requests at 3 TB/s.  This kernel streams whole 14016-byte blocks into shared memory with
+// cp.async.bulk (TMA bulk copy, one instruction per block, 3 blocks in flight per CTA) and picks the
+// key words out of shared memory: same DRAM bytes, sequential, and almost no LSU work.
+// ---------------------------------------------------------------------------------------------
+constexpr int kExThreads = 128;
+constexpr int kExStages = 3;
+
+__device__ __forceinline__ uint32_t ex_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int FIELD>
+__global__ void __launch_bounds__(kExThreads)
+extract_stream_kernel(const uint32_t *__restrict__ img, uint64_t nblocks, uint64_t nrows, uint32_t kw,
+                      uint32_t *__restrict__ out_w0, uint32_t *__restrict__ out_str, uint32_t *__restrict__ out_recid,
+                      ExtractStats *stats) {
+    extern __shared__ __align__(128) unsigned char ex_raw[];
+    uint32_t(*stage)[kBlockWords] = reinterpret_cast<uint32_t(*)[kBlockWords]>(ex_raw);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(ex_raw + sizeof(uint32_t) * kBlockWords * kExStages);
+    __shared__ uint32_t s_or[34], s_and[34], s_flags[2];
+    const bool HAS_STR = (FIELD >= 2);
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < 34; i += kExThreads) {
+        s_or[i] = 0;
+        s_and[i] = 0xFFFFFFFFu;
+    }
+    if (tid < 2) s_flags[tid] = 0;
+    const uint64_t first = blockIdx.x, step = gridDim.x;
+    const uint64_t my_blocks = first < nblocks ? (nblocks - first + step - 1) / step : 0;
+    auto issue = [&](uint64_t k) { // thread 0: bulk-copy my k-th block into stage k % kExStages
+        const int sidx = (int)(k % kExStages);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ex_smem_u32(&mbar[sidx])),
+                     "r"((uint32_t)DBT_BLOCK_BYTES)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         ex_smem_u32(stage[sidx])),
+                     "l"(img + (first + k * step) * kBlockWords), "r"((uint32_t)DBT_BLOCK_BYTES),
+                     "r"(ex_smem_u32(&mbar[sidx]))
+                     : "memory");
+    };
+    if (tid == 0) {
+        for (int i = 0; i < kExStages; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ex_smem_u32(&mbar[i])), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (uint64_t k = 0; k < (uint64_t)(kExStages - 1) && k < my_blocks; ++k) issue(k);
+    }
+    __syncthreads();
+    uint32_t o_w0 = 0, a_w0 = 0xFFFFFFFFu, o_id = 0, a_id = 0xFFFFFFFFu, unsorted = 0, overflow = 0;
+    for (uint64_t k = 0; k < my_blocks; ++k) {
+        if (tid == 0 && k + kExStages - 1 < my_blocks) issue(k + kExStages - 1);
+        const int sidx = (int)(k % kExStages);
+        const uint32_t parity = (uint32_t)((k / kExStages) & 1);
+        uint32_t ok = 0;
+        while (!ok)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok)
+                         : "r"(ex_smem_u32(&mbar[sidx])), "r"(parity)
+                         : "memory");
+        const uint64_t b = first + k * step;
+        const uint32_t *blk = stage[sidx];
+        const uint64_t row = b * kRpb + tid;
+        const bool live = tid < (int)kRpb && row < nrows;
+        const uint32_t *rec = blk + kEntriesWord + (live ? tid : 0) * kRecWords;
+        if (live) {
+            const uint32_t recid = rec[0];
+            const uint32_t w0 = (FIELD == 0) ? recid : ((FIELD == 2) ? 0u : rec[1]);
+            out_recid[row] = recid;
+            if (FIELD != 2) out_w0[row] = w0;
+            o_w0 |= w0;
+            a_w0 &= w0;
+            o_id |= recid;
+            a_id &= recid;
+            uint32_t prev = recid;
+            if (tid > 0) prev = rec[-(int)kRecWords];
+            else if (b > 0) prev = img[(b - 1) * kBlockWords + kEntriesWord + (kRpb - 1) * kRecWords];
+            unsorted |= recid < prev;
+        }
+        if (HAS_STR) { // whole warps take part: the per-word OR/AND go through warp reductions
+            bool ended = false;
+            uint32_t *dst = out_str + row * kw;
+            for (uint32_t j = 0; j < kw; ++j) {
+                uint32_t w = 0;
+                if (live) {
+                    w = norm_word(rec[kStrWord + j], ended);
+                    dst[j] = w;
+                }
+                const uint32_t so = __reduce_or_sync(0xFFFFFFFFu, live ? w : 0u);
+                const uint32_t sa = __reduce_and_sync(0xFFFFFFFFu, live ? w : 0xFFFFFFFFu);
+                if (lane == 0) {
+                    atomicOr(&s_or[2 + j], so);
+                    atomicAnd(&s_and[2 + j], sa);
+                }
+            }
+            overflow |= (live && !ended && kw < kStrWords);
+        }
+        __syncthreads(); // everyone is done with this stage before it is refilled
+    }
+    o_w0 = __reduce_or_sync(0xFFFFFFFFu, o_w0);
+    a_w0 = __reduce_and_sync(0xFFFFFFFFu, a_w0);
+    o_id = __reduce_or_sync(0xFFFFFFFFu, o_id);
+    a_id = __reduce_and_sync(0xFFFFFFFFu, a_id);
+    unsorted = __reduce_or_sync(0xFFFFFFFFu, unsorted);
+    overflow = __reduce_or_sync(0xFFFFFFFFu, overflow);
+    if (lane == 0) {
+        atomicOr(&s_or[0], o_w0);
+        atomicAnd(&s_and[0], a_w0);
+        atomicOr(&s_or[1], o_id);
+        atomicAnd(&s_and[1], a_id);
+        if (unsorted) s_flags[0] = 1;
+        if (overflow) s_flags[1] = 1;
+    }
+    __syncthreads();
+    if (my_blocks == 0) return;
+    if (tid == 0) {
+        atomicOr(&stats->or_w0, s_or[0]);
+        atomicAnd(&stats->and_w0, s_and[0]);
+        atomicOr(&stats->or_recid, s_or[1]);
+        atomicAnd(&stats->and_recid, s_and[1]);
+        if (s_flags[0]) atomicOr(&stats->recid_unsorted, 1u);
+        if (s_flags[1]) atomicOr(&stats->str_overflow, 1u);
+    }
+    if (HAS_STR && tid < (int)kw) {
+        atomicOr(&stats->str_or[tid], s_or[2 + tid]);
+        atomicAnd(&stats->str_and[tid], s_and[2 + tid]);
+    }
+}
+
+template <int FIELD>
+static int launch_extract_stream(const uint32_t *img, uint64_t nblocks, uint64_t nrows, uint32_t kw, uint32_t *d_w0,
+                                 uint32_t *d_str, uint32_t *d_recid, ExtractStats *d_stats, cudaStream_t st) {
+    size_t smem = sizeof(uint32_t) * kBlockWords * kExStages + 8 * kExStages + 128;
+    auto kfn = extract_stream_kernel<FIELD>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        DBT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    int grid = (int)std::min<uint64_t>(nblocks, 148 * 5);
+    kfn<<<grid, kExThreads, smem, st>>>(img, nblocks, nrows, kw, d_w0, d_str, d_recid, d_stats);
+    return 0;
+}
+
 int extract_keys(const void *d_image, uint64_t nrows, const uint32_t *d_row_slot, int field, uint32_t kw,
                  uint32_t *d_w0, uint32_t *d_str, uint32_t *d_recid, ExtractStats *d_stats, cudaStream_t st) {
     StageScope sc(ST_EXTRACT, st);
     init_stats_kernel<<<1, 128, 0, st>>>(d_stats);
     count_launch();
-    if (nrows) {
+    const bool stream_ok = (d_row_slot == nullptr) && ((uintptr_t)d_image % 16 == 0) && getenv("DBT_EXTRACT_STRIDED") == nullptr;
+    if (nrows && stream_ok) {
+        const uint32_t *img = (const uint32_t *)d_image;
+        const uint64_t nblocks = (nrows + kRpb - 1) / kRpb;
+        switch (field) {
+        case '0': DBT_TRY(launch_extract_stream<0>(img, nblocks, nrows, kw, d_w0, d_str, d_recid, d_stats, st)); break;
+        case '1': DBT_TRY(launch_extract_stream<1>(img, nblocks, nrows, kw, d_w0, d_str, d_recid, d_stats, st)); break;
+        case '2': DBT_TRY(launch_extract_stream<2>(img, nblocks, nrows, kw, d_w0, d_str, d_recid, d_stats, st)); break;
+        case '3': DBT_TRY(launch_extract_stream<3>(img, nblocks, nrows, kw, d_w0, d_str, d_recid, d_stats, st)); break;
+        default: set_error("bad field"); return DBT_ERR_ARG;
+        }
+        count_launch();
+    } else if (nrows) {
         int grid = (int)((nrows + 255) / 256);
         const uint32_t *img = (const uint32_t *)d_image;
         switch (field) {

@@ -19,11 +19,11 @@ constexpr uint64_t kSfAgg = 1ull << 62, kSfInc = 2ull << 62, kSvMask = (1ull << 
 
 __device__ __forceinline__ uint64_t ld_volatile64(const uint64_t *p) {
     uint64_t v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_volatile64(uint64_t *p, uint64_t v) {
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v));
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 struct ScanWs {
@@ -31,12 +31,14 @@ struct ScanWs {
     uint32_t *ctr;   // zeroed
 };
 
-constexpr int kScanThreads = 256;
+constexpr int kScanThreads = 512;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
 
-// CountFn: uint32_t operator()(uint64_t i) const           -- how many outputs row i produces
-// EmitFn : void operator()(uint64_t i, uint64_t off, uint32_t c) const -- write them at [off, off+c)
+// CountFn: void load(uint64_t i0, uint64_t n, uint32_t c[8], uint32_t pay[8]) const
+//            -- for the 8 consecutive rows i0..i0+7: how many outputs each produces, and a payload word
+//               (vector loads: a thread's 8 rows are 32 contiguous bytes of every input column)
+// EmitFn : void operator()(uint64_t i, uint64_t off, uint32_t c, uint32_t pay) const -- write at [off, off+c)
 template <class CountFn, class EmitFn>
 __global__ void __launch_bounds__(kScanThreads)
 scan_emit_kernel(uint64_t n, CountFn cnt, EmitFn emit, ScanWs ws, unsigned long long *total_out) {
@@ -48,13 +50,11 @@ scan_emit_kernel(uint64_t n, CountFn cnt, EmitFn emit, ScanWs ws, unsigned long 
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint64_t i0 = (uint64_t)tile * kScanTile + (uint64_t)tid * kScanItems; // blocked arrangement
-    uint32_t c[kScanItems];
+    uint32_t c[kScanItems], pay[kScanItems];
     uint64_t local = 0;
+    cnt.load(i0, n, c, pay);
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        c[k] = (i0 + k < n) ? cnt(i0 + k) : 0u;
-        local += c[k];
-    }
+    for (int k = 0; k < kScanItems; ++k) local += c[k];
     uint64_t x = local;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -77,14 +77,23 @@ scan_emit_kernel(uint64_t n, CountFn cnt, EmitFn emit, ScanWs ws, unsigned long 
         } else {
             st_volatile64(&ws.state[tile], kSfAgg | agg);
             int64_t p = (int64_t)tile - 1;
-            while (true) {
-                uint64_t s;
-                do {
-                    s = ld_volatile64(&ws.state[p]);
-                } while ((s >> 62) == 0);
-                excl += s & kSvMask;
-                if (s & kSfInc) break;
-                --p;
+            while (p >= 0) { // four predecessors per round trip
+                uint64_t s[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) s[q] = (p - q >= 0) ? ld_volatile64(&ws.state[p - q]) : kSfInc;
+                int q = 0;
+                bool done = false;
+#pragma unroll
+                for (; q < 4; ++q) {
+                    if ((s[q] >> 62) == 0) break;
+                    excl += s[q] & kSvMask;
+                    if (s[q] & kSfInc) {
+                        done = true;
+                        break;
+                    }
+                }
+                if (done) break;
+                p -= q;
             }
             st_volatile64(&ws.state[tile], kSfInc | (excl + agg));
         }
@@ -95,7 +104,7 @@ scan_emit_kernel(uint64_t n, CountFn cnt, EmitFn emit, ScanWs ws, unsigned long 
     uint64_t off = s_prefix + pre + x - local;
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
-        if (c[k]) emit(i0 + k, off, c[k]);
+        if (c[k]) emit(i0 + k, off, c[k], pay[k]);
         off += c[k];
     }
 }
@@ -142,22 +151,53 @@ struct RowKeyEq { // full-key equality of two rows through the key columns
     }
 };
 
-struct UniqueCountSorted { // 1-word keys: the sorted key column is at hand
+// 8 consecutive words of a column (32 contiguous, 32-byte aligned bytes when the tile is inside the array)
+__device__ __forceinline__ void load8(const uint32_t *col, uint64_t i0, uint64_t n, uint32_t v[8]) {
+    if (i0 + 8 <= n) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(col + i0);
+        const uint4 b = *reinterpret_cast<const uint4 *>(col + i0 + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = (i0 + k < n) ? col[i0 + k] : 0u;
+    }
+}
+
+struct UniqueCountSorted { // 1-word keys: the sorted key column is at hand; payload = the row (perm[i])
     const uint32_t *sorted;
-    __device__ uint32_t operator()(uint64_t i) const { return (i == 0 || sorted[i] != sorted[i - 1]) ? 1u : 0u; }
+    const uint32_t *perm;
+    __device__ void load(uint64_t i0, uint64_t n, uint32_t c[8], uint32_t pay[8]) const {
+        uint32_t key[8];
+        load8(sorted, i0, n, key);
+        load8(perm, i0, n, pay);
+        uint32_t prev = (i0 > 0 && i0 < n) ? sorted[i0 - 1] : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            c[k] = (i0 + k < n) ? ((i0 + k == 0 || key[k] != prev) ? 1u : 0u) : 0u;
+            prev = key[k];
+        }
+    }
 };
 struct UniqueCountRows {
     const uint32_t *perm;
     RowKeyEq eq;
-    __device__ uint32_t operator()(uint64_t i) const { return (i == 0 || !eq(perm[i - 1], perm[i])) ? 1u : 0u; }
+    __device__ void load(uint64_t i0, uint64_t n, uint32_t c[8], uint32_t pay[8]) const {
+        load8(perm, i0, n, pay);
+        uint32_t prev = (i0 > 0 && i0 < n) ? perm[i0 - 1] : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            c[k] = (i0 + k < n) ? ((i0 + k == 0 || !eq(prev, pay[k])) ? 1u : 0u) : 0u;
+            prev = pay[k];
+        }
+    }
 };
 struct EmitPerm {
-    const uint32_t *perm;
     uint32_t *out;
     uint32_t *out_key;         // optional: compacted sorted key column
     const uint32_t *sorted;
-    __device__ void operator()(uint64_t i, uint64_t off, uint32_t) const {
-        out[off] = perm[i];
+    __device__ void operator()(uint64_t i, uint64_t off, uint32_t, uint32_t row) const {
+        out[off] = row;
         if (out_key) out_key[off] = sorted[i];
     }
 };
@@ -165,9 +205,9 @@ struct EmitPerm {
 int unique_rows(const KeyCols &k, int field, const uint32_t *d_perm, const uint32_t *d_sorted_w0, uint64_t n,
                 uint32_t *d_uperm, uint32_t *d_ukeys, uint64_t *d_count, Arena &ws, cudaStream_t st) {
     StageScope sc(ST_UNIQUE, st);
-    EmitPerm emit{d_perm, d_uperm, d_ukeys, d_sorted_w0};
+    EmitPerm emit{d_uperm, d_ukeys, d_sorted_w0};
     if ((field == '0' || field == '1') && d_sorted_w0) {
-        return run_scan_emit(n, UniqueCountSorted{d_sorted_w0}, emit, d_count, ws, st);
+        return run_scan_emit(n, UniqueCountSorted{d_sorted_w0, d_perm}, emit, d_count, ws, st);
     }
     emit.out_key = nullptr;
     RowKeyEq eq{(field == '2') ? nullptr : k.w0, (field >= '2') ? k.str : nullptr, k.kw};
@@ -179,14 +219,20 @@ int unique_rows(const KeyCols &k, int field, const uint32_t *d_perm, const uint3
 // ---------------------------------------------------------------------------------------------
 struct CountFromArray {
     const uint32_t *c;
-    __device__ uint32_t operator()(uint64_t i) const { return c[i]; }
+    const uint32_t *values; // optional payload column (else the row index itself)
+    __device__ void load(uint64_t i0, uint64_t n, uint32_t cnt[8], uint32_t pay[8]) const {
+        load8(c, i0, n, cnt);
+        if (values) load8(values, i0, n, pay);
+        else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) pay[k] = (uint32_t)(i0 + k);
+        }
+    }
 };
 struct EmitRowRepeated {
     uint32_t *out;
-    const uint32_t *values; // optional: emit values[i] instead of i
     uint64_t cap;
-    __device__ void operator()(uint64_t i, uint64_t off, uint32_t c) const {
-        uint32_t v = values ? values[i] : (uint32_t)i;
+    __device__ void operator()(uint64_t, uint64_t off, uint32_t c, uint32_t v) const {
         for (uint32_t t = 0; t < c; ++t)
             if (off + t < cap) out[off + t] = v;
     }
@@ -194,7 +240,7 @@ struct EmitRowRepeated {
 int compact_select(const uint32_t *d_counts, const uint32_t *d_values, uint64_t n, uint32_t *d_out, uint64_t out_cap,
                    uint64_t *d_total, Arena &ws, cudaStream_t st) {
     StageScope sc(ST_COMPACT, st);
-    return run_scan_emit(n, CountFromArray{d_counts}, EmitRowRepeated{d_out, d_values, out_cap}, d_total, ws, st);
+    return run_scan_emit(n, CountFromArray{d_counts, d_values}, EmitRowRepeated{d_out, out_cap}, d_total, ws, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -226,11 +272,21 @@ gather_kernel(const uint32_t *__restrict__ in, const uint32_t *__restrict__ rows
         }
         __syncthreads();
         const uint32_t nwords = cnt * kRecWords;
-#pragma unroll 4
-        for (uint32_t idx = tid; idx < kRpb * kRecWords; idx += kGatherThreads) {
+        // all of a thread's loads are issued before the first shared-memory store: ~14 independent
+        // 4-byte loads in flight per thread (the first version had 4 and was latency-bound, ncu r01)
+        constexpr int kPerThread = (kRpb * kRecWords + kGatherThreads - 1) / kGatherThreads;
+        uint32_t v[kPerThread];
+#pragma unroll
+        for (int k = 0; k < kPerThread; ++k) {
+            uint32_t idx = tid + k * kGatherThreads;
             uint32_t rec = idx / kRecWords;
             uint32_t w = idx - rec * kRecWords;
-            stage[kEntriesWord + idx] = (idx < nwords) ? in[src[rec] + w] : 0u;
+            v[k] = (idx < nwords) ? __ldg(in + src[rec] + w) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < kPerThread; ++k) {
+            uint32_t idx = tid + k * kGatherThreads;
+            if (idx < kRpb * kRecWords) stage[kEntriesWord + idx] = v[k];
         }
         __syncthreads();
         const uint4 *sv = reinterpret_cast<const uint4 *>(stage);

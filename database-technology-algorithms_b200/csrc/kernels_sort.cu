@@ -25,13 +25,41 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
 }
+// tile-state words carry flag and value together, so relaxed gpu-scope accesses are enough
+// (ld.volatile would be system scope: LDG.E.STRONG.SYS, measurably slower in the look-back loop)
 __device__ __forceinline__ uint32_t ld_volatile(const uint32_t *p) {
     uint32_t v;
-    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_volatile(uint32_t *p, uint32_t v) {
-    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v));
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Decoupled look-back for one digit column: sum the aggregates of the predecessor tiles until one
+// with an inclusive prefix is met.  Four predecessors are fetched per round trip (speculatively).
+__device__ __forceinline__ uint32_t lookback_exclusive(const uint32_t *state, uint32_t tile, uint32_t col) {
+    uint32_t excl = 0;
+    int p = (int)tile - 1;
+    while (p >= 0) {
+        uint32_t s[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            s[q] = (p - q >= 0) ? ld_volatile(&state[(size_t)(p - q) * 256 + col]) : 0x80000000u;
+        int q = 0;
+        bool done = false;
+#pragma unroll
+        for (; q < 4; ++q) {
+            if ((s[q] >> 30) == 0) break; // not published yet: poll again from here
+            excl += s[q] & 0x3FFFFFFFu;
+            if (s[q] & 0x80000000u) {
+                done = true;
+                break;
+            }
+        }
+        if (done) break;
+        p -= q;
+    }
+    return excl;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -171,15 +199,29 @@ onesweep_kernel(const uint32_t *__restrict__ kin, uint32_t *__restrict__ kout, c
         key[j] = (full || idx < n) ? kin[idx] : 0xFFFFFFFFu;
     }
 
-    // ---- rank inside the warp: match-any gives the lanes with my digit; the group leader bumps the
-    // warp's counter once for the whole group (no shared-memory atomics)
+    // ---- rank inside the warp.  The lanes holding my digit ("peers") come from 8 warp ballots, one per
+    // digit bit (VOTE + LOP3 on the ALU path).  match.any would give the same mask in one instruction
+    // but runs on the ADU pipe at ~2 cycles per distinct value in the warp (ncu: 64% ADU, the limiter
+    // of the first version, profiles/r01_notes.md).  The group leader bumps the warp's private counter
+    // once for the whole group, so there are no shared-memory atomics.
     uint32_t rank[ITEMS];
     const uint32_t lt = lanemask_lt();
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
-        const bool valid = full || (idx0 + j * 32 < n);
         const uint32_t d = (key[j] >> shift) & 0xFFu;
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, valid ? d : 0x100u);
+        uint32_t peers = 0xFFFFFFFFu;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const bool bit = (d >> b) & 1u;
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, bit);
+            peers &= bit ? m : ~m;
+        }
+        bool valid = true;
+        if (!full) {
+            valid = idx0 + j * 32 < n;
+            const uint32_t vm = __ballot_sync(0xFFFFFFFFu, valid);
+            peers &= valid ? vm : ~vm;
+        }
         const int leader = __ffs(peers) - 1;
         uint32_t old = 0;
         if (lane == leader && valid) {
@@ -241,16 +283,7 @@ onesweep_kernel(const uint32_t *__restrict__ kin, uint32_t *__restrict__ kout, c
     if (tid < kRadix) {
         uint32_t excl_prefix = 0;
         if (tile > 0) {
-            int p = (int)tile - 1;
-            while (true) {
-                uint32_t s;
-                do {
-                    s = ld_volatile(&state[(size_t)p * kRadix + tid]);
-                } while ((s & (kFlagAgg | kFlagInc)) == 0);
-                excl_prefix += s & kValMask;
-                if (s & kFlagInc) break;
-                --p;
-            }
+            excl_prefix = lookback_exclusive(state, tile, tid);
             st_volatile(&state[(size_t)tile * kRadix + tid], kFlagInc | (excl_prefix + count_d));
         }
         sm.goff[tid] = digit_base[tid] + excl_prefix - sm.excl[tid];
@@ -268,6 +301,252 @@ onesweep_kernel(const uint32_t *__restrict__ kin, uint32_t *__restrict__ kout, c
             kout[dst] = k;
             if (HAS_VALS) vout[dst] = sm.vals[i];
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Onesweep pass, version 2: persistent CTAs with a double-buffered TMA bulk-copy pipeline.
+//
+// Why (ncu, profiles/r01_notes.md): version 1 is latency-bound -- the loads of a tile are only issued
+// when its CTA starts, ranking waits on them, and MATCH.ANY (ADU pipe) alone caps the pass at ~36% of
+// the HBM roofline.  Here every CTA keeps the NEXT tile's keys and rows in flight with
+// cp.async.bulk (global -> shared, completion on an mbarrier) while it ranks the current tile out of
+// shared memory, ranks with warp ballots (ALU pipe), optionally mixing in match.any (ADU pipe) so
+// both pipes work, and reuses the stage buffer for the digit-ordered staging of the scatter.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int THREADS, int ITEMS>
+struct Os2Smem {
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int TILE = THREADS * ITEMS;
+    alignas(128) uint32_t keys[2][TILE];
+    alignas(128) uint32_t vals[2][TILE];
+    uint32_t hist[WARPS][kRadix]; // per-warp digit counters -> (tile-exclusive + warp-exclusive) offsets
+    uint32_t goff[kRadix];        // global offset of the digit run minus its tile-local offset
+    uint32_t wsum[8];
+    alignas(8) uint64_t mbar[2];
+    uint32_t next_tile[2];
+};
+
+template <int THREADS, int ITEMS, bool HAS_VALS, bool IOTA_VALS, int RANK, bool FULL>
+__device__ __forceinline__ void os2_process_tile(Os2Smem<THREADS, ITEMS> &sm, int stg, uint32_t tile,
+                                                 const uint32_t *__restrict__ kin, uint32_t *__restrict__ kout,
+                                                 const uint32_t *__restrict__ vin, uint32_t *__restrict__ vout,
+                                                 uint32_t n, int shift, const uint32_t *__restrict__ digit_base,
+                                                 uint32_t *state) {
+    using Smem = Os2Smem<THREADS, ITEMS>;
+    constexpr int WARPS = Smem::WARPS;
+    constexpr int TILE = Smem::TILE;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = lanemask_lt();
+        const uint32_t base = tile * (uint32_t)TILE;
+        const uint32_t nvalid = FULL ? (uint32_t)TILE : n - base;
+        const uint32_t nbulk = FULL ? (uint32_t)TILE : (((nvalid * 4u) & ~15u) >> 2);
+        uint32_t *skeys = sm.keys[stg];
+        uint32_t *svals = sm.vals[stg];
+        const uint32_t li0 = warp * (ITEMS * 32) + lane; // warp-striped arrangement inside the tile
+
+        uint32_t key[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const uint32_t li = li0 + j * 32;
+            if (FULL) key[j] = skeys[li];
+            else key[j] = (li < nbulk) ? skeys[li] : ((li < nvalid) ? kin[base + li] : 0xFFFFFFFFu);
+        }
+
+        // ---- rank inside the warp (positions fit 16 bits: two per register)
+        uint32_t rank2[(ITEMS + 1) / 2];
+#pragma unroll
+        for (int j = 0; j < (ITEMS + 1) / 2; ++j) rank2[j] = 0;
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const uint32_t d = (key[j] >> shift) & 0xFFu;
+            bool valid = true;
+            uint32_t peers;
+            if (RANK == 0 || (RANK == 2 && (j & 1))) {
+                if (!FULL) valid = li0 + j * 32 < nvalid;
+                peers = __match_any_sync(0xFFFFFFFFu, valid ? d : 0x100u);
+            } else {
+                peers = 0xFFFFFFFFu;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const bool bit = (d >> b) & 1u;
+                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, bit);
+                    peers &= bit ? m : ~m;
+                }
+                if (!FULL) {
+                    valid = li0 + j * 32 < nvalid;
+                    const uint32_t vm = __ballot_sync(0xFFFFFFFFu, valid);
+                    peers &= valid ? vm : ~vm;
+                }
+            }
+            const int leader = __ffs(peers) - 1;
+            uint32_t old = 0;
+            if (lane == leader && valid) {
+                old = sm.hist[warp][d];
+                sm.hist[warp][d] = old + __popc(peers);
+            }
+            old = __shfl_sync(0xFFFFFFFFu, old, leader);
+            rank2[j >> 1] |= (old + __popc(peers & lt)) << ((j & 1) * 16);
+            __syncwarp();
+        }
+        uint32_t val[HAS_VALS ? ITEMS : 1];
+        if (HAS_VALS) {
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) {
+                const uint32_t li = li0 + j * 32;
+                if (IOTA_VALS) val[j] = base + li;
+                else if (FULL) val[j] = svals[li];
+                else val[j] = (li < nbulk) ? svals[li] : ((li < nvalid) ? vin[base + li] : 0u);
+            }
+        }
+        __syncthreads(); // every key/row of the tile is in registers; warp histograms are complete
+
+        // ---- per digit: count, publish the aggregate at once, tile-local exclusive offsets
+        uint32_t count_d = 0, incl = 0;
+        if (tid < kRadix) {
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) count_d += sm.hist[w][tid];
+            st_volatile(&state[(size_t)tile * kRadix + tid], (tile == 0 ? kFlagInc : kFlagAgg) | count_d);
+            incl = count_d;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) sm.wsum[warp] = incl;
+        }
+        __syncthreads();
+        uint32_t excl_d = 0;
+        if (tid < kRadix) {
+            uint32_t pre = 0;
+            for (int w = 0; w < warp; ++w) pre += sm.wsum[w];
+            excl_d = pre + incl - count_d;
+            uint32_t acc = excl_d; // hist[w][d] := tile-local offset of warp w's first key with digit d
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) {
+                const uint32_t t = sm.hist[w][tid];
+                sm.hist[w][tid] = acc;
+                acc += t;
+            }
+        }
+        __syncthreads();
+
+        // ---- stage the tile ordered by digit, in place (the look-back latency hides behind this)
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const uint32_t d = (key[j] >> shift) & 0xFFu;
+            const uint32_t pos = sm.hist[warp][d] + ((rank2[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu);
+            if (FULL || (li0 + j * 32 < nvalid)) {
+                skeys[pos] = key[j];
+                if (HAS_VALS) svals[pos] = val[j];
+            }
+        }
+        if (tid < kRadix) { // decoupled look-back, one thread per digit
+            uint32_t excl_prefix = 0;
+            if (tile > 0) {
+                excl_prefix = lookback_exclusive(state, tile, tid);
+                st_volatile(&state[(size_t)tile * kRadix + tid], kFlagInc | (excl_prefix + count_d));
+            }
+            sm.goff[tid] = digit_base[tid] + excl_prefix - excl_d;
+        }
+        __syncthreads();
+
+        // ---- coalesced writes of the digit runs
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const uint32_t i = tid + j * THREADS;
+            if (FULL || i < nvalid) {
+                const uint32_t k = skeys[i];
+                const uint32_t dst = sm.goff[(k >> shift) & 0xFFu] + i;
+                kout[dst] = k;
+                if (HAS_VALS) vout[dst] = svals[i];
+            }
+        }
+}
+
+// RANK: 0 = match.any, 1 = 8 ballots, 2 = mixed (even items ballots, odd items match.any)
+template <int THREADS, int ITEMS, bool HAS_VALS, bool IOTA_VALS, int RANK>
+__global__ void __launch_bounds__(THREADS, (THREADS * ITEMS <= 4096) ? 3 : 1)
+onesweep2_kernel(const uint32_t *__restrict__ kin, uint32_t *__restrict__ kout, const uint32_t *__restrict__ vin,
+                 uint32_t *__restrict__ vout, uint32_t n, int shift, const uint32_t *__restrict__ digit_base,
+                 uint32_t *state /*[ntiles][256], zeroed*/, uint32_t *tile_ctr /*zeroed*/) {
+    using Smem = Os2Smem<THREADS, ITEMS>;
+    constexpr int WARPS = Smem::WARPS;
+    constexpr int TILE = Smem::TILE;
+    constexpr bool LOAD_VALS = HAS_VALS && !IOTA_VALS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t ntiles = (n + TILE - 1) / TILE;
+    const uint32_t lt = lanemask_lt();
+
+    auto issue = [&](uint32_t t, int stg) { // thread 0: start the bulk copies of tile t into stage stg
+        const uint32_t base = t * (uint32_t)TILE;
+        const uint32_t valid = min((uint32_t)TILE, n - base);
+        const uint32_t bytes = (valid * 4u) & ~15u;
+        fence_proxy_async(); // earlier generic-proxy writes to this stage are ordered before the async writes
+        mbar_expect_tx(&sm.mbar[stg], LOAD_VALS ? 2 * bytes : bytes);
+        if (bytes) {
+            bulk_g2s(sm.keys[stg], kin + base, bytes, &sm.mbar[stg]);
+            if (LOAD_VALS) bulk_g2s(sm.vals[stg], vin + base, bytes, &sm.mbar[stg]);
+        }
+    };
+
+    if (tid == 0) {
+        mbar_init(&sm.mbar[0], 1);
+        mbar_init(&sm.mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t t = atomicAdd(tile_ctr, 1u);
+        sm.next_tile[0] = t;
+        if (t < ntiles) issue(t, 0);
+    }
+    __syncthreads();
+    uint32_t tile = sm.next_tile[0];
+    int stg = 0;
+    uint32_t parity = 0; // bit s = parity to wait for on stage s
+
+    while (tile < ntiles) {
+        if (tid == 0) { // grab the next tile now and keep its data in flight while this one is processed
+            const uint32_t t = atomicAdd(tile_ctr, 1u);
+            sm.next_tile[stg ^ 1] = t;
+            if (t < ntiles) issue(t, stg ^ 1);
+        }
+        for (int i = tid; i < WARPS * kRadix; i += THREADS) (&sm.hist[0][0])[i] = 0;
+        while (!mbar_try_wait(&sm.mbar[stg], (parity >> stg) & 1u)) {
+        }
+        parity ^= 1u << stg;
+        __syncthreads();
+        if (tile * (uint32_t)TILE + (uint32_t)TILE <= n)
+            os2_process_tile<THREADS, ITEMS, HAS_VALS, IOTA_VALS, RANK, true>(sm, stg, tile, kin, kout, vin, vout, n, shift,
+                                                                              digit_base, state);
+        else
+            os2_process_tile<THREADS, ITEMS, HAS_VALS, IOTA_VALS, RANK, false>(sm, stg, tile, kin, kout, vin, vout, n, shift,
+                                                                               digit_base, state);
+        __syncthreads(); // the stage buffers are free again; next_tile[stg^1] was written long ago
+        tile = sm.next_tile[stg ^ 1];
+        stg ^= 1;
     }
 }
 
@@ -313,6 +592,55 @@ static int launch_onesweep_t(const uint32_t *kin, uint32_t *kout, const uint32_t
     return 0;
 }
 
+struct Os2Cfg {
+    int impl;  // 1 = version 1 (one tile per CTA), 2 = persistent pipelined
+    int rank;  // 0 match.any, 1 ballots, 2 mixed
+    int ctas_per_sm;
+};
+static Os2Cfg os2_cfg() {
+    static Os2Cfg cfg = [] {
+        Os2Cfg c{2, 2, 3};
+        if (const char *e = getenv("DBT_ONESWEEP_IMPL")) c.impl = atoi(e);
+        if (const char *e = getenv("DBT_ONESWEEP_RANK")) c.rank = atoi(e);
+        if (const char *e = getenv("DBT_ONESWEEP_CTAS")) c.ctas_per_sm = atoi(e);
+        return c;
+    }();
+    return cfg;
+}
+
+template <int THREADS, int ITEMS>
+static int launch_onesweep2_t(const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, uint32_t n,
+                              int shift, const uint32_t *digit_base, uint32_t *state, uint32_t *ctr, bool iota, int rank,
+                              cudaStream_t st) {
+    using Smem = Os2Smem<THREADS, ITEMS>;
+    size_t smem = sizeof(Smem) + 128;
+    uint32_t ntiles = (n + Smem::TILE - 1) / Smem::TILE;
+    int grid = (int)std::min<uint32_t>(ntiles, 148u * (uint32_t)os2_cfg().ctas_per_sm);
+#define DBT_LAUNCH_OS2(IO, RK)                                                                                   \
+    do {                                                                                                         \
+        auto kfn = onesweep2_kernel<THREADS, ITEMS, true, IO, RK>;                                               \
+        static bool attr_done = false;                                                                           \
+        if (!attr_done) {                                                                                        \
+            DBT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+            attr_done = true;                                                                                    \
+        }                                                                                                        \
+        kfn<<<grid, THREADS, smem, st>>>(kin, kout, vin, vout, n, shift, digit_base, state, ctr);                \
+    } while (0)
+    if (iota) {
+        if (rank == 0) DBT_LAUNCH_OS2(true, 0);
+        else if (rank == 2) DBT_LAUNCH_OS2(true, 2);
+        else DBT_LAUNCH_OS2(true, 1);
+    } else {
+        if (rank == 0) DBT_LAUNCH_OS2(false, 0);
+        else if (rank == 2) DBT_LAUNCH_OS2(false, 2);
+        else DBT_LAUNCH_OS2(false, 1);
+    }
+#undef DBT_LAUNCH_OS2
+    count_launch();
+    DBT_KERNEL_CHECK();
+    return 0;
+}
+
 static int tile_items() {
     OnesweepCfg c = current_cfg();
     return c.threads * c.items;
@@ -322,17 +650,25 @@ static int launch_onesweep(const uint32_t *kin, uint32_t *kout, const uint32_t *
                            int shift, const uint32_t *digit_base, uint32_t *state, uint32_t *ctr, bool has_vals,
                            bool iota, cudaStream_t st) {
     OnesweepCfg c = current_cfg();
+    const bool aligned = (((uintptr_t)kin | (uintptr_t)vin) & 15) == 0; // cp.async.bulk needs 16-byte aligned sources
+    if (os2_cfg().impl == 2 && has_vals && aligned) {
+        int rk = os2_cfg().rank;
+        if (c.threads == 256 && c.items == 16)
+            return launch_onesweep2_t<256, 16>(kin, kout, vin, vout, n, shift, digit_base, state, ctr, iota, rk, st);
+        if (c.threads == 256 && c.items == 12)
+            return launch_onesweep2_t<256, 12>(kin, kout, vin, vout, n, shift, digit_base, state, ctr, iota, rk, st);
+        if (c.threads == 512 && c.items == 8)
+            return launch_onesweep2_t<512, 8>(kin, kout, vin, vout, n, shift, digit_base, state, ctr, iota, rk, st);
+        if (c.threads == 384 && c.items == 12)
+            return launch_onesweep2_t<384, 12>(kin, kout, vin, vout, n, shift, digit_base, state, ctr, iota, rk, st);
+    }
 #define DBT_CFG(T, I)                \
     if (c.threads == T && c.items == I) \
         return launch_onesweep_t<T, I>(kin, kout, vin, vout, n, shift, digit_base, state, ctr, has_vals, iota, st);
     DBT_CFG(256, 16)
     DBT_CFG(256, 12)
-    DBT_CFG(256, 20)
     DBT_CFG(384, 12)
-    DBT_CFG(384, 16)
     DBT_CFG(512, 8)
-    DBT_CFG(512, 12)
-    DBT_CFG(512, 16)
 #undef DBT_CFG
     set_error("unsupported DBT_ONESWEEP_CFG");
     return DBT_ERR_ARG;

@@ -1,6 +1,7 @@
 // runtime.cu -- error plumbing, stage timing, launch accounting, counter formulae.
 #include "dbt_internal.cuh"
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -79,6 +80,10 @@ void stage_resolve() {
     }
     g_pending.clear();
 }
+
+// One-time device configuration hook (nothing to set today: cudaLimitMaxL2FetchGranularity was tried
+// for the 140-byte random reads and has no effect on B200, profiles/micro/l2gran.cu).
+int device_setup() { return 0; }
 
 } // namespace dbt
 
