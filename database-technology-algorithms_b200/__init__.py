@@ -27,6 +27,7 @@ C_ABI_SYMBOLS = [
     "dbt_last_error", "dbt_abi_version", "dbt_device_count",
     "dbt_sort_counters", "dbt_dedup_nios", "dbt_hashjoin_nios", "dbt_mergejoin_nios",
     "dbt_sort_pairs_ws_bytes", "dbt_sort_pairs_u32", "dbt_gather_records",
+    "dbt_dev_extract_keys_u32", "dbt_dev_partition_rows", "dbt_dev_partition_ws_bytes",
     "dbt_dev_ws_bytes", "dbt_dev_ws_bytes_kw", "dbt_dev_mergesort", "dbt_dev_dedup", "dbt_dev_mergejoin", "dbt_dev_hashjoin",
     "dbt_host_mergesort", "dbt_host_dedup", "dbt_host_mergejoin", "dbt_host_hashjoin",
     "dbt_host_alloc", "dbt_host_free", "dbt_gen_syn",
@@ -84,6 +85,10 @@ def lib() -> C.CDLL:
     L.dbt_dev_dedup.argtypes = [vp, u64, ci, vp, vp, sz, vp, pu64, pu64]
     L.dbt_dev_mergejoin.argtypes = [vp, u64, vp, u64, ci, vp, vp, vp, vp, sz, vp, pu64]
     L.dbt_dev_hashjoin.argtypes = [vp, u64, vp, u64, ci, vp, u64, vp, sz, vp, pu64]
+    L.dbt_dev_extract_keys_u32.argtypes = [vp, u64, ci, vp, vp, sz, vp, pu64]
+    L.dbt_dev_partition_rows.argtypes = [vp, u64, ci, C.POINTER(u32), u32, vp, pu64, vp, sz, vp]
+    L.dbt_dev_partition_ws_bytes.restype = sz
+    L.dbt_dev_partition_ws_bytes.argtypes = [u64]
     L.dbt_host_mergesort.argtypes = [vp, u64, ci, vp, ci, pu64]
     L.dbt_host_dedup.argtypes = [vp, u64, ci, vp, ci, pu64, pu64]
     L.dbt_host_mergejoin.argtypes = [vp, u64, vp, u64, ci, vp, vp, vp, ci, pu64]

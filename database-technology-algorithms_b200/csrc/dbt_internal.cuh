@@ -135,6 +135,8 @@ int unique_rows(const KeyCols &k, int field, const uint32_t *d_perm, const uint3
 // out = values[i] (or i when values == nullptr) repeated counts[i] times, ascending i; *d_total = sum(counts)
 int compact_select(const uint32_t *d_counts, const uint32_t *d_values, uint64_t n, uint32_t *d_out, uint64_t out_cap,
                    uint64_t *d_total, Arena &ws, cudaStream_t st);
+int exclusive_offsets(const uint32_t *d_counts, uint64_t n, uint32_t *d_off, uint64_t *d_total, Arena &ws,
+                      cudaStream_t st);
 int gather_records(const void *d_in, const uint32_t *d_rows, const uint32_t *d_row_slot, uint64_t nrows_out,
                    void *d_out, cudaStream_t st);
 

@@ -126,7 +126,7 @@ static int finish(cudaStream_t st) {
 static size_t rel_bytes(uint64_t nb, int field, uint32_t kw, bool sorted) {
     uint64_t n = nb * kRpb;
     size_t b = 0;
-    b += pad256(4 * nb) + 512;                       // nreserved + header stats
+    b += 2 * pad256(4 * nb) + pad256(8 * (nb / 2048 + 2)) + 2048; // nreserved, block row offsets, scan state, stats
     b += pad256(4 * n);                              // ragged slot list
     b += 512 + pad256(4 * n);                        // stats + recid
     if (field != '2') b += pad256(4 * n);            // w0
@@ -169,6 +169,111 @@ extern "C" size_t dbt_dev_ws_bytes(int op, uint64_t nbr, uint64_t nbs, int field
             return DBT_ERR_ARG;    \
         }                          \
     } while (0)
+
+// ---- multi-GPU building blocks ---------------------------------------------------------------
+namespace dbt {
+__device__ __forceinline__ uint32_t part_hash(uint32_t k) { // must not correlate with the join table's hash
+    k ^= k >> 15;
+    k *= 0x2C1B3C6Du;
+    k ^= k >> 12;
+    k *= 0x297A2D39u;
+    k ^= k >> 15;
+    return k;
+}
+struct Splitters {
+    uint32_t v[64];
+};
+__global__ void __launch_bounds__(256)
+dest_kernel(const uint32_t *__restrict__ keys, uint64_t n, int mode, Splitters sp, uint32_t nparts,
+            uint32_t *__restrict__ dest) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t k = keys[i], d = 0;
+        if (mode == 0) {
+            for (uint32_t j = 0; j + 1 < nparts; ++j) d += (sp.v[j] <= k) ? 1u : 0u; // <= 63 compares, branch-free
+        } else {
+            d = part_hash(k) % nparts;
+        }
+        dest[i] = d;
+    }
+}
+__global__ void __launch_bounds__(256) dest_count_kernel(const uint32_t *__restrict__ dest, uint64_t n,
+                                                         unsigned long long *counts /*[64]*/) {
+    __shared__ uint32_t sh[64];
+    if (threadIdx.x < 64) sh[threadIdx.x] = 0;
+    __syncthreads();
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t d = dest[i];
+        uint32_t peers = __match_any_sync(__activemask(), d); // few distinct values per warp: cheap here
+        if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sh[d], __popc(peers));
+    }
+    __syncthreads();
+    if (threadIdx.x < 64 && sh[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+} // namespace dbt
+
+extern "C" size_t dbt_dev_partition_ws_bytes(uint64_t nblocks) {
+    uint64_t n = nblocks * kRpb;
+    return 4 * pad256(4 * n) + sort_ws_bytes(n) + (1 << 20);
+}
+
+extern "C" int dbt_dev_extract_keys_u32(const void *d_in, uint64_t nblocks, int field, uint32_t *d_keys, void *d_ws,
+                                        size_t ws_bytes, void *stream, uint64_t *nrows) {
+    if (field != '0' && field != '1') {
+        set_error("dbt_dev_extract_keys_u32: only fields '0' and '1' have u32 keys");
+        return DBT_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    Arena ws(d_ws, ws_bytes);
+    Prepared p;
+    DBT_TRY(prepare(d_in, nblocks, field, ws, st, &p));
+    if (p.info.nrows) DBT_CUDA(cudaMemcpyAsync(d_keys, p.keys.w0, 4 * p.info.nrows, cudaMemcpyDeviceToDevice, st));
+    if (nrows) *nrows = p.info.nrows;
+    return finish(st);
+}
+
+extern "C" int dbt_dev_partition_rows(const uint32_t *d_keys, uint64_t n, int mode, const uint32_t *h_splitters,
+                                      uint32_t nparts, uint32_t *d_rows_grouped, uint64_t *h_counts, void *d_ws,
+                                      size_t ws_bytes, void *stream) {
+    if (nparts == 0 || nparts > 64 || (mode != 0 && mode != 1) || !h_counts) {
+        set_error("dbt_dev_partition_rows: bad arguments (1 <= nparts <= 64)");
+        return DBT_ERR_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    Arena ws(d_ws, ws_bytes);
+    for (uint32_t i = 0; i < nparts; ++i) h_counts[i] = 0;
+    if (n == 0) return 0;
+    uint32_t *dest = ws.take<uint32_t>(n), *dest_alt = ws.take<uint32_t>(n), *rows = ws.take<uint32_t>(n);
+    unsigned long long *d_counts = ws.take<unsigned long long>(64);
+    if (!dest || !dest_alt || !rows || !d_counts) {
+        set_error("dbt_dev_partition_rows: workspace too small");
+        return DBT_ERR_WORKSPACE;
+    }
+    Splitters sp;
+    memset(&sp, 0, sizeof sp);
+    if (mode == 0)
+        for (uint32_t j = 0; j + 1 < nparts; ++j) sp.v[j] = h_splitters[j];
+    {
+        StageScope sc(ST_MISC, st);
+        int grid = (int)std::min<uint64_t>((n + 255) / 256, 148 * 16);
+        DBT_CUDA(cudaMemsetAsync(d_counts, 0, 64 * 8, st));
+        dest_kernel<<<grid, 256, 0, st>>>(d_keys, n, mode, sp, nparts, dest);
+        dest_count_kernel<<<grid, 256, 0, st>>>(dest, n, d_counts);
+        count_launch(2);
+        DBT_KERNEL_CHECK();
+    }
+    uint32_t mask = 0;
+    while ((1u << __builtin_popcount(mask)) < nparts) mask = (mask << 1) | 1u; // bits needed for nparts-1
+    uint32_t *k = dest, *ka = dest_alt, *v = rows, *va = d_rows_grouped;
+    DBT_TRY(sort_pairs_masked(k, ka, v, va, n, mask, true, ws, st)); // one stable pass on the destination id
+    if (v != d_rows_grouped) DBT_CUDA(cudaMemcpyAsync(d_rows_grouped, v, 4 * n, cudaMemcpyDeviceToDevice, st));
+    unsigned long long hc[64];
+    DBT_CUDA(cudaMemcpyAsync(hc, d_counts, sizeof hc, cudaMemcpyDeviceToHost, st));
+    DBT_TRY(finish(st));
+    for (uint32_t i = 0; i < nparts; ++i) h_counts[i] = hc[i];
+    return 0;
+}
 
 extern "C" int dbt_dev_mergesort(const void *d_in, uint64_t nblocks, int field, void *d_out, void *d_ws, size_t ws_bytes,
                                  void *stream, uint64_t *nrows) {

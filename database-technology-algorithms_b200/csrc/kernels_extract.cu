@@ -38,31 +38,15 @@ __global__ void __launch_bounds__(256) header_kernel(const uint32_t *__restrict_
     }
 }
 
-// ragged images only (rare): serial-per-CTA scan of nreserved, then slot list.  One CTA, chunked.
-__global__ void __launch_bounds__(1024) ragged_slots_kernel(const uint32_t *__restrict__ nres, uint64_t nblocks,
-                                                            uint32_t *__restrict__ row_slot) {
-    __shared__ uint32_t wsum[32];
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint64_t b0 = 0; b0 < nblocks; b0 += 1024) {
-        uint64_t b = b0 + threadIdx.x;
-        uint32_t v = b < nblocks ? nres[b] : 0, x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, o);
-            if (lane >= o) x += t;
-        }
-        if (lane == 31) wsum[warp] = x;
-        __syncthreads();
-        uint32_t pre = carry;
-        for (int w = 0; w < warp; ++w) pre += wsum[w];
-        uint32_t off = pre + x - v;
-        for (uint32_t i = 0; i < v; ++i) row_slot[off + i] = (uint32_t)(b * kRpb + i);
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = pre + x;
-        __syncthreads();
+// ragged images (partial blocks in the middle: what a rank receives from the all-to-all, or a user file
+// with holes): row offsets of the blocks come from the device-wide scan in kernels_gather.cu, then one
+// thread per (block, entry) writes the slot list with coalesced stores.
+__global__ void __launch_bounds__(128)
+ragged_fill_kernel(const uint32_t *__restrict__ nres, const uint32_t *__restrict__ row_off, uint64_t nblocks,
+                   uint32_t *__restrict__ row_slot) {
+    for (uint64_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        const uint32_t e = threadIdx.x;
+        if (e < nres[b]) row_slot[row_off[b] + e] = (uint32_t)(b * kRpb + e);
     }
 }
 
@@ -99,7 +83,15 @@ int image_info(const void *d_image, uint64_t nblocks, uint32_t **d_row_slot_out,
             set_error("image_info: workspace too small (ragged slot list)");
             return DBT_ERR_WORKSPACE;
         }
-        ragged_slots_kernel<<<1, 1024, 0, st>>>(d_nres, nblocks, slots);
+        uint32_t *row_off = ws.take<uint32_t>(nblocks);
+        uint64_t *d_total = ws.take<uint64_t>(8);
+        if (!row_off || !d_total) {
+            set_error("image_info: workspace too small (ragged offsets)");
+            return DBT_ERR_WORKSPACE;
+        }
+        DBT_TRY(exclusive_offsets(d_nres, nblocks, row_off, d_total, ws, st));
+        int grid = (int)std::min<uint64_t>(nblocks, 148 * 32);
+        ragged_fill_kernel<<<grid, 128, 0, st>>>(d_nres, row_off, nblocks, slots);
         count_launch();
         DBT_KERNEL_CHECK();
         *d_row_slot_out = slots;

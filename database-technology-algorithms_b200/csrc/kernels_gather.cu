@@ -243,6 +243,29 @@ int compact_select(const uint32_t *d_counts, const uint32_t *d_values, uint64_t 
     return run_scan_emit(n, CountFromArray{d_counts, d_values}, EmitRowRepeated{d_out, out_cap}, d_total, ws, st);
 }
 
+// exclusive prefix sums of a u32 array (offsets < 2^32): out[i] = sum(counts[0..i))
+struct EmitOffset {
+    uint32_t *out;
+    __device__ void operator()(uint64_t i, uint64_t off, uint32_t, uint32_t) const { out[i] = (uint32_t)off; }
+};
+__global__ void __launch_bounds__(256)
+fix_zero_offsets_kernel(const uint32_t *__restrict__ counts, uint64_t n, uint32_t *__restrict__ off) {
+    // rows with count 0 were skipped by the emit; their offset equals the next emitted row's (or the total)
+    // -- they are never dereferenced (no entries), so any value is fine; write 0 for determinism
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && counts[i] == 0) off[i] = 0;
+}
+int exclusive_offsets(const uint32_t *d_counts, uint64_t n, uint32_t *d_off, uint64_t *d_total, Arena &ws,
+                      cudaStream_t st) {
+    DBT_TRY(run_scan_emit(n, CountFromArray{d_counts, nullptr}, EmitOffset{d_off}, d_total, ws, st));
+    if (n) {
+        fix_zero_offsets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_counts, n, d_off);
+        count_launch();
+        DBT_KERNEL_CHECK();
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Record gather + block packer.  One CTA builds one 14016-byte output block in shared memory
 // from 4-byte gathered words (records are only 4-byte aligned) and stores it with

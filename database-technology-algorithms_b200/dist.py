@@ -1,0 +1,216 @@
+"""Multi-GPU sharding of the tuple operators: one process per GPU, torch.distributed for the plumbing.
+
+SURVEY.md 8e / north_star: sort and dedup shard by sample-sort key-range splitters, joins by key hash,
+each with ONE all-to-all over NVLink.  What travels is whole records, as block images: the output of a
+distributed sort is range-partitioned across the ranks (rank r holds the r-th key range, so the
+concatenation of the ranks' outputs is the globally sorted file), which means (P-1)/P of all records
+must cross the fabric whatever the algorithm.
+
+Per rank:   keys = extract(image)                                   [C-ABI, CUDA]
+            dest = range bucket by splitters | hash(key) mod P       [C-ABI, CUDA]
+            rows grouped by dest (one stable radix pass)             [C-ABI, CUDA]
+            P record gathers -> P block images                       [C-ABI, CUDA]
+            all_to_all_single of the images                          [NCCL]
+            the ordinary single-GPU operator on the received image   [C-ABI, CUDA]
+
+`LocalOps` is the CUDA backend (no fallback).  The orchestration in `DistOps` only needs the small
+interface below, which is what lets tests/test_dist_gloo.py drive it on CPU tensors over gloo with a
+test-side backend.  u32 keys (fields '0' and '1') in this round.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import importlib
+
+BLOCK_BYTES = 14016
+RPB = 100
+
+
+def _pkg():
+    return importlib.import_module("database-technology-algorithms_b200")
+
+
+class LocalOps:
+    """Single-GPU building blocks through the C-ABI of libdbt_b200.so; torch owns the memory."""
+
+    def __init__(self, device):
+        import torch
+
+        self.torch = torch
+        self.dbt = _pkg()
+        self.L = self.dbt.lib()
+        if self.L.dbt_device_count() == 0:
+            raise RuntimeError("no CUDA device visible: there is no CPU fallback")
+        self.device = device
+        self._ws = None
+
+    def _stream(self) -> int:
+        return self.torch.cuda.current_stream().cuda_stream
+
+    def alloc(self, nbytes: int):
+        return self.torch.empty(max(int(nbytes), 256), dtype=self.torch.uint8, device=self.device)
+
+    def workspace(self, nbytes: int):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = self.alloc(nbytes)
+        return self._ws
+
+    def extract_keys(self, img, nblocks: int, field: str):
+        keys = self.torch.empty(max(nblocks * RPB, 1), dtype=self.torch.int32, device=self.device)
+        wsb = self.dbt.dev_ws_bytes(self.dbt.OP_SORT, nblocks, 0, field)
+        ws = self.workspace(wsb)
+        n = C.c_uint64()
+        self.dbt.check(self.L.dbt_dev_extract_keys_u32(img.data_ptr(), nblocks, ord(field), keys.data_ptr(), ws.data_ptr(),
+                                                       wsb, self._stream(), C.byref(n)))
+        return keys[: n.value]
+
+    def partition(self, keys, mode: int, splitters, nparts: int):
+        n = keys.numel()
+        rows = self.torch.empty(max(n, 1), dtype=self.torch.int32, device=self.device)
+        wsb = self.L.dbt_dev_partition_ws_bytes((n + RPB - 1) // RPB + 1)
+        ws = self.workspace(wsb)
+        sp = (C.c_uint32 * 64)(*[int(x) for x in splitters]) if splitters else (C.c_uint32 * 64)()
+        counts = (C.c_uint64 * 64)()
+        self.dbt.check(self.L.dbt_dev_partition_rows(keys.data_ptr(), n, mode, sp, nparts, rows.data_ptr(), counts,
+                                                     ws.data_ptr(), wsb, self._stream()))
+        return rows[:n], [int(counts[i]) for i in range(nparts)]
+
+    def gather(self, img, rows, out_img):
+        self.dbt.check(self.L.dbt_gather_records(img.data_ptr(), rows.data_ptr(), None, rows.numel(), out_img.data_ptr(),
+                                                 self._stream()))
+
+    def sample_keys(self, keys, nsamples: int):
+        """Exactly `nsamples` evenly spaced keys as an int64 tensor of unsigned values (-1 = no row)."""
+        n = keys.numel()
+        if n == 0:
+            return self.torch.full((nsamples,), -1, dtype=self.torch.int64, device=self.device)
+        idx = (self.torch.arange(nsamples, device=self.device, dtype=self.torch.int64) * n) // nsamples  # exact (float32 linspace is not)
+        return keys[idx].to(self.torch.int64) & 0xFFFFFFFF
+
+    def run(self, op: str, field: str, img_r, nb_r: int, img_s=None, nb_s: int = 0):
+        """The ordinary device-scope operator on (possibly ragged) images; returns (out image, info)."""
+        dbt = self.dbt
+        if op == "sort":
+            out = self.alloc(nb_r * BLOCK_BYTES)
+            wsb = dbt.dev_ws_bytes(dbt.OP_SORT, nb_r, 0, field)
+            n = dbt.dev_mergesort(img_r.data_ptr(), nb_r, field, out.data_ptr(), self.workspace(wsb).data_ptr(), wsb, self._stream())
+            return out, {"rows": n, "out_rows": n}
+        if op == "dedup":
+            out = self.alloc(nb_r * BLOCK_BYTES)
+            wsb = dbt.dev_ws_bytes(dbt.OP_DEDUP, nb_r, 0, field)
+            n, u = dbt.dev_dedup(img_r.data_ptr(), nb_r, field, out.data_ptr(), self.workspace(wsb).data_ptr(), wsb, self._stream())
+            return out, {"rows": n, "out_rows": u}
+        if op == "hashjoin":
+            out = self.alloc(nb_s * BLOCK_BYTES)
+            wsb = dbt.dev_ws_bytes(dbt.OP_HASHJOIN, nb_r, nb_s, field)
+            k = dbt.dev_hashjoin(img_r.data_ptr(), nb_r, img_s.data_ptr(), nb_s, field, out.data_ptr(), nb_s,
+                                 self.workspace(wsb).data_ptr(), wsb, self._stream())
+            return out, {"out_rows": k}
+        if op == "mergejoin":
+            out = self.alloc(min(nb_r, nb_s) * BLOCK_BYTES)
+            ur, us = self.alloc(nb_r * BLOCK_BYTES), self.alloc(nb_s * BLOCK_BYTES)
+            wsb = dbt.dev_ws_bytes(dbt.OP_MERGEJOIN, nb_r, nb_s, field)
+            info = dbt.dev_mergejoin(img_r.data_ptr(), nb_r, img_s.data_ptr(), nb_s, field, ur.data_ptr(), us.data_ptr(),
+                                     out.data_ptr(), self.workspace(wsb).data_ptr(), wsb, self._stream())
+            return out, {"out_rows": info["nres"], **info}
+        raise ValueError(op)
+
+
+def choose_splitters(all_samples, nparts: int):
+    """nparts-1 ascending key values cutting the gathered sample (1-D int64 tensor, -1 = padding) into
+    equal parts.  Split on key only, so equal keys always land on the same rank."""
+    s = all_samples[all_samples >= 0].sort().values
+    if s.numel() == 0 or nparts <= 1:
+        return [0] * max(nparts - 1, 0)
+    n = s.numel()
+    return [int(s[min(n - 1, (n * (i + 1)) // nparts)].item()) for i in range(nparts - 1)]
+
+
+class DistOps:
+    """Sharded operators over a torch.distributed process group (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, ops, group=None, samples_per_rank: int = 16384):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.ops, self.group = torch, dist, ops, group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.samples_per_rank = samples_per_rank
+        self.last_exchange = {}
+
+    # -- the one exchange step ---------------------------------------------------------------
+    def exchange(self, img, nblocks: int, field: str, mode: int, splitters=None):
+        """Route every row of the local image to its owner; returns (received image, nblocks_received).
+        The received image is the concatenation, in rank order, of one block image per source rank
+        (each with a partial last block at most): a ragged image the device operators accept."""
+        torch, dist, P = self.torch, self.dist, self.world
+        keys = self.ops.extract_keys(img, nblocks, field)
+        if mode == 0 and splitters is None:
+            splitters = self.splitters_from(self.ops.sample_keys(keys, self.samples_per_rank))
+        rows, counts = self.ops.partition(keys, mode, splitters or [], P)
+        send_blocks = [(c + RPB - 1) // RPB for c in counts]
+        send = self.ops.alloc(sum(send_blocks) * BLOCK_BYTES)
+        off_rows, off_blocks = 0, 0
+        for d in range(P):
+            if counts[d]:
+                self.ops.gather(img, rows[off_rows:off_rows + counts[d]], send[off_blocks * BLOCK_BYTES:])
+            off_rows += counts[d]
+            off_blocks += send_blocks[d]
+        # sizes: one tiny all-to-all of block counts, then the data
+        sb = torch.tensor(send_blocks, dtype=torch.int64, device=send.device)
+        rb = torch.empty_like(sb)
+        dist.all_to_all_single(rb, sb, group=self.group)
+        recv_blocks = [int(x) for x in rb.cpu().tolist()]
+        recv = self.ops.alloc(sum(recv_blocks) * BLOCK_BYTES)
+        in_split = [b * BLOCK_BYTES for b in send_blocks]
+        out_split = [b * BLOCK_BYTES for b in recv_blocks]
+        send_v = send[: sum(in_split)]
+        recv_v = recv[: sum(out_split)]
+        ev = None
+        if send.is_cuda:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        dist.all_to_all_single(recv_v, send_v, out_split, in_split, group=self.group)
+        if ev:
+            ev[1].record()
+        self.last_exchange = {"bytes_sent_remote": sum(b for d, b in enumerate(in_split) if d != self.rank),
+                              "bytes_sent": sum(in_split), "events": ev, "splitters": splitters, "send_rows": counts}
+        return recv, sum(recv_blocks)
+
+    def splitters_from(self, my_samples):
+        gathered = [self.torch.empty_like(my_samples) for _ in range(self.world)]
+        self.dist.all_gather(gathered, my_samples, group=self.group)
+        return choose_splitters(self.torch.cat(gathered), self.world)
+
+    # -- operators ------------------------------------------------------------------------------
+    def sort(self, img, nblocks: int, field: str):
+        recv, nb = self.exchange(img, nblocks, field, mode=0)
+        return self.ops.run("sort", field, recv, nb)
+
+    def dedup(self, img, nblocks: int, field: str):
+        recv, nb = self.exchange(img, nblocks, field, mode=0)
+        return self.ops.run("dedup", field, recv, nb)
+
+    def hashjoin(self, img_r, nb_r: int, img_s, nb_s: int, field: str):
+        rr, nbr = self.exchange(img_r, nb_r, field, mode=1)
+        rs, nbs = self.exchange(img_s, nb_s, field, mode=1)
+        return self.ops.run("hashjoin", field, rr, nbr, rs, nbs)
+
+    def mergejoin(self, img_r, nb_r: int, img_s, nb_s: int, field: str):
+        # both relations must use the SAME splitters so that equal keys of R and S meet
+        torch, dist, P = self.torch, self.dist, self.world
+        kr = self.ops.extract_keys(img_r, nb_r, field)
+        ks = self.ops.extract_keys(img_s, nb_s, field)
+        sp = self.splitters_from(torch.cat([self.ops.sample_keys(kr, self.samples_per_rank // 2),
+                                            self.ops.sample_keys(ks, self.samples_per_rank // 2)]))
+        rr, nbr = self.exchange(img_r, nb_r, field, mode=0, splitters=sp)
+        rs, nbs = self.exchange(img_s, nb_s, field, mode=0, splitters=sp)
+        return self.ops.run("mergejoin", field, rr, nbr, rs, nbs)
+
+    def total(self, value: int) -> int:
+        t = self.torch.tensor([int(value)], dtype=self.torch.int64,
+                              device=self.ops.device if hasattr(self.ops, "device") else "cpu")
+        self.dist.all_reduce(t, group=self.group)
+        return int(t.item())

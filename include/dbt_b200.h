@@ -119,6 +119,25 @@ int dbt_dev_hashjoin(const void *d_in_r, uint64_t nblocks_r, const void *d_in_s,
                      uint64_t *nres);
 
 /* ----------------------------------------------------------------------------------------------
+ * Multi-GPU building blocks.  The operators shard by KEY: sort / dedup by key range
+ * (sample-sort splitters, so equal keys meet on one GPU and the concatenation of the ranks' outputs
+ * is globally ordered), joins by key hash.  Each rank: extract keys -> choose a destination per row ->
+ * group its rows by destination -> gather each group into its own block image -> ONE all-to-all of
+ * images (NCCL, issued by the caller) -> the ordinary device-scope operator on what it received.
+ * u32 keys (fields '0' and '1') in this round.
+ * ---------------------------------------------------------------------------------------------- */
+/* key column of an image: d_keys[row] for the live rows in file order; *nrows receives the count */
+int dbt_dev_extract_keys_u32(const void *d_in, uint64_t nblocks, int field, uint32_t *d_keys, void *d_ws,
+                             size_t ws_bytes, void *stream, uint64_t *nrows);
+/* Destination of every row and the rows grouped by destination (stable: file order inside a group).
+ * mode 0: dest = number of splitters <= key   (h_splitters: nparts-1 ascending keys, host memory)
+ * mode 1: dest = mixhash(key) mod nparts      (h_splitters ignored)
+ * d_rows_grouped[n]: row ids, group 0 first; h_counts[nparts]: group sizes (host memory). */
+int dbt_dev_partition_rows(const uint32_t *d_keys, uint64_t n, int mode, const uint32_t *h_splitters, uint32_t nparts,
+                           uint32_t *d_rows_grouped, uint64_t *h_counts, void *d_ws, size_t ws_bytes, void *stream);
+size_t dbt_dev_partition_ws_bytes(uint64_t nblocks);
+
+/* ----------------------------------------------------------------------------------------------
  * Host-scope operators: image in host memory -> image in host memory, copies included.
  * These are what the file-based dbtproj entry points call after reading the block files into
  * pinned staging.  `device` is the CUDA device index.  h_out sized like the device-scope case.

@@ -1,0 +1,133 @@
+"""CPU test of the N>1 path: the DistOps orchestration (splitters, routing, one all-to-all of block
+images, local operator on the ragged received image) over gloo with world_size 2 and 3.  The per-rank
+building blocks are a TEST-SIDE numpy/oracle backend here (the product backend is CUDA-only and is
+covered by the -m gpu tests); what this checks is that the sharded algorithm composes to exactly the
+single-node CANON result."""
+import importlib
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BLOCK = 14016
+
+
+class OracleOps:
+    """Same interface as dist.LocalOps, on CPU tensors, backed by the oracle (test infrastructure)."""
+
+    device = "cpu"
+
+    def __init__(self, orc):
+        self.orc = orc
+
+    def alloc(self, nbytes):
+        return torch.zeros(max(int(nbytes), 256), dtype=torch.uint8)
+
+    def _blocks(self, img, nblocks):
+        return self.orc.as_blocks(img[: nblocks * BLOCK].numpy())
+
+    def extract_keys(self, img, nblocks, field):
+        rows = self.orc.rows_of(self._blocks(img, nblocks))
+        col = rows["recid"] if field == "0" else rows["num"]
+        return torch.from_numpy(col.astype(np.uint32).view(np.int32).copy())
+
+    def sample_keys(self, keys, nsamples):
+        if keys.numel() == 0:
+            return torch.full((nsamples,), -1, dtype=torch.int64)
+        idx = (torch.arange(nsamples, dtype=torch.int64) * keys.numel()) // nsamples
+        return keys[idx].to(torch.int64) & 0xFFFFFFFF
+
+    def partition(self, keys, mode, splitters, nparts):
+        k = keys.numpy().view(np.uint32).astype(np.int64)
+        if mode == 0:
+            dest = np.searchsorted(np.asarray(splitters, dtype=np.int64), k, side="right") if nparts > 1 else np.zeros_like(k)
+        else:
+            dest = (k * 2654435761 % (2**32)) % nparts
+        order = np.argsort(dest, kind="stable")
+        counts = [int((dest == d).sum()) for d in range(nparts)]
+        return torch.from_numpy(order.astype(np.int32)), counts
+
+    def gather(self, img, rows, out_img):
+        # rows index the live rows of a block-dense image
+        src = self.orc.as_blocks(img.numpy()[: (img.numel() // BLOCK) * BLOCK])["entries"].reshape(-1)
+        picked = src[rows.numpy().astype(np.int64)]
+        nb = (len(picked) + 99) // 100
+        blocks = self.orc.new_blocks(nb)
+        for b in range(nb):
+            live = min(100, len(picked) - 100 * b)
+            blocks["entries"][b, :live] = picked[100 * b:100 * b + live]  # (reshape(-1) of this view would copy)
+            blocks["blockid"][b], blocks["nreserved"][b], blocks["valid"][b], blocks["dummy"][b] = b, live, 1, live
+        out_img[: nb * BLOCK] = torch.from_numpy(blocks.view(np.uint8).reshape(-1).copy())
+
+    def run(self, op, field, img_r, nb_r, img_s=None, nb_s=0):
+        o = self.orc
+        r = self._blocks(img_r, nb_r)
+        if op == "sort":
+            out = o.sort(r, field)
+        elif op == "dedup":
+            out = o.dedup(r, field)
+        elif op == "hashjoin":
+            out = o.hashjoin(r, self._blocks(img_s, nb_s), field)
+        else:
+            out, _, _, _ = o.mergejoin(r, self._blocks(img_s, nb_s), field)
+        t = torch.from_numpy(out.view(np.uint8).reshape(-1).copy()) if len(out) else torch.zeros(0, dtype=torch.uint8)
+        return t, {"out_rows": o.count_rows(out)}
+
+
+def _worker(rank, world, port, tmp, field):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import pyoracle as orc
+
+    dmod = importlib.import_module("database-technology-algorithms_b200.dist")
+    ops = OracleOps(orc)
+    d = dmod.DistOps(ops, samples_per_rank=512)
+    nb_local = 30
+    # one global relation of world*3000 rows, rank r holds rows [r*3000, (r+1)*3000); heavy key duplication
+    f1, f2 = orc.gen_ref(5, nb_local * world, num_mod=4000)
+    mine1 = f1[rank * nb_local:(rank + 1) * nb_local].copy()
+    mine2 = f2[rank * nb_local:(rank + 1) * nb_local].copy()
+    t1 = torch.from_numpy(mine1.view(np.uint8).reshape(-1).copy())
+    t2 = torch.from_numpy(mine2.view(np.uint8).reshape(-1).copy())
+    res = {}
+    for op in ("sort", "dedup"):
+        out, info = getattr(d, op)(t1, nb_local, field)
+        res[op] = orc.rows_of(orc.as_blocks(out.numpy()[: ((info["out_rows"] + 99) // 100) * BLOCK]))["recid"].copy()
+    out, info = d.hashjoin(t1, nb_local, t2, nb_local, field)
+    res["hashjoin"] = orc.rows_of(orc.as_blocks(out.numpy()[: ((info["out_rows"] + 99) // 100) * BLOCK]))["recid"].copy()
+    out, info = d.mergejoin(t1, nb_local, t2, nb_local, field)
+    res["mergejoin"] = orc.rows_of(orc.as_blocks(out.numpy()[: ((info["out_rows"] + 99) // 100) * BLOCK]))["recid"].copy()
+    np.savez(os.path.join(tmp, f"rank{rank}.npz"), **res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world,field", [(2, "1"), (3, "1"), (2, "0")])
+def test_sharded_operators_compose_to_the_single_node_result(orc, tmp_path, world, field):
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), field), nprocs=world, join=True)
+    parts = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    f1, f2 = orc.gen_ref(5, 30 * world, num_mod=4000)
+    # sort / dedup: range partition => concatenation in rank order is the global CANON result
+    for op, want in (("sort", orc.sort(f1, field)), ("dedup", orc.dedup(f1, field))):
+        got = np.concatenate([p[op] for p in parts])
+        assert np.array_equal(got, orc.rows_of(want)["recid"]), op
+    # joins: hash / range partition => compare as sorted recid multisets (multi-GPU rule)
+    want = np.sort(orc.rows_of(orc.hashjoin(f1, f2, field))["recid"])
+    assert np.array_equal(np.sort(np.concatenate([p["hashjoin"] for p in parts])), want)
+    want_mj = orc.rows_of(orc.mergejoin(f1, f2, field)[0])["recid"]
+    assert np.array_equal(np.concatenate([p["mergejoin"] for p in parts]), want_mj)  # range partition keeps key order
