@@ -95,3 +95,17 @@ def test_bench_reference_arm_prints_a_contract_line():
     if "unavailable" not in line:
         assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] == 1
         assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
+
+
+def test_reference_main_links_against_the_library_unchanged(dbt, tmp_path):
+    """The drop-in claim at link level: the reference's own main.cpp (untouched, compiled from where it
+    lies) resolves MergeJoin/HashJoin from libdbt_b200.so.  Only where /root/reference exists."""
+    ref = "/root/reference"
+    if not os.path.exists(os.path.join(ref, "main.cpp")):
+        pytest.skip("no /root/reference here")
+    exe = tmp_path / "dbt_ref_main"
+    libdir = os.path.dirname(dbt.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++11", "-w", "-I", ref, os.path.join(ref, "main.cpp"), "-L", libdir, "-ldbt_b200",
+                           f"-Wl,-rpath,{libdir}", "-o", str(exe)])
+    und = subprocess.check_output(["nm", "-u", str(exe)], text=True)
+    assert dbt.CXX_ENTRY_POINTS["MergeJoin"] in und and dbt.CXX_ENTRY_POINTS["HashJoin"] in und

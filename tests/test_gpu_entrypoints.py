@@ -230,3 +230,22 @@ def test_large_dedup_properties_and_cpu_spot_checks(dbt, orc):
     b = recs_in.reshape(-1, 35)[src_rows]
     assert torch.equal(a, b)
     assert bool((img_out[:, 1] == 100).all()) and bool((img_out[:, 0] == torch.arange(nbo, device="cuda", dtype=torch.int32)).all())
+
+
+def test_driver_runs_the_reference_workflow(dbt, orc, tmp_path):
+    """dbt_main = the reference main.cpp workflow (generate, MergeJoin, HashJoin on the side files)."""
+    exe = os.path.join(os.path.dirname(dbt.LIB_PATH), "dbt_main")
+    if not os.path.exists(exe):
+        pytest.skip("dbt_main not built")
+    p = subprocess.run([exe, "--nblocks", "200", "--seed", "42", "--nmem", "100", "--ops", "sort,dedup,mjoin,hjoin", "--keep"],
+                       cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    f1, f2 = orc.gen_ref(42, 200)
+    assert H.same_image(read_blocks(orc, tmp_path / "file.bin"), f1)      # the driver's generator == main.cpp:41-77
+    assert H.same_image(read_blocks(orc, tmp_path / "file2.bin"), f2)
+    want, ur, us, info = orc.mergejoin(f1, f2, "1")
+    assert H.same_image(read_blocks(orc, tmp_path / "outmerge.bin"), want)
+    assert f"pairs in the output {info['nres']} " in p.stdout
+    c = orc.sort_counters(200, 100)
+    assert os.path.exists(tmp_path / f"segment{c['nsorted_segs']}.bin")
+    assert H.same_image(read_blocks(orc, tmp_path / "NOduplicates.bin"), orc.dedup(f1, "1"))
