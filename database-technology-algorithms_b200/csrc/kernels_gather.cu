@@ -32,7 +32,7 @@ struct ScanWs {
 };
 
 constexpr int kScanThreads = 512;
-constexpr int kScanItems = 8;
+constexpr int kScanItems = 16; // two groups of 8 consecutive rows per thread
 constexpr int kScanTile = kScanThreads * kScanItems;
 
 // CountFn: void load(uint64_t i0, uint64_t n, uint32_t c[8], uint32_t pay[8]) const
@@ -53,6 +53,7 @@ scan_emit_kernel(uint64_t n, CountFn cnt, EmitFn emit, ScanWs ws, unsigned long 
     uint32_t c[kScanItems], pay[kScanItems];
     uint64_t local = 0;
     cnt.load(i0, n, c, pay);
+    cnt.load(i0 + 8, n, c + 8, pay + 8);
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) local += c[k];
     uint64_t x = local;
@@ -70,35 +71,34 @@ scan_emit_kernel(uint64_t n, CountFn cnt, EmitFn emit, ScanWs ws, unsigned long 
         if (w < warp) pre += t;
         agg += t;
     }
-    if (tid == 0) {
+    if (warp == 0) { // warp-parallel decoupled look-back: 32 predecessors per round trip
         uint64_t excl = 0;
         if (tile == 0) {
-            st_volatile64(&ws.state[0], kSfInc | agg);
+            if (lane == 0) st_volatile64(&ws.state[0], kSfInc | agg);
         } else {
-            st_volatile64(&ws.state[tile], kSfAgg | agg);
+            if (lane == 0) st_volatile64(&ws.state[tile], kSfAgg | agg);
             int64_t p = (int64_t)tile - 1;
-            while (p >= 0) { // four predecessors per round trip
-                uint64_t s[4];
+            while (true) {
+                const int64_t idx = p - lane;
+                const uint64_t sv = (idx >= 0) ? ld_volatile64(&ws.state[idx]) : kSfInc;
+                const uint32_t ready = __ballot_sync(0xFFFFFFFFu, (sv >> 62) != 0);
+                const uint32_t inc = __ballot_sync(0xFFFFFFFFu, (sv & kSfInc) != 0);
+                const int first_inc = inc ? (__ffs(inc) - 1) : 32;
+                const uint32_t need = (first_inc >= 31) ? 0xFFFFFFFFu : ((2u << first_inc) - 1u);
+                if ((ready & need) != need) continue; // a predecessor before the first inclusive one is not published yet
+                uint64_t v = (lane <= first_inc) ? (sv & kSvMask) : 0ull;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) s[q] = (p - q >= 0) ? ld_volatile64(&ws.state[p - q]) : kSfInc;
-                int q = 0;
-                bool done = false;
-#pragma unroll
-                for (; q < 4; ++q) {
-                    if ((s[q] >> 62) == 0) break;
-                    excl += s[q] & kSvMask;
-                    if (s[q] & kSfInc) {
-                        done = true;
-                        break;
-                    }
-                }
-                if (done) break;
-                p -= q;
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+                excl += v;
+                if (first_inc < 32) break;
+                p -= 32;
             }
-            st_volatile64(&ws.state[tile], kSfInc | (excl + agg));
+            if (lane == 0) st_volatile64(&ws.state[tile], kSfInc | (excl + agg));
         }
-        s_prefix = excl;
-        if ((uint64_t)(tile + 1) * kScanTile >= n) *total_out = excl + agg; // last tile
+        if (lane == 0) {
+            s_prefix = excl;
+            if ((uint64_t)(tile + 1) * kScanTile >= n) *total_out = excl + agg; // last tile
+        }
     }
     __syncthreads();
     uint64_t off = s_prefix + pre + x - local;

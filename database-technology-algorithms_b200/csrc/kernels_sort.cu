@@ -387,6 +387,18 @@ __device__ __forceinline__ void os2_process_tile(Os2Smem<THREADS, ITEMS> &sm, in
             if (RANK == 0 || (RANK == 2 && (j & 1))) {
                 if (!FULL) valid = li0 + j * 32 < nvalid;
                 peers = __match_any_sync(0xFFFFFFFFu, valid ? d : 0x100u);
+            } else if (RANK >= 13 && RANK <= 15) {
+                // hybrid: match.any on the low K bits (cost ~ number of distinct values: <= 2^K groups, ADU pipe)
+                // and one ballot per remaining bit (ALU pipe): every item loads both pipes lightly
+                constexpr int K = RANK - 10;
+                if (!FULL) valid = li0 + j * 32 < nvalid;
+                peers = __match_any_sync(0xFFFFFFFFu, valid ? (d & ((1u << K) - 1u)) : (1u << K));
+#pragma unroll
+                for (int b = K; b < 8; ++b) {
+                    const bool bit = (d >> b) & 1u;
+                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, bit);
+                    peers &= bit ? m : ~m;
+                }
             } else {
                 peers = 0xFFFFFFFFu;
 #pragma unroll
@@ -488,7 +500,7 @@ __device__ __forceinline__ void os2_process_tile(Os2Smem<THREADS, ITEMS> &sm, in
 
 // RANK: 0 = match.any, 1 = 8 ballots, 2 = mixed (even items ballots, odd items match.any)
 template <int THREADS, int ITEMS, bool HAS_VALS, bool IOTA_VALS, int RANK>
-__global__ void __launch_bounds__(THREADS, (THREADS * ITEMS <= 4096) ? 3 : 1)
+__global__ void __launch_bounds__(THREADS, (THREADS * ITEMS <= 4096) ? 3 : ((THREADS * ITEMS <= 6144) ? 2 : 1))
 onesweep2_kernel(const uint32_t *__restrict__ kin, uint32_t *__restrict__ kout, const uint32_t *__restrict__ vin,
                  uint32_t *__restrict__ vout, uint32_t n, int shift, const uint32_t *__restrict__ digit_base,
                  uint32_t *state /*[ntiles][256], zeroed*/, uint32_t *tile_ctr /*zeroed*/) {
@@ -556,7 +568,7 @@ struct OnesweepCfg {
 };
 static OnesweepCfg current_cfg() {
     static OnesweepCfg cfg = [] {
-        OnesweepCfg c{256, 16};
+        OnesweepCfg c{256, 24}; // tuned on B200: profiles/r01_notes.md
         if (const char *e = getenv("DBT_ONESWEEP_CFG")) { // tuning hook: "<threads>x<items>"
             int t = 0, i = 0;
             if (sscanf(e, "%dx%d", &t, &i) == 2) c = OnesweepCfg{t, i};
@@ -599,7 +611,7 @@ struct Os2Cfg {
 };
 static Os2Cfg os2_cfg() {
     static Os2Cfg cfg = [] {
-        Os2Cfg c{2, 2, 3};
+        Os2Cfg c{2, 13, 2}; // persistent pipelined kernel, match(3 low bits)+5 ballots, 2 CTAs/SM
         if (const char *e = getenv("DBT_ONESWEEP_IMPL")) c.impl = atoi(e);
         if (const char *e = getenv("DBT_ONESWEEP_RANK")) c.rank = atoi(e);
         if (const char *e = getenv("DBT_ONESWEEP_CTAS")) c.ctas_per_sm = atoi(e);
@@ -629,10 +641,16 @@ static int launch_onesweep2_t(const uint32_t *kin, uint32_t *kout, const uint32_
     if (iota) {
         if (rank == 0) DBT_LAUNCH_OS2(true, 0);
         else if (rank == 2) DBT_LAUNCH_OS2(true, 2);
+        else if (rank == 13) DBT_LAUNCH_OS2(true, 13);
+        else if (rank == 14) DBT_LAUNCH_OS2(true, 14);
+        else if (rank == 15) DBT_LAUNCH_OS2(true, 15);
         else DBT_LAUNCH_OS2(true, 1);
     } else {
         if (rank == 0) DBT_LAUNCH_OS2(false, 0);
         else if (rank == 2) DBT_LAUNCH_OS2(false, 2);
+        else if (rank == 13) DBT_LAUNCH_OS2(false, 13);
+        else if (rank == 14) DBT_LAUNCH_OS2(false, 14);
+        else if (rank == 15) DBT_LAUNCH_OS2(false, 15);
         else DBT_LAUNCH_OS2(false, 1);
     }
 #undef DBT_LAUNCH_OS2
@@ -661,10 +679,17 @@ static int launch_onesweep(const uint32_t *kin, uint32_t *kout, const uint32_t *
             return launch_onesweep2_t<512, 8>(kin, kout, vin, vout, n, shift, digit_base, state, ctr, iota, rk, st);
         if (c.threads == 384 && c.items == 12)
             return launch_onesweep2_t<384, 12>(kin, kout, vin, vout, n, shift, digit_base, state, ctr, iota, rk, st);
+        if (c.threads == 256 && c.items == 24)
+            return launch_onesweep2_t<256, 24>(kin, kout, vin, vout, n, shift, digit_base, state, ctr, iota, rk, st);
+        if (c.threads == 384 && c.items == 16)
+            return launch_onesweep2_t<384, 16>(kin, kout, vin, vout, n, shift, digit_base, state, ctr, iota, rk, st);
+        if (c.threads == 512 && c.items == 12)
+            return launch_onesweep2_t<512, 12>(kin, kout, vin, vout, n, shift, digit_base, state, ctr, iota, rk, st);
     }
 #define DBT_CFG(T, I)                \
     if (c.threads == T && c.items == I) \
         return launch_onesweep_t<T, I>(kin, kout, vin, vout, n, shift, digit_base, state, ctr, has_vals, iota, st);
+    DBT_CFG(256, 24)
     DBT_CFG(256, 16)
     DBT_CFG(256, 12)
     DBT_CFG(384, 12)
