@@ -30,6 +30,7 @@ C_ABI_SYMBOLS = [
     "dbt_dev_extract_keys_u32", "dbt_dev_partition_rows", "dbt_dev_partition_ws_bytes",
     "dbt_dev_ws_bytes", "dbt_dev_ws_bytes_kw", "dbt_dev_mergesort", "dbt_dev_dedup", "dbt_dev_mergejoin", "dbt_dev_hashjoin",
     "dbt_host_mergesort", "dbt_host_dedup", "dbt_host_mergejoin", "dbt_host_hashjoin",
+    "dbt_ipc_alloc", "dbt_ipc_open", "dbt_ipc_close", "dbt_ipc_free",
     "dbt_host_alloc", "dbt_host_free", "dbt_gen_syn",
     "dbt_stage_timing_enable", "dbt_stage_timing_reset", "dbt_stage_count", "dbt_stage_name", "dbt_stage_ms",
     "dbt_stage_launches", "dbt_kernel_launches",
@@ -93,6 +94,10 @@ def lib() -> C.CDLL:
     L.dbt_host_dedup.argtypes = [vp, u64, ci, vp, ci, pu64, pu64]
     L.dbt_host_mergejoin.argtypes = [vp, u64, vp, u64, ci, vp, vp, vp, ci, pu64]
     L.dbt_host_hashjoin.argtypes = [vp, u64, vp, u64, ci, vp, u64, ci, pu64]
+    L.dbt_ipc_alloc.argtypes = [sz, C.POINTER(vp), C.c_char_p]
+    L.dbt_ipc_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.dbt_ipc_close.argtypes = [vp]
+    L.dbt_ipc_free.argtypes = [vp]
     L.dbt_host_alloc.argtypes = [C.POINTER(vp), sz]
     L.dbt_host_free.argtypes = [vp]
     L.dbt_gen_syn.argtypes = [u64, u64, u64, ci, u64, u64, u32, vp, vp]

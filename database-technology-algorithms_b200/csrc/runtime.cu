@@ -154,6 +154,30 @@ uint64_t dbt_mergejoin_nios(uint64_t BR, uint64_t BS, uint32_t M, const uint64_t
     return dbt_dedup_nios(BR, M, res[1]) + dbt_dedup_nios(BS, M, res[2]) + 2 + res[3] + (res[0] + kRpb - 1) / kRpb;
 }
 
+// ---- peer memory (CUDA IPC) for the fused gather + exchange --------------------------------------
+int dbt_ipc_alloc(size_t bytes, void **d_ptr, unsigned char handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DBT_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 256));
+    cudaIpcMemHandle_t h;
+    DBT_CUDA(cudaIpcGetMemHandle(&h, *d_ptr));
+    memcpy(handle, &h, 64);
+    return 0;
+}
+int dbt_ipc_open(const unsigned char handle[64], void **d_ptr) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    DBT_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int dbt_ipc_close(void *d_ptr) {
+    DBT_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return 0;
+}
+int dbt_ipc_free(void *d_ptr) {
+    DBT_CUDA(cudaFree(d_ptr));
+    return 0;
+}
+
 int dbt_host_alloc(void **p, size_t bytes) {
     DBT_CUDA(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault));
     return 0;

@@ -80,6 +80,29 @@ class LocalOps:
         self.dbt.check(self.L.dbt_gather_records(img.data_ptr(), rows.data_ptr(), None, rows.numel(), out_img.data_ptr(),
                                                  self._stream()))
 
+    def gather_to_ptr(self, img, rows, out_ptr: int):
+        """Same kernel, output given as a raw device address (a peer's receive buffer mapped over NVLink)."""
+        self.dbt.check(self.L.dbt_gather_records(img.data_ptr(), rows.data_ptr(), None, rows.numel(), out_ptr, self._stream()))
+
+    # -- peer memory -----------------------------------------------------------------------------
+    def ipc_alloc(self, nbytes: int):
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        self.dbt.check(self.L.dbt_ipc_alloc(nbytes, C.byref(ptr), handle))
+        return ptr.value, handle.raw
+
+    def ipc_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        self.dbt.check(self.L.dbt_ipc_open(C.create_string_buffer(handle, 64), C.byref(ptr)))
+        return ptr.value
+
+    def view(self, ptr: int, nbytes: int):
+        """torch uint8 view of library-owned device memory (no copy, not owned by torch)."""
+        class _Holder:
+            __cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+        return self.torch.as_tensor(_Holder(), device=self.device)
+
     def sample_keys(self, keys, nsamples: int):
         """Exactly `nsamples` evenly spaced keys as an int64 tensor of unsigned values (-1 = no row)."""
         n = keys.numel()
@@ -130,7 +153,9 @@ def choose_splitters(all_samples, nparts: int):
 class DistOps:
     """Sharded operators over a torch.distributed process group (NCCL on GPUs, gloo in the CPU tests)."""
 
-    def __init__(self, ops, group=None, samples_per_rank: int = 16384):
+    def __init__(self, ops, group=None, samples_per_rank: int = 16384, peer_exchange=None):
+        import os
+
         import torch
         import torch.distributed as dist
 
@@ -139,9 +164,63 @@ class DistOps:
         self.world = dist.get_world_size(group)
         self.samples_per_rank = samples_per_rank
         self.last_exchange = {}
+        # fused gather + exchange over peer memory (CUDA IPC + NVLink stores); the NCCL all-to-all of
+        # gathered images remains for CPU/gloo tests and as an explicit choice (DBT_DIST_EXCHANGE=nccl)
+        if peer_exchange is None:
+            peer_exchange = hasattr(ops, "ipc_alloc") and os.environ.get("DBT_DIST_EXCHANGE", "p2p") == "p2p"
+        self.peer_exchange = bool(peer_exchange) and self.world > 1
+        self._recv = {}  # slot -> (capacity bytes, own ptr, [peer ptrs])
+
+    def _peer_buffers(self, slot: int, need_bytes: int):
+        """Receive buffer `slot` of every rank, mapped here; (re)allocated collectively when too small."""
+        torch, dist, P = self.torch, self.dist, self.world
+        cur = self._recv.get(slot)
+        want = torch.tensor([need_bytes], dtype=torch.int64, device=self.ops.device)
+        dist.all_reduce(want, op=dist.ReduceOp.MAX, group=self.group)
+        need = int(want.item())
+        if cur is not None and cur[0] >= need:
+            return cur
+        cap = need + need // 4 + (1 << 20)
+        ptr, handle = self.ops.ipc_alloc(cap)
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.ops.device)
+        allh = [torch.empty_like(mine) for _ in range(P)]
+        dist.all_gather(allh, mine, group=self.group)
+        peers = [ptr if r == self.rank else self.ops.ipc_open(bytes(allh[r].cpu().tolist())) for r in range(P)]
+        self._recv[slot] = (cap, ptr, peers)  # (older, smaller buffers are kept alive: peers may still map them)
+        return self._recv[slot]
 
     # -- the one exchange step ---------------------------------------------------------------
-    def exchange(self, img, nblocks: int, field: str, mode: int, splitters=None):
+    def _exchange_p2p(self, img, rows, counts, send_blocks, splitters, slot):
+        """Fused gather + exchange: every per-destination gather writes straight into the destination
+        rank's receive buffer (16-byte stores over NVLink); one tiny all-gather of block counts before
+        (it also orders this step after every rank's previous consumer) and one barrier after."""
+        torch, dist, P = self.torch, self.dist, self.world
+        sb = torch.tensor(send_blocks, dtype=torch.int64, device=self.ops.device)
+        mat = [torch.empty_like(sb) for _ in range(P)]
+        dist.all_gather(mat, sb, group=self.group)
+        M = torch.stack(mat).cpu().tolist()  # M[src][dst] blocks
+        recv_blocks = [int(M[src][self.rank]) for src in range(P)]
+        my_need = sum(recv_blocks) * BLOCK_BYTES
+        cap, own, peers = self._peer_buffers(slot, my_need)
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+        row_off = [0] * P
+        for d in range(1, P):
+            row_off[d] = row_off[d - 1] + counts[d - 1]
+        for k in range(P):  # rotate the destination order so that the ranks do not all hit the same peer at once
+            d = (self.rank + 1 + k) % P
+            if counts[d] == 0:
+                continue
+            blk_off = sum(int(M[src][d]) for src in range(self.rank))
+            self.ops.gather_to_ptr(img, rows[row_off[d]:row_off[d] + counts[d]], peers[d] + blk_off * BLOCK_BYTES)
+        ev[1].record()
+        dist.barrier(group=self.group)  # stream-ordered: every rank's stores have landed before anyone consumes
+        remote = sum(b for d, b in enumerate(send_blocks) if d != self.rank) * BLOCK_BYTES
+        self.last_exchange = {"bytes_sent_remote": remote, "bytes_sent": sum(send_blocks) * BLOCK_BYTES, "events": ev,
+                              "splitters": splitters, "send_rows": counts, "mode": "p2p"}
+        return self.ops.view(own, max(my_need, 256)), sum(recv_blocks)
+
+    def exchange(self, img, nblocks: int, field: str, mode: int, splitters=None, slot: int = 0):
         """Route every row of the local image to its owner; returns (received image, nblocks_received).
         The received image is the concatenation, in rank order, of one block image per source rank
         (each with a partial last block at most): a ragged image the device operators accept."""
@@ -151,6 +230,8 @@ class DistOps:
             splitters = self.splitters_from(self.ops.sample_keys(keys, self.samples_per_rank))
         rows, counts = self.ops.partition(keys, mode, splitters or [], P)
         send_blocks = [(c + RPB - 1) // RPB for c in counts]
+        if self.peer_exchange:
+            return self._exchange_p2p(img, rows, counts, send_blocks, splitters, slot)
         send = self.ops.alloc(sum(send_blocks) * BLOCK_BYTES)
         off_rows, off_blocks = 0, 0
         for d in range(P):
@@ -176,7 +257,8 @@ class DistOps:
         if ev:
             ev[1].record()
         self.last_exchange = {"bytes_sent_remote": sum(b for d, b in enumerate(in_split) if d != self.rank),
-                              "bytes_sent": sum(in_split), "events": ev, "splitters": splitters, "send_rows": counts}
+                              "bytes_sent": sum(in_split), "events": ev, "splitters": splitters, "send_rows": counts,
+                              "mode": "nccl"}
         return recv, sum(recv_blocks)
 
     def splitters_from(self, my_samples):
@@ -195,7 +277,7 @@ class DistOps:
 
     def hashjoin(self, img_r, nb_r: int, img_s, nb_s: int, field: str):
         rr, nbr = self.exchange(img_r, nb_r, field, mode=1)
-        rs, nbs = self.exchange(img_s, nb_s, field, mode=1)
+        rs, nbs = self.exchange(img_s, nb_s, field, mode=1, slot=1)
         return self.ops.run("hashjoin", field, rr, nbr, rs, nbs)
 
     def mergejoin(self, img_r, nb_r: int, img_s, nb_s: int, field: str):
@@ -206,7 +288,7 @@ class DistOps:
         sp = self.splitters_from(torch.cat([self.ops.sample_keys(kr, self.samples_per_rank // 2),
                                             self.ops.sample_keys(ks, self.samples_per_rank // 2)]))
         rr, nbr = self.exchange(img_r, nb_r, field, mode=0, splitters=sp)
-        rs, nbs = self.exchange(img_s, nb_s, field, mode=0, splitters=sp)
+        rs, nbs = self.exchange(img_s, nb_s, field, mode=0, splitters=sp, slot=1)
         return self.ops.run("mergejoin", field, rr, nbr, rs, nbs)
 
     def total(self, value: int) -> int:

@@ -137,6 +137,15 @@ int dbt_dev_partition_rows(const uint32_t *d_keys, uint64_t n, int mode, const u
                            uint32_t *d_rows_grouped, uint64_t *h_counts, void *d_ws, size_t ws_bytes, void *stream);
 size_t dbt_dev_partition_ws_bytes(uint64_t nblocks);
 
+/* Peer memory for the fused gather+exchange: a rank's receive buffer is allocated with dbt_ipc_alloc,
+ * its 64-byte handle is handed to the other ranks (any transport), and they map it with dbt_ipc_open.
+ * dbt_gather_records then takes the mapped pointer as its output image: the gather kernel's 16-byte
+ * stores travel over NVLink straight into the owner's HBM -- no send buffer, no separate collective. */
+int dbt_ipc_alloc(size_t bytes, void **d_ptr, unsigned char handle[64]);
+int dbt_ipc_open(const unsigned char handle[64], void **d_ptr);
+int dbt_ipc_close(void *d_ptr);
+int dbt_ipc_free(void *d_ptr);
+
 /* ----------------------------------------------------------------------------------------------
  * Host-scope operators: image in host memory -> image in host memory, copies included.
  * These are what the file-based dbtproj entry points call after reading the block files into
