@@ -368,8 +368,8 @@ def bench_dist(args, dbt, rank, world, local_rank):
     e0.record(stream)
     for _ in range(args.steps):
         out, info = step()
-        ev = d.last_exchange["events"]
-        xbytes = d.last_exchange["bytes_sent_remote"]
+        ev = d.last_exchange.get("gather_events") or d.last_exchange["events"]
+        xbytes = d.last_exchange.get("remote_record_bytes_read") or d.last_exchange["bytes_sent_remote"]
         xms.append(ev)
         del out
     e1.record(stream)
@@ -440,7 +440,9 @@ def bench_dist(args, dbt, rank, world, local_rank):
             roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": load_traffic(dom), "peak_source": peak_src, "ms_per_step_all_launches": ms_dom,
                         "algorithmic_bytes_per_step": 280.0 * rows_moved}
-        nvlink = {"bytes_sent_per_gpu": float(a2a[1].item()), "all_to_all_ms": float(a2a[0].item()),
+        nvlink = {"exchange": d.last_exchange.get("mode"),
+                  "what": "record bytes crossing NVLink per GPU per step, and the duration of the phase that moves them (max over ranks)",
+                  "bytes_sent_per_gpu": float(a2a[1].item()), "all_to_all_ms": float(a2a[0].item()),
                   "achieved_gbs_per_direction": float(a2a[1].item()) / (float(a2a[0].item()) * 1e-3) / 1e9 if a2a[0].item() > 0 else None,
                   "peak_gbs_per_direction": 770.0, "peak_source": "B200_PROFILING.md measured peer copy"}
         line = {

@@ -30,6 +30,8 @@ C_ABI_SYMBOLS = [
     "dbt_dev_extract_keys_u32", "dbt_dev_partition_rows", "dbt_dev_partition_ws_bytes",
     "dbt_dev_ws_bytes", "dbt_dev_ws_bytes_kw", "dbt_dev_mergesort", "dbt_dev_dedup", "dbt_dev_mergejoin", "dbt_dev_hashjoin",
     "dbt_host_mergesort", "dbt_host_dedup", "dbt_host_mergejoin", "dbt_host_hashjoin",
+    "dbt_dev_extract_key_recid_u32", "dbt_dev_take_u32", "dbt_dev_order_columns", "dbt_dev_order_columns_ws_bytes",
+    "dbt_gather_records_multi", "dbt_ipc_export",
     "dbt_ipc_alloc", "dbt_ipc_open", "dbt_ipc_close", "dbt_ipc_free",
     "dbt_host_alloc", "dbt_host_free", "dbt_gen_syn",
     "dbt_stage_timing_enable", "dbt_stage_timing_reset", "dbt_stage_count", "dbt_stage_name", "dbt_stage_ms",
@@ -94,6 +96,13 @@ def lib() -> C.CDLL:
     L.dbt_host_dedup.argtypes = [vp, u64, ci, vp, ci, pu64, pu64]
     L.dbt_host_mergejoin.argtypes = [vp, u64, vp, u64, ci, vp, vp, vp, ci, pu64]
     L.dbt_host_hashjoin.argtypes = [vp, u64, vp, u64, ci, vp, u64, ci, pu64]
+    L.dbt_dev_extract_key_recid_u32.argtypes = [vp, u64, ci, vp, vp, vp, sz, vp, pu64, C.POINTER(ci)]
+    L.dbt_dev_take_u32.argtypes = [vp, vp, u64, vp, vp]
+    L.dbt_dev_order_columns.argtypes = [vp, vp, u64, ci, vp, pu64, vp, sz, vp]
+    L.dbt_dev_order_columns_ws_bytes.restype = sz
+    L.dbt_dev_order_columns_ws_bytes.argtypes = [u64]
+    L.dbt_gather_records_multi.argtypes = [C.POINTER(vp), u32, pu64, vp, vp, u64, vp, vp]
+    L.dbt_ipc_export.argtypes = [vp, C.c_char_p, pu64]
     L.dbt_ipc_alloc.argtypes = [sz, C.POINTER(vp), C.c_char_p]
     L.dbt_ipc_open.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.dbt_ipc_close.argtypes = [vp]

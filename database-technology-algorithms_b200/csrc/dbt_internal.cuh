@@ -109,6 +109,8 @@ struct KeyCols {
 struct ImageInfo {
     uint64_t nrows;      // live rows
     int prefix_full;     // every block except the last is full => slot == row
+    const uint32_t *blk_nres;    // ragged images only: live rows per block ...
+    const uint32_t *blk_row_off; // ... and the row index of each block's first live row
 };
 int image_info(const void *d_image, uint64_t nblocks, uint32_t **d_row_slot_out, Arena &ws, cudaStream_t st,
                ImageInfo *info);
@@ -116,8 +118,9 @@ struct ExtractStats { // device-side
     uint32_t or_w0, and_w0, or_recid, and_recid, recid_unsorted, str_overflow, pad[2];
     uint32_t str_or[32], str_and[32];
 };
-int extract_keys(const void *d_image, uint64_t nrows, const uint32_t *d_row_slot, int field, uint32_t kw,
-                 uint32_t *d_w0, uint32_t *d_str, uint32_t *d_recid, ExtractStats *d_stats, cudaStream_t st);
+int extract_keys(const void *d_image, uint64_t nblocks_img, uint64_t nrows, const uint32_t *d_row_slot,
+                 const uint32_t *d_blk_nres, const uint32_t *d_blk_row_off, int field, uint32_t kw, uint32_t *d_w0,
+                 uint32_t *d_str, uint32_t *d_recid, ExtractStats *d_stats, cudaStream_t st);
 
 // radix sort (kernels_sort.cu)
 size_t sort_ws_bytes(uint64_t n);

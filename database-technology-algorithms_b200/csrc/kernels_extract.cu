@@ -54,6 +54,8 @@ int image_info(const void *d_image, uint64_t nblocks, uint32_t **d_row_slot_out,
                ImageInfo *info) {
     StageScope sc(ST_HEADERS, st);
     *d_row_slot_out = nullptr;
+    info->blk_nres = nullptr;
+    info->blk_row_off = nullptr;
     info->nrows = 0;
     info->prefix_full = 1;
     if (nblocks == 0) return 0;
@@ -95,6 +97,8 @@ int image_info(const void *d_image, uint64_t nblocks, uint32_t **d_row_slot_out,
         count_launch();
         DBT_KERNEL_CHECK();
         *d_row_slot_out = slots;
+        info->blk_nres = d_nres;
+        info->blk_row_off = row_off;
     }
     return 0;
 }
@@ -225,6 +229,7 @@ __device__ __forceinline__ uint32_t ex_smem_u32(const void *p) { return (uint32_
 template <int FIELD>
 __global__ void __launch_bounds__(kExThreads)
 extract_stream_kernel(const uint32_t *__restrict__ img, uint64_t nblocks, uint64_t nrows, uint32_t kw,
+                      const uint32_t *__restrict__ blk_nres, const uint32_t *__restrict__ blk_row_off,
                       uint32_t *__restrict__ out_w0, uint32_t *__restrict__ out_str, uint32_t *__restrict__ out_recid,
                       ExtractStats *stats) {
     extern __shared__ __align__(128) unsigned char ex_raw[];
@@ -272,8 +277,9 @@ extract_stream_kernel(const uint32_t *__restrict__ img, uint64_t nblocks, uint64
                          : "memory");
         const uint64_t b = first + k * step;
         const uint32_t *blk = stage[sidx];
-        const uint64_t row = b * kRpb + tid;
-        const bool live = tid < (int)kRpb && row < nrows;
+        // block-dense images: row = 100 b + entry; ragged images: the block's row offset comes from the header scan
+        const uint64_t row = (blk_row_off ? (uint64_t)blk_row_off[b] : b * kRpb) + tid;
+        const bool live = blk_nres ? (tid < (int)blk_nres[b]) : (tid < (int)kRpb && row < nrows);
         const uint32_t *rec = blk + kEntriesWord + (live ? tid : 0) * kRecWords;
         if (live) {
             const uint32_t recid = rec[0];
@@ -286,7 +292,12 @@ extract_stream_kernel(const uint32_t *__restrict__ img, uint64_t nblocks, uint64
             a_id &= recid;
             uint32_t prev = recid;
             if (tid > 0) prev = rec[-(int)kRecWords];
-            else if (b > 0) prev = img[(b - 1) * kBlockWords + kEntriesWord + (kRpb - 1) * kRecWords];
+            else if (b > 0) { // last live row of the nearest earlier non-empty block
+                uint64_t pb = b - 1;
+                uint32_t pn = blk_nres ? blk_nres[pb] : kRpb;
+                while (pn == 0 && pb > 0) pn = blk_nres[--pb];
+                if (pn) prev = img[pb * kBlockWords + kEntriesWord + (pn - 1) * kRecWords];
+            }
             unsorted |= recid < prev;
         }
         if (HAS_STR) { // whole warps take part: the per-word OR/AND go through warp reductions
@@ -340,7 +351,8 @@ extract_stream_kernel(const uint32_t *__restrict__ img, uint64_t nblocks, uint64
 }
 
 template <int FIELD>
-static int launch_extract_stream(const uint32_t *img, uint64_t nblocks, uint64_t nrows, uint32_t kw, uint32_t *d_w0,
+static int launch_extract_stream(const uint32_t *img, uint64_t nblocks, uint64_t nrows, uint32_t kw,
+                                 const uint32_t *blk_nres, const uint32_t *blk_row_off, uint32_t *d_w0,
                                  uint32_t *d_str, uint32_t *d_recid, ExtractStats *d_stats, cudaStream_t st) {
     size_t smem = sizeof(uint32_t) * kBlockWords * kExStages + 8 * kExStages + 128;
     auto kfn = extract_stream_kernel<FIELD>;
@@ -350,24 +362,28 @@ static int launch_extract_stream(const uint32_t *img, uint64_t nblocks, uint64_t
         attr_done = true;
     }
     int grid = (int)std::min<uint64_t>(nblocks, 148 * 5);
-    kfn<<<grid, kExThreads, smem, st>>>(img, nblocks, nrows, kw, d_w0, d_str, d_recid, d_stats);
+    kfn<<<grid, kExThreads, smem, st>>>(img, nblocks, nrows, kw, blk_nres, blk_row_off, d_w0, d_str, d_recid, d_stats);
     return 0;
 }
 
-int extract_keys(const void *d_image, uint64_t nrows, const uint32_t *d_row_slot, int field, uint32_t kw,
-                 uint32_t *d_w0, uint32_t *d_str, uint32_t *d_recid, ExtractStats *d_stats, cudaStream_t st) {
+int extract_keys(const void *d_image, uint64_t nblocks_img, uint64_t nrows, const uint32_t *d_row_slot,
+                 const uint32_t *d_blk_nres, const uint32_t *d_blk_row_off, int field, uint32_t kw, uint32_t *d_w0,
+                 uint32_t *d_str, uint32_t *d_recid, ExtractStats *d_stats, cudaStream_t st) {
     StageScope sc(ST_EXTRACT, st);
     init_stats_kernel<<<1, 128, 0, st>>>(d_stats);
     count_launch();
-    const bool stream_ok = (d_row_slot == nullptr) && ((uintptr_t)d_image % 16 == 0) && getenv("DBT_EXTRACT_STRIDED") == nullptr;
+    const bool ragged = d_row_slot != nullptr;
+    const bool stream_ok = (!ragged || (d_blk_nres && d_blk_row_off)) && ((uintptr_t)d_image % 16 == 0) &&
+                           getenv("DBT_EXTRACT_STRIDED") == nullptr;
     if (nrows && stream_ok) {
         const uint32_t *img = (const uint32_t *)d_image;
-        const uint64_t nblocks = (nrows + kRpb - 1) / kRpb;
+        const uint64_t nblocks = ragged ? nblocks_img : (nrows + kRpb - 1) / kRpb;
+        const uint32_t *bn = ragged ? d_blk_nres : nullptr, *bo = ragged ? d_blk_row_off : nullptr;
         switch (field) {
-        case '0': DBT_TRY(launch_extract_stream<0>(img, nblocks, nrows, kw, d_w0, d_str, d_recid, d_stats, st)); break;
-        case '1': DBT_TRY(launch_extract_stream<1>(img, nblocks, nrows, kw, d_w0, d_str, d_recid, d_stats, st)); break;
-        case '2': DBT_TRY(launch_extract_stream<2>(img, nblocks, nrows, kw, d_w0, d_str, d_recid, d_stats, st)); break;
-        case '3': DBT_TRY(launch_extract_stream<3>(img, nblocks, nrows, kw, d_w0, d_str, d_recid, d_stats, st)); break;
+        case '0': DBT_TRY(launch_extract_stream<0>(img, nblocks, nrows, kw, bn, bo, d_w0, d_str, d_recid, d_stats, st)); break;
+        case '1': DBT_TRY(launch_extract_stream<1>(img, nblocks, nrows, kw, bn, bo, d_w0, d_str, d_recid, d_stats, st)); break;
+        case '2': DBT_TRY(launch_extract_stream<2>(img, nblocks, nrows, kw, bn, bo, d_w0, d_str, d_recid, d_stats, st)); break;
+        case '3': DBT_TRY(launch_extract_stream<3>(img, nblocks, nrows, kw, bn, bo, d_w0, d_str, d_recid, d_stats, st)); break;
         default: set_error("bad field"); return DBT_ERR_ARG;
         }
         count_launch();

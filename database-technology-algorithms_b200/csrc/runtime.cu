@@ -163,6 +163,32 @@ int dbt_ipc_alloc(size_t bytes, void **d_ptr, unsigned char handle[64]) {
     memcpy(handle, &h, 64);
     return 0;
 }
+int dbt_ipc_export(const void *d_ptr, unsigned char handle[64], uint64_t *offset) {
+    // cudaIpcGetMemHandle wants the allocation's base pointer: ask the driver for the address range
+    typedef int (*range_fn)(unsigned long long *, size_t *, unsigned long long);
+    static range_fn fn = nullptr;
+    if (!fn) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        DBT_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &sym, cudaEnableDefault, &q));
+        fn = (range_fn)sym;
+        if (!fn) {
+            set_error("cuMemGetAddressRange unavailable");
+            return DBT_ERR_CUDA;
+        }
+    }
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (fn(&base, &size, (unsigned long long)(uintptr_t)d_ptr) != 0) {
+        set_error("dbt_ipc_export: pointer is not inside a device allocation");
+        return DBT_ERR_ARG;
+    }
+    cudaIpcMemHandle_t h;
+    DBT_CUDA(cudaIpcGetMemHandle(&h, (void *)(uintptr_t)base));
+    memcpy(handle, &h, 64);
+    *offset = (uint64_t)((uintptr_t)d_ptr - base);
+    return 0;
+}
 int dbt_ipc_open(const unsigned char handle[64], void **d_ptr) {
     cudaIpcMemHandle_t h;
     memcpy(&h, handle, 64);

@@ -84,6 +84,47 @@ class LocalOps:
         """Same kernel, output given as a raw device address (a peer's receive buffer mapped over NVLink)."""
         self.dbt.check(self.L.dbt_gather_records(img.data_ptr(), rows.data_ptr(), None, rows.numel(), out_ptr, self._stream()))
 
+    # -- columns for the "rows stay put" sort / dedup ------------------------------------------------
+    def extract_key_recid(self, img, nblocks: int, field: str):
+        t = self.torch
+        keys = t.empty(max(nblocks * RPB, 1), dtype=t.int32, device=self.device)
+        recids = t.empty_like(keys)
+        wsb = self.dbt.dev_ws_bytes(self.dbt.OP_SORT, nblocks, 0, field)
+        ws = self.workspace(wsb)
+        n, dense = C.c_uint64(), C.c_int()
+        self.dbt.check(self.L.dbt_dev_extract_key_recid_u32(img.data_ptr(), nblocks, ord(field), keys.data_ptr(),
+                                                            recids.data_ptr(), ws.data_ptr(), wsb, self._stream(),
+                                                            C.byref(n), C.byref(dense)))
+        return keys[: n.value], recids[: n.value], bool(dense.value)
+
+    def take(self, src, idx):
+        out = self.torch.empty_like(idx)
+        self.dbt.check(self.L.dbt_dev_take_u32(src.data_ptr(), idx.data_ptr(), idx.numel(), out.data_ptr(), self._stream()))
+        return out
+
+    def order_columns(self, keys, recids, dedup: bool):
+        m = keys.numel()
+        order = self.torch.empty(max(m, 1), dtype=self.torch.int32, device=self.device)
+        wsb = self.L.dbt_dev_order_columns_ws_bytes(m)
+        ws = self.workspace(wsb)
+        cnt = C.c_uint64()
+        self.dbt.check(self.L.dbt_dev_order_columns(keys.data_ptr(), recids.data_ptr(), m, 1 if dedup else 0, order.data_ptr(),
+                                                    C.byref(cnt), ws.data_ptr(), wsb, self._stream()))
+        return order, cnt.value
+
+    def gather_multi(self, bases, seg_start, order, rrow, count: int, out_img):
+        P = len(bases)
+        hb = (C.c_void_p * P)(*[C.c_void_p(int(b)) for b in bases])
+        hs = (C.c_uint64 * (P + 1))(*[int(x) for x in seg_start])
+        self.dbt.check(self.L.dbt_gather_records_multi(hb, P, hs, order.data_ptr(), rrow.data_ptr(), count, out_img.data_ptr(),
+                                                       self._stream()))
+
+    def ipc_export(self, tensor):
+        handle = C.create_string_buffer(64)
+        off = C.c_uint64()
+        self.dbt.check(self.L.dbt_ipc_export(tensor.data_ptr(), handle, C.byref(off)))
+        return handle.raw, off.value
+
     # -- peer memory -----------------------------------------------------------------------------
     def ipc_alloc(self, nbytes: int):
         ptr = C.c_void_p()
@@ -170,6 +211,76 @@ class DistOps:
             peer_exchange = hasattr(ops, "ipc_alloc") and os.environ.get("DBT_DIST_EXCHANGE", "p2p") == "p2p"
         self.peer_exchange = bool(peer_exchange) and self.world > 1
         self._recv = {}  # slot -> (capacity bytes, own ptr, [peer ptrs])
+        self._opened = {}  # IPC handle bytes -> mapped base pointer
+        self.rows_stay_put = self.peer_exchange and os.environ.get("DBT_DIST_SORT", "keys") == "keys"
+
+    def _peer_image_bases(self, img):
+        """Device pointers to every rank's input image (this rank's own, the others mapped over NVLink)."""
+        torch, dist, P = self.torch, self.dist, self.world
+        try:
+            handle, off = self.ops.ipc_export(img)
+            ok = 1
+        except Exception:  # noqa: BLE001  (e.g. memory from a VMM allocator cannot be exported)
+            handle, off, ok = bytes(64), 0, 0
+        rec = torch.tensor(list(handle) + list(int(off).to_bytes(8, "little")) + [ok], dtype=torch.uint8, device=self.ops.device)
+        allr = [torch.empty_like(rec) for _ in range(P)]
+        dist.all_gather(allr, rec, group=self.group)
+        rows = [bytes(t.cpu().tolist()) for t in allr]
+        if not all(r[72] for r in rows):
+            return None
+        bases = []
+        for r in range(P):
+            if r == self.rank:
+                bases.append(img.data_ptr())
+                continue
+            h, o = rows[r][:64], int.from_bytes(rows[r][64:72], "little")
+            if h not in self._opened:
+                self._opened[h] = self.ops.ipc_open(h)
+            bases.append(self._opened[h] + o)
+        return bases
+
+    def _sort_rows_stay_put(self, img, nblocks: int, field: str, dedup: bool):
+        """Sort / dedup where only (key, recid, row) columns are exchanged (12 B per row) and every rank's
+        final gather pulls the records it owns straight out of the peers' input images over NVLink."""
+        torch, dist, P = self.torch, self.dist, self.world
+        keys, recids, dense = self.ops.extract_key_recid(img, nblocks, field)
+        flag = torch.tensor([1 if dense else 0], dtype=torch.int32, device=self.ops.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        bases = self._peer_image_bases(img) if int(flag.item()) else None
+        if bases is None:
+            return None  # ragged image somewhere, or memory that cannot be mapped: use the record exchange
+        splitters = self.splitters_from(self.ops.sample_keys(keys, self.samples_per_rank))
+        rows, counts = self.ops.partition(keys, 0, splitters, P)
+        skey, srec = self.ops.take(keys, rows), self.ops.take(recids, rows)
+        sc = torch.tensor(counts, dtype=torch.int64, device=self.ops.device)
+        rc = torch.empty_like(sc)
+        dist.all_to_all_single(rc, sc, group=self.group)
+        rcounts = [int(x) for x in rc.cpu().tolist()]
+        m = sum(rcounts)
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+        recv = []
+        for col in (skey, srec, rows):
+            r = torch.empty(max(m, 1), dtype=torch.int32, device=self.ops.device)[:m]
+            dist.all_to_all_single(r, col, rcounts, counts, group=self.group)
+            recv.append(r)
+        ev[1].record()
+        rkey, rrec, rrow = recv
+        order, cnt = self.ops.order_columns(rkey, rrec, dedup)
+        out = self.ops.alloc(((cnt + RPB - 1) // RPB) * BLOCK_BYTES)
+        seg = [0]
+        for c in rcounts:
+            seg.append(seg[-1] + c)
+        gev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        gev[0].record()
+        self.ops.gather_multi(bases, seg, order, rrow, cnt, out)
+        gev[1].record()
+        dist.barrier(group=self.group)  # nobody may touch its input image before every peer has read it
+        remote_rows = m - rcounts[self.rank]
+        self.last_exchange = {"bytes_sent_remote": 12 * (sum(counts) - counts[self.rank]), "bytes_sent": 12 * sum(counts),
+                              "events": ev, "gather_events": gev, "mode": "keys+remote-gather",
+                              "remote_record_bytes_read": int(remote_rows * (cnt / max(m, 1)) * 140), "splitters": splitters}
+        return out, {"rows": m, "out_rows": cnt}
 
     def _peer_buffers(self, slot: int, need_bytes: int):
         """Receive buffer `slot` of every rank, mapped here; (re)allocated collectively when too small."""
@@ -268,10 +379,18 @@ class DistOps:
 
     # -- operators ------------------------------------------------------------------------------
     def sort(self, img, nblocks: int, field: str):
+        if self.rows_stay_put:
+            r = self._sort_rows_stay_put(img, nblocks, field, dedup=False)
+            if r is not None:
+                return r
         recv, nb = self.exchange(img, nblocks, field, mode=0)
         return self.ops.run("sort", field, recv, nb)
 
     def dedup(self, img, nblocks: int, field: str):
+        if self.rows_stay_put:
+            r = self._sort_rows_stay_put(img, nblocks, field, dedup=True)
+            if r is not None:
+                return r
         recv, nb = self.exchange(img, nblocks, field, mode=0)
         return self.ops.run("dedup", field, recv, nb)
 

@@ -141,6 +141,27 @@ size_t dbt_dev_partition_ws_bytes(uint64_t nblocks);
  * its 64-byte handle is handed to the other ranks (any transport), and they map it with dbt_ipc_open.
  * dbt_gather_records then takes the mapped pointer as its output image: the gather kernel's 16-byte
  * stores travel over NVLink straight into the owner's HBM -- no send buffer, no separate collective. */
+/* Multi-GPU sort / dedup without moving records twice ("rows stay put"): only (key, recid, row) columns
+ * are exchanged; the owner of a key range orders what it received with dbt_dev_order_columns and then
+ * pulls the winning records straight out of the peers' input images (mapped with dbt_ipc_export /
+ * dbt_ipc_open) into their final positions with dbt_gather_records_multi.  u32 keys. */
+int dbt_dev_extract_key_recid_u32(const void *d_in, uint64_t nblocks, int field, uint32_t *d_keys, uint32_t *d_recids,
+                                  void *d_ws, size_t ws_bytes, void *stream, uint64_t *nrows, int *block_dense);
+/* out[i] = src[idx[i]] */
+int dbt_dev_take_u32(const uint32_t *d_src, const uint32_t *d_idx, uint64_t n, uint32_t *d_out, void *stream);
+/* Order m (key, recid) tuples by (key, recid) (stable beyond that) and optionally keep the first of every key:
+ * d_order receives indices into the input columns, *count their number.  d_keys is clobbered. */
+int dbt_dev_order_columns(uint32_t *d_keys, const uint32_t *d_recids, uint64_t m, int dedup, uint32_t *d_order,
+                          uint64_t *count, void *d_ws, size_t ws_bytes, void *stream);
+size_t dbt_dev_order_columns_ws_bytes(uint64_t m);
+/* Record gather from several (block-dense) images: output row j is row d_row[d_order[j]] of image s, where s is
+ * the segment of the received columns that index d_order[j] falls into (h_seg_start[nsrc+1], host memory);
+ * h_bases[nsrc] are device pointers (local or peer-mapped). */
+int dbt_gather_records_multi(const void *const *h_bases, uint32_t nsrc, const uint64_t *h_seg_start,
+                             const uint32_t *d_order, const uint32_t *d_row, uint64_t count, void *d_out, void *stream);
+
+/* handle + byte offset of any device pointer inside a cudaMalloc allocation (for mapping on the peers) */
+int dbt_ipc_export(const void *d_ptr, unsigned char handle[64], uint64_t *offset);
 int dbt_ipc_alloc(size_t bytes, void **d_ptr, unsigned char handle[64]);
 int dbt_ipc_open(const unsigned char handle[64], void **d_ptr);
 int dbt_ipc_close(void *d_ptr);
