@@ -383,6 +383,13 @@ def bench_dist(args, dbt, rank, world, local_rank):
     a2a = torch.tensor([a2a_ms, float(xbytes)], device=dev, dtype=torch.float64)
     dist.all_reduce(a2a, op=dist.ReduceOp.MAX)
     stages, clocks = {}, None
+    timeline = None
+    if rank == 0 and "timeline" in d.last_exchange:
+        tl = d.last_exchange["timeline"]
+        timeline = {name: round(tl[0][1].elapsed_time(e), 3) for name, e in tl}
+        pe = d.last_exchange["events"]
+        timeline["push_start"] = round(tl[0][1].elapsed_time(pe[0]), 3)
+        timeline["push_end"] = round(tl[0][1].elapsed_time(pe[1]), 3)
     if rank == 0:
         stages = dbt.stage_report()
         L.dbt_stage_timing_enable(0)
@@ -451,6 +458,7 @@ def bench_dist(args, dbt, rank, world, local_rank):
             "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": workload_config(args, world),
             "e2e": e2e, "roofline": roofline, "nvlink": nvlink, "cpu_baseline": None, "clocks": clocks,
             "gpu_launches": launches, "stage_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in stages.items()},
+            "timeline_ms_last_step_rank0": timeline,
         }
         print(json.dumps(line))
     dist.barrier()

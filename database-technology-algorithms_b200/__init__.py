@@ -26,7 +26,7 @@ OP_SORT, OP_DEDUP, OP_MERGEJOIN, OP_HASHJOIN = 0, 1, 2, 3
 C_ABI_SYMBOLS = [
     "dbt_last_error", "dbt_abi_version", "dbt_device_count",
     "dbt_sort_counters", "dbt_dedup_nios", "dbt_hashjoin_nios", "dbt_mergejoin_nios",
-    "dbt_sort_pairs_ws_bytes", "dbt_sort_pairs_u32", "dbt_gather_records",
+    "dbt_sort_pairs_ws_bytes", "dbt_sort_pairs_u32", "dbt_gather_records", "dbt_gather_records_limited",
     "dbt_dev_extract_keys_u32", "dbt_dev_partition_rows", "dbt_dev_partition_ws_bytes",
     "dbt_dev_ws_bytes", "dbt_dev_ws_bytes_kw", "dbt_dev_mergesort", "dbt_dev_dedup", "dbt_dev_mergejoin", "dbt_dev_hashjoin",
     "dbt_host_mergesort", "dbt_host_dedup", "dbt_host_mergejoin", "dbt_host_hashjoin",
@@ -80,6 +80,7 @@ def lib() -> C.CDLL:
     L.dbt_sort_pairs_ws_bytes.argtypes = [u64]
     L.dbt_sort_pairs_u32.argtypes = [vp, vp, vp, vp, u64, ci, ci, vp, sz, vp, C.POINTER(ci)]
     L.dbt_gather_records.argtypes = [vp, vp, vp, u64, vp, vp]
+    L.dbt_gather_records_limited.argtypes = [vp, vp, vp, u64, vp, vp, ci]
     L.dbt_dev_ws_bytes.restype = sz
     L.dbt_dev_ws_bytes.argtypes = [ci, u64, u64, ci]
     L.dbt_dev_ws_bytes_kw.restype = sz

@@ -141,7 +141,7 @@ int compact_select(const uint32_t *d_counts, const uint32_t *d_values, uint64_t 
 int exclusive_offsets(const uint32_t *d_counts, uint64_t n, uint32_t *d_off, uint64_t *d_total, Arena &ws,
                       cudaStream_t st);
 int gather_records(const void *d_in, const uint32_t *d_rows, const uint32_t *d_row_slot, uint64_t nrows_out,
-                   void *d_out, cudaStream_t st);
+                   void *d_out, cudaStream_t st, int max_ctas = 0);
 
 // joins (kernels_join.cu)
 size_t hash_table_slots(uint64_t nr);

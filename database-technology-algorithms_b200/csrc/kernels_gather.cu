@@ -340,7 +340,8 @@ gather_multi_kernel(MultiSrc ms, const uint32_t *__restrict__ order, const uint3
             const uint32_t idx = order[r0 + tid];
             uint32_t s = 0;
             while (s + 1 < ms.nsrc && (unsigned long long)idx >= ms.seg_start[s + 1]) ++s;
-            src[tid] = ms.base[s] + slot_word(rrow[idx]);
+            const uint64_t row = rrow ? (uint64_t)rrow[idx] : (uint64_t)idx - ms.seg_start[s]; // null: k-th tuple <-> k-th row
+            src[tid] = ms.base[s] + slot_word(row);
         }
         if (tid == 0) {
             stage[0] = (uint32_t)ob;
@@ -400,11 +401,11 @@ take_kernel(const uint32_t *__restrict__ src, const uint32_t *__restrict__ idx, 
 }
 
 int gather_records(const void *d_in, const uint32_t *d_rows, const uint32_t *d_row_slot, uint64_t nrows_out, void *d_out,
-                   cudaStream_t st) {
+                   cudaStream_t st, int max_ctas) {
     StageScope sc(ST_GATHER, st);
     if (nrows_out == 0) return 0;
     uint64_t nb = (nrows_out + kRpb - 1) / kRpb;
-    int grid = (int)std::min<uint64_t>(nb, 148 * 8 * 4);
+    int grid = (int)std::min<uint64_t>(nb, max_ctas > 0 ? (uint64_t)max_ctas : 148 * 8 * 4);
     gather_kernel<<<grid, kGatherThreads, 0, st>>>((const uint32_t *)d_in, d_rows, d_row_slot, nrows_out, (uint4 *)d_out,
                                                    nb);
     count_launch();
@@ -452,5 +453,14 @@ extern "C" int dbt_gather_records(const void *d_in_image, const uint32_t *d_rows
         dbt::set_error("dbt_gather_records: NULL image");
         return DBT_ERR_ARG;
     }
-    return dbt::gather_records(d_in_image, d_rows, d_row_slot, nrows_out, d_out_image, (cudaStream_t)stream);
+    return dbt::gather_records(d_in_image, d_rows, d_row_slot, nrows_out, d_out_image, (cudaStream_t)stream, 0);
+}
+
+extern "C" int dbt_gather_records_limited(const void *d_in_image, const uint32_t *d_rows, const uint32_t *d_row_slot,
+                                          uint64_t nrows_out, void *d_out_image, void *stream, int max_ctas) {
+    if (!d_in_image || !d_out_image) {
+        dbt::set_error("dbt_gather_records_limited: NULL image");
+        return DBT_ERR_ARG;
+    }
+    return dbt::gather_records(d_in_image, d_rows, d_row_slot, nrows_out, d_out_image, (cudaStream_t)stream, max_ctas);
 }

@@ -79,6 +79,10 @@ int dbt_sort_pairs_u32(uint32_t *d_keys, uint32_t *d_keys_alt, uint32_t *d_vals,
  * d_row_slot may be NULL when every input block except the last is full (slot == row). */
 int dbt_gather_records(const void *d_in_image, const uint32_t *d_rows, const uint32_t *d_row_slot, uint64_t nrows_out,
                        void *d_out_image, void *stream);
+/* same, with the grid capped at max_ctas CTAs (0 = no cap): for link-bound gathers (output in peer memory) that
+ * should leave SMs to kernels running concurrently on other streams */
+int dbt_gather_records_limited(const void *d_in_image, const uint32_t *d_rows, const uint32_t *d_row_slot,
+                               uint64_t nrows_out, void *d_out_image, void *stream, int max_ctas);
 
 /* ----------------------------------------------------------------------------------------------
  * Device-scope operators: image in HBM -> image in HBM.  `d_out` must hold
@@ -156,7 +160,8 @@ int dbt_dev_order_columns(uint32_t *d_keys, const uint32_t *d_recids, uint64_t m
 size_t dbt_dev_order_columns_ws_bytes(uint64_t m);
 /* Record gather from several (block-dense) images: output row j is row d_row[d_order[j]] of image s, where s is
  * the segment of the received columns that index d_order[j] falls into (h_seg_start[nsrc+1], host memory);
- * h_bases[nsrc] are device pointers (local or peer-mapped). */
+ * h_bases[nsrc] are device pointers (local or peer-mapped).  d_row == NULL means the k-th index of segment s is
+ * row k of image s (the images were filled in the same order as the columns). */
 int dbt_gather_records_multi(const void *const *h_bases, uint32_t nsrc, const uint64_t *h_seg_start,
                              const uint32_t *d_order, const uint32_t *d_row, uint64_t count, void *d_out, void *stream);
 
