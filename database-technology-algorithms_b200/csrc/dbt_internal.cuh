@@ -150,7 +150,7 @@ int hash_join_counts(const KeyCols &r, const KeyCols &s, int field, uint32_t *d_
 // sorted unique row lists of R and S -> per-R-unique-row 0/1 match flags, and the reference walk's read count
 int intersect_sorted(const KeyCols &r, const uint32_t *d_ur, const uint32_t *d_urkeys, uint64_t nur, const KeyCols &s,
                      const uint32_t *d_us, const uint32_t *d_uskeys, uint64_t nus, int field, uint32_t *d_flags,
-                     uint64_t *d_later_reads, cudaStream_t st);
+                     uint64_t *d_later_reads, Arena &ws, cudaStream_t st);
 
 // generator (kernels_gen.cu)
 int gen_syn(uint64_t seed, uint64_t n_total, uint64_t U, int kind, uint64_t row0, uint64_t nrows, uint32_t recid0,

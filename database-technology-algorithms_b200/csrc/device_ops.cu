@@ -151,6 +151,8 @@ extern "C" size_t dbt_dev_ws_bytes_kw(int op, uint64_t nbr, uint64_t nbs, int fi
     case DBT_OP_MERGEJOIN:
         b += rel_bytes(nbr, field, kw, true) + rel_bytes(nbs, field, kw, true) + 2 * pad256(4 * nr) + 2 * pad256(4 * ns) +
              2 * pad256(4 * nr) + scan + 4096;
+        if (field >= '2') b += pad256(4 * (kw + 1) * nr) + pad256(4 * (kw + 1) * ns); // contiguous sorted keys for the merge path
+        b += pad256(8 * ((nr + ns) / 1024 + 2));
         break;
     case DBT_OP_HASHJOIN:
         b += rel_bytes(nbr, field, kw, false) + rel_bytes(nbs, field, kw, false) + 2 * pad256(4 * hash_table_slots(nr)) +
@@ -458,7 +460,7 @@ extern "C" int dbt_dev_mergejoin(const void *d_in_r, uint64_t nbr, const void *d
             set_error("mergejoin: workspace too small");
             return DBT_ERR_WORKSPACE;
         }
-        DBT_TRY(intersect_sorted(pr.keys, ur, urk, nur, ps.keys, us, usk, nus, field, flags, d_res + 1, st));
+        DBT_TRY(intersect_sorted(pr.keys, ur, urk, nur, ps.keys, us, usk, nus, field, flags, d_res + 1, ws, st));
         DBT_TRY(compact_select(flags, ur, nur, mrows, nur, d_res, ws, st));
         uint64_t h[2];
         DBT_TRY(read_u64(d_res, h, 2, st));

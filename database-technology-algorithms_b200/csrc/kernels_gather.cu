@@ -186,6 +186,36 @@ struct UniqueCountRows {
     RowKeyEq eq;
     __device__ void load(uint64_t i0, uint64_t n, uint32_t c[8], uint32_t pay[8]) const {
         load8(perm, i0, n, pay);
+        if (eq.str && eq.kw == 8) {
+            // 32-byte string keys: fetch each row's key once (two 16-byte loads) and carry it in registers as the
+            // "previous key" of the next position -- the generic path below would fetch every key twice
+            uint4 pa, pb;
+            uint32_t pw = 0;
+            const uint32_t prow = (i0 > 0 && i0 < n) ? perm[i0 - 1] : 0u;
+            {
+                const uint4 *kp = reinterpret_cast<const uint4 *>(eq.str + (uint64_t)prow * 8);
+                pa = kp[0];
+                pb = kp[1];
+                if (eq.w0) pw = eq.w0[prow];
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (i0 + k < n) {
+                    const uint4 *kp = reinterpret_cast<const uint4 *>(eq.str + (uint64_t)pay[k] * 8);
+                    const uint4 a = kp[0], b = kp[1];
+                    const uint32_t w = eq.w0 ? eq.w0[pay[k]] : 0u;
+                    const bool same = (i0 + k > 0) && w == pw && a.x == pa.x && a.y == pa.y && a.z == pa.z && a.w == pa.w &&
+                                      b.x == pb.x && b.y == pb.y && b.z == pb.z && b.w == pb.w;
+                    c[k] = same ? 0u : 1u;
+                    pa = a;
+                    pb = b;
+                    pw = w;
+                } else {
+                    c[k] = 0u;
+                }
+            }
+            return;
+        }
         uint32_t prev = (i0 > 0 && i0 < n) ? perm[i0 - 1] : 0u;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {

@@ -363,17 +363,122 @@ __global__ void walk_reads_kernel(SortedList r, SortedList s, unsigned long long
     *out = reads;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Merge-path intersection of two sorted unique key arrays A[na][kw], B[nb][kw] (contiguous).
+// The merge path (A before B on ties) is cut into tiles of kMpTile merged elements by one binary
+// search per tile; a CTA then holds its tile's B range (+1 element) in shared memory and every A
+// element of the tile finds its equal, if any, by a short search there.  Both inputs are read once,
+// sequentially: (kw*4) bytes per element instead of ~10 random 128-byte lines per binary search.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMpTile = 1024;
+constexpr int kMpThreads = 256;
+
+__device__ __forceinline__ int key_cmp(const uint32_t *a, const uint32_t *b, uint32_t kw) {
+    for (uint32_t j = 0; j < kw; ++j)
+        if (a[j] != b[j]) return a[j] < b[j] ? -1 : 1;
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+mp_partition_kernel(const uint32_t *__restrict__ A, uint64_t na, const uint32_t *__restrict__ B, uint64_t nb, uint32_t kw,
+                    uint64_t ntiles, unsigned long long *__restrict__ a_start /*[ntiles+1]*/) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > ntiles) return;
+    uint64_t d = min(t * (uint64_t)kMpTile, na + nb);
+    uint64_t lo = d > nb ? d - nb : 0, hi = min(d, na);
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1; // candidate: mid elements of A, d-mid of B
+        if (key_cmp(A + mid * kw, B + (d - 1 - mid) * kw, kw) <= 0) lo = mid + 1; // A[mid] precedes B[d-1-mid]: take more of A
+        else hi = mid;
+    }
+    a_start[t] = lo;
+}
+
+__global__ void __launch_bounds__(kMpThreads)
+mp_intersect_kernel(const uint32_t *__restrict__ A, uint64_t na, const uint32_t *__restrict__ B, uint64_t nb, uint32_t kw,
+                    const unsigned long long *__restrict__ a_start, uint32_t *__restrict__ flags) {
+    extern __shared__ uint32_t sb[]; // (kMpTile + 1) * kw words
+    const uint64_t t = blockIdx.x;
+    const uint64_t a0 = a_start[t], a1 = a_start[t + 1];
+    const uint64_t d0 = min(t * (uint64_t)kMpTile, na + nb), d1 = min((t + 1) * (uint64_t)kMpTile, na + nb);
+    const uint64_t b0 = d0 - a0, b1 = min(d1 - a1 + 1, nb); // one extra B element: the equal of the tile's last A may be there
+    const uint32_t nbw = (uint32_t)((b1 > b0 ? b1 - b0 : 0) * kw);
+    for (uint32_t i = threadIdx.x; i < nbw; i += kMpThreads) sb[i] = B[b0 * kw + i];
+    __syncthreads();
+    const uint32_t cntb = nbw / kw;
+    for (uint64_t i = a0 + threadIdx.x; i < a1; i += kMpThreads) {
+        const uint32_t *ka = A + i * kw;
+        uint32_t lo = 0, hi = cntb;
+        while (lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (key_cmp(sb + mid * kw, ka, kw) < 0) lo = mid + 1;
+            else hi = mid;
+        }
+        flags[i] = (lo < cntb && key_cmp(sb + lo * kw, ka, kw) == 0) ? 1u : 0u;
+    }
+}
+
+// contiguous copy of the keys of a sorted row list: out[i] = (w0[row], str[row][0..kw))
+__global__ void __launch_bounds__(256)
+gather_keys_kernel(KeyView kv, const uint32_t *__restrict__ rows, uint64_t n, uint32_t kwt, uint32_t *__restrict__ out) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t row = rows[i];
+        uint32_t *o = out + i * kwt;
+        uint32_t j = 0;
+        if (kv.w0) o[j++] = kv.w0[row];
+        if (kv.str) {
+            const uint32_t *p = kv.str + (uint64_t)row * kv.kw;
+            for (uint32_t q = 0; q < kv.kw; ++q) o[j + q] = p[q];
+        }
+    }
+}
+
 int intersect_sorted(const KeyCols &r, const uint32_t *d_ur, const uint32_t *d_urkeys, uint64_t nur, const KeyCols &s,
                      const uint32_t *d_us, const uint32_t *d_uskeys, uint64_t nus, int field, uint32_t *d_flags,
-                     uint64_t *d_later_reads, cudaStream_t st) {
+                     uint64_t *d_later_reads, Arena &ws, cudaStream_t st) {
     StageScope sc(ST_INTERSECT, st);
     const bool one = (field == '0' || field == '1');
     SortedList a{one ? d_urkeys : nullptr, d_ur, KeyView{field == '2' ? nullptr : r.w0, r.str, r.kw}, nur};
     SortedList b{one ? d_uskeys : nullptr, d_us, KeyView{field == '2' ? nullptr : s.w0, s.str, s.kw}, nus};
-    if (nur) {
-        int grid = (int)std::min<uint64_t>((nur + 255) / 256, 148 * 16);
-        intersect_kernel<<<grid, 256, 0, st>>>(a, b, d_flags);
-        count_launch();
+    if (nur && nus == 0) {
+        DBT_CUDA(cudaMemsetAsync(d_flags, 0, 4 * nur, st));
+    } else if (nur) {
+        const uint32_t kwt = one ? 1u : ((field == '2' ? 0u : 1u) + r.kw);
+        const uint32_t *A = d_urkeys, *B = d_uskeys;
+        size_t m0 = ws.mark();
+        bool ok = true;
+        if (!one) { // multi-word keys: make the two sorted key lists contiguous first (one random 32-byte read per key)
+            uint32_t *ca = ws.take<uint32_t>(nur * kwt), *cb = ws.take<uint32_t>(nus * kwt);
+            if (!ca || !cb) ok = false;
+            else {
+                int ga = (int)std::min<uint64_t>((nur + 255) / 256, 148 * 16), gb2 = (int)std::min<uint64_t>((nus + 255) / 256, 148 * 16);
+                gather_keys_kernel<<<ga, 256, 0, st>>>(a.kv, d_ur, nur, kwt, ca);
+                gather_keys_kernel<<<gb2, 256, 0, st>>>(b.kv, d_us, nus, kwt, cb);
+                count_launch(2);
+                A = ca;
+                B = cb;
+            }
+        }
+        const uint64_t ntiles = (nur + nus + kMpTile - 1) / kMpTile;
+        unsigned long long *a_start = ok ? ws.take<unsigned long long>(ntiles + 1) : nullptr;
+        const size_t smem = (size_t)(kMpTile + 1) * kwt * 4;
+        if (ok && a_start && smem <= 200 * 1024) {
+            mp_partition_kernel<<<(unsigned)((ntiles + 1 + 255) / 256), 256, 0, st>>>(A, nur, B, nus, kwt, ntiles, a_start);
+            static bool attr_done = false;
+            if (!attr_done) {
+                DBT_CUDA(cudaFuncSetAttribute(mp_intersect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                attr_done = true;
+            }
+            mp_intersect_kernel<<<(unsigned)ntiles, kMpThreads, smem, st>>>(A, nur, B, nus, kwt, a_start, d_flags);
+            count_launch(2);
+        } else { // not enough workspace for the contiguous copies: binary search through the row lists
+            int grid = (int)std::min<uint64_t>((nur + 255) / 256, 148 * 16);
+            intersect_kernel<<<grid, 256, 0, st>>>(a, b, d_flags);
+            count_launch();
+        }
+        DBT_KERNEL_CHECK();
+        ws.release(m0);
     }
     walk_reads_kernel<<<1, 1, 0, st>>>(a, b, (unsigned long long *)d_later_reads);
     count_launch();
