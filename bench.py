@@ -518,6 +518,47 @@ def extra_measurements(dbt, torch, dev, peak):
         torch.cuda.empty_cache()
     except Exception as e:  # noqa: BLE001
         out["pair_sort_1B_u32"] = {"error": str(e)[:200]}
+    # HashJoin field=num, R=100M x S=400M rows (BASELINE configs[3] asks for S=1B: 140 GB of S records do not
+    # fit beside R and the output on one 180 GB GPU, so the single-GPU figure uses the largest S that does)
+    for kind, label in ((1, "uniform"), (2, "skewed")):
+        try:
+            nr, ns, D = 100_000_000, 400_000_000, 100_000_000
+            nbr, nbs = nr // RPB, ns // RPB
+            d_r = torch.empty(nbr * BLOCK_BYTES, dtype=torch.uint8, device=dev)
+            d_s = torch.empty(nbs * BLOCK_BYTES, dtype=torch.uint8, device=dev)
+            d_o = torch.empty(nbs * BLOCK_BYTES, dtype=torch.uint8, device=dev)
+            dbt.check(L.dbt_gen_syn(7, nr, D, 1, 0, nr, 0, d_r.data_ptr(), sp))
+            dbt.check(L.dbt_gen_syn(9, ns, D, kind, 0, ns, 0, d_s.data_ptr(), sp))
+            wsb = dbt.dev_ws_bytes(dbt.OP_HASHJOIN, nbr, nbs, FIELD)
+            ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            L.dbt_stage_timing_enable(1)
+            times = []
+            for it in range(4):
+                torch.cuda.synchronize()
+                L.dbt_stage_timing_reset()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                k = dbt.dev_hashjoin(d_r.data_ptr(), nbr, d_s.data_ptr(), nbs, FIELD, d_o.data_ptr(), nbs, ws.data_ptr(), wsb, sp)
+                e1.record()
+                torch.cuda.synchronize()
+                if it:
+                    times.append(e0.elapsed_time(e1))
+            rep = dbt.stage_report()
+            L.dbt_stage_timing_enable(0)
+            ms = sum(times) / len(times)
+            probe_ms = rep["hash_probe"][0]
+            sel = k / ns
+            out[f"hashjoin_R100M_S400M_{label}"] = {
+                "probe_tuples_per_s": ns / (ms * 1e-3), "ms": ms, "nres": k, "selectivity": sel,
+                "stage_ms": {a: round(b[0], 3) for a, b in rep.items()},
+                "probe_kernel_hbm_frac_of_measured": (8 + 4 * sel) * ns / (probe_ms * 1e-3) / 1e9 / peak,
+                "note": "semi-join (reference semantics): S rows in S order whose key is in keys(R); probe kernel = "
+                        "L2-resident bitmap test because keys(R) span < 2^29; whole operator includes extraction of "
+                        "both images and the gather of the matching S records"}
+            del d_r, d_s, d_o, ws
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            out[f"hashjoin_R100M_S400M_{label}"] = {"error": str(e)[:200]}
     return out
 
 

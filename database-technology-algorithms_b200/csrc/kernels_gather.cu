@@ -40,7 +40,9 @@ constexpr int kScanTile = kScanThreads * kScanItems;
 // CountFn: void load(uint64_t i0, uint64_t n, uint32_t c[8], uint32_t pay[8]) const
 //            -- for the 8 consecutive rows i0..i0+7: how many outputs each produces, and a payload word
 //               (vector loads: a thread's 8 rows are 32 contiguous bytes of every input column)
-// EmitFn : void operator()(uint64_t i, uint64_t off, uint32_t c, uint32_t pay) const -- write at [off, off+c)
+// EmitFn : kTwo (second output column?), v1(i, pay) / v2(i, pay) = the values row i emits (c times), out1/out2/cap.
+//          A tile's outputs are first compacted in shared memory and then written coalesced; a tile that emits
+//          more than it holds (field-'3' multiplicities) writes directly.
 template <class CountFn, class EmitFn>
 __global__ void __launch_bounds__(kScanThreads)
 scan_emit_kernel(uint64_t n, CountFn cnt, EmitFn emit, ScanWs ws, unsigned long long *total_out) {
@@ -103,11 +105,53 @@ scan_emit_kernel(uint64_t n, CountFn cnt, EmitFn emit, ScanWs ws, unsigned long 
         }
     }
     __syncthreads();
-    uint64_t off = s_prefix + pre + x - local;
+    extern __shared__ uint32_t s_stage[]; // [kScanTile] (+ [kScanTile] when EmitFn::kTwo)
+    const uint64_t tile_prefix = s_prefix;
+    if constexpr (EmitFn::kIndexed) { // plain exclusive scan: every input row records its offset
+        uint64_t off = tile_prefix + pre + x - local;
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        if (c[k]) emit(i0 + k, off, c[k], pay[k]);
-        off += c[k];
+        for (int k = 0; k < kScanItems; ++k) {
+            if (i0 + k < n) emit.at(i0 + k, off);
+            off += c[k];
+        }
+        return;
+    } else if (agg <= (uint64_t)kScanTile) {
+        uint32_t lo = (uint32_t)(pre + x - local); // tile-local offset of this thread's first output
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            if (c[k]) {
+                const uint32_t a = emit.v1(i0 + k, pay[k]);
+                const uint32_t b = EmitFn::kTwo ? emit.v2(i0 + k, pay[k]) : 0u;
+                for (uint32_t t = 0; t < c[k]; ++t) {
+                    s_stage[lo + t] = a;
+                    if (EmitFn::kTwo) s_stage[kScanTile + lo + t] = b;
+                }
+                lo += c[k];
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < (uint32_t)agg; i += kScanThreads) {
+            const uint64_t g = tile_prefix + i;
+            if (g < emit.cap) {
+                emit.out1[g] = s_stage[i];
+                if (EmitFn::kTwo) emit.out2[g] = s_stage[kScanTile + i];
+            }
+        }
+    } else {
+        uint64_t off = tile_prefix + pre + x - local;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            if (c[k]) {
+                const uint32_t a = emit.v1(i0 + k, pay[k]);
+                const uint32_t b = EmitFn::kTwo ? emit.v2(i0 + k, pay[k]) : 0u;
+                for (uint32_t t = 0; t < c[k]; ++t)
+                    if (off + t < emit.cap) {
+                        emit.out1[off + t] = a;
+                        if (EmitFn::kTwo) emit.out2[off + t] = b;
+                    }
+            }
+            off += c[k];
+        }
     }
 }
 
@@ -128,7 +172,14 @@ static int run_scan_emit(uint64_t n, CountFn cnt, EmitFn emit, uint64_t *d_total
     }
     DBT_CUDA(cudaMemsetAsync(sw.state, 0, ntiles * 8, st));
     DBT_CUDA(cudaMemsetAsync(sw.ctr, 0, 4, st));
-    scan_emit_kernel<<<(unsigned)ntiles, kScanThreads, 0, st>>>(n, cnt, emit, sw, (unsigned long long *)d_total);
+    const size_t smem = (size_t)kScanTile * 4 * (EmitFn::kTwo ? 2 : 1);
+    auto kfn = scan_emit_kernel<CountFn, EmitFn>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        DBT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    kfn<<<(unsigned)ntiles, kScanThreads, smem, st>>>(n, cnt, emit, sw, (unsigned long long *)d_total);
     count_launch();
     DBT_KERNEL_CHECK();
     ws.release(m);
@@ -224,26 +275,29 @@ struct UniqueCountRows {
         }
     }
 };
-struct EmitPerm {
-    uint32_t *out;
-    uint32_t *out_key;         // optional: compacted sorted key column
+template <bool TWO>
+struct EmitPerm { // out1 = the row (payload); out2 = its key from the sorted column (optional)
+    static constexpr bool kTwo = TWO;
+    static constexpr bool kIndexed = false;
+    uint32_t *out1;
+    uint32_t *out2;
     const uint32_t *sorted;
-    __device__ void operator()(uint64_t i, uint64_t off, uint32_t, uint32_t row) const {
-        out[off] = row;
-        if (out_key) out_key[off] = sorted[i];
-    }
+    uint64_t cap;
+    __device__ void at(uint64_t, uint64_t) const {}
+    __device__ uint32_t v1(uint64_t, uint32_t row) const { return row; }
+    __device__ uint32_t v2(uint64_t i, uint32_t) const { return sorted[i]; }
 };
 
 int unique_rows(const KeyCols &k, int field, const uint32_t *d_perm, const uint32_t *d_sorted_w0, uint64_t n,
                 uint32_t *d_uperm, uint32_t *d_ukeys, uint64_t *d_count, Arena &ws, cudaStream_t st) {
     StageScope sc(ST_UNIQUE, st);
-    EmitPerm emit{d_uperm, d_ukeys, d_sorted_w0};
     if ((field == '0' || field == '1') && d_sorted_w0) {
-        return run_scan_emit(n, UniqueCountSorted{d_sorted_w0, d_perm}, emit, d_count, ws, st);
+        if (d_ukeys)
+            return run_scan_emit(n, UniqueCountSorted{d_sorted_w0, d_perm}, EmitPerm<true>{d_uperm, d_ukeys, d_sorted_w0, n}, d_count, ws, st);
+        return run_scan_emit(n, UniqueCountSorted{d_sorted_w0, d_perm}, EmitPerm<false>{d_uperm, nullptr, nullptr, n}, d_count, ws, st);
     }
-    emit.out_key = nullptr;
     RowKeyEq eq{(field == '2') ? nullptr : k.w0, (field >= '2') ? k.str : nullptr, k.kw};
-    return run_scan_emit(n, UniqueCountRows{d_perm, eq}, emit, d_count, ws, st);
+    return run_scan_emit(n, UniqueCountRows{d_perm, eq}, EmitPerm<false>{d_uperm, nullptr, nullptr, n}, d_count, ws, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -262,40 +316,37 @@ struct CountFromArray {
     }
 };
 struct EmitRowRepeated {
-    uint32_t *out;
+    static constexpr bool kTwo = false;
+    static constexpr bool kIndexed = false;
+    uint32_t *out1;
+    uint32_t *out2;
     uint64_t cap;
-    __device__ void operator()(uint64_t, uint64_t off, uint32_t c, uint32_t v) const {
-        for (uint32_t t = 0; t < c; ++t)
-            if (off + t < cap) out[off + t] = v;
-    }
+    __device__ void at(uint64_t, uint64_t) const {}
+    __device__ uint32_t v1(uint64_t, uint32_t v) const { return v; }
+    __device__ uint32_t v2(uint64_t, uint32_t) const { return 0u; }
 };
 int compact_select(const uint32_t *d_counts, const uint32_t *d_values, uint64_t n, uint32_t *d_out, uint64_t out_cap,
                    uint64_t *d_total, Arena &ws, cudaStream_t st) {
     StageScope sc(ST_COMPACT, st);
-    return run_scan_emit(n, CountFromArray{d_counts, d_values}, EmitRowRepeated{d_out, out_cap}, d_total, ws, st);
+    return run_scan_emit(n, CountFromArray{d_counts, d_values}, EmitRowRepeated{d_out, nullptr, out_cap}, d_total, ws, st);
 }
 
 // exclusive prefix sums of a u32 array (offsets < 2^32): out[i] = sum(counts[0..i))
 struct EmitOffset {
+    static constexpr bool kTwo = false;
+    static constexpr bool kIndexed = true;
     uint32_t *out;
-    __device__ void operator()(uint64_t i, uint64_t off, uint32_t, uint32_t) const { out[i] = (uint32_t)off; }
+    uint32_t *out1 = nullptr, *out2 = nullptr; // unused by the indexed mode
+    uint64_t cap = 0;
+    __device__ void at(uint64_t i, uint64_t off) const { out[i] = (uint32_t)off; }
+    __device__ uint32_t v1(uint64_t, uint32_t) const { return 0u; }
+    __device__ uint32_t v2(uint64_t, uint32_t) const { return 0u; }
 };
-__global__ void __launch_bounds__(256)
-fix_zero_offsets_kernel(const uint32_t *__restrict__ counts, uint64_t n, uint32_t *__restrict__ off) {
-    // rows with count 0 were skipped by the emit; their offset equals the next emitted row's (or the total)
-    // -- they are never dereferenced (no entries), so any value is fine; write 0 for determinism
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && counts[i] == 0) off[i] = 0;
-}
 int exclusive_offsets(const uint32_t *d_counts, uint64_t n, uint32_t *d_off, uint64_t *d_total, Arena &ws,
                       cudaStream_t st) {
-    DBT_TRY(run_scan_emit(n, CountFromArray{d_counts, nullptr}, EmitOffset{d_off}, d_total, ws, st));
-    if (n) {
-        fix_zero_offsets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_counts, n, d_off);
-        count_launch();
-        DBT_KERNEL_CHECK();
-    }
-    return 0;
+    EmitOffset e;
+    e.out = d_off;
+    return run_scan_emit(n, CountFromArray{d_counts, nullptr}, e, d_total, ws, st);
 }
 
 // ---------------------------------------------------------------------------------------------
