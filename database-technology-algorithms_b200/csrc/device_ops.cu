@@ -224,15 +224,21 @@ extern "C" size_t dbt_dev_partition_ws_bytes(uint64_t nblocks) {
 
 extern "C" int dbt_dev_extract_keys_u32(const void *d_in, uint64_t nblocks, int field, uint32_t *d_keys, void *d_ws,
                                         size_t ws_bytes, void *stream, uint64_t *nrows) {
-    if (field != '0' && field != '1') {
-        set_error("dbt_dev_extract_keys_u32: only fields '0' and '1' have u32 keys");
-        return DBT_ERR_UNSUPPORTED;
+    // The routing word: the most significant word of the key.  Equal keys share it, so routing on it (range or
+    // hash) brings equal keys to the same GPU for every field: recid ('0'), num ('1' and '3'), the first four
+    // bytes of str ('2').
+    if (!field_ok(field)) {
+        set_error("Wrong field! Please give a field between 0 and 3!");
+        return DBT_ERR_ARG;
     }
     cudaStream_t st = (cudaStream_t)stream;
     Arena ws(d_ws, ws_bytes);
     Prepared p;
     DBT_TRY(prepare(d_in, nblocks, field, ws, st, &p));
-    if (p.info.nrows) DBT_CUDA(cudaMemcpyAsync(d_keys, p.keys.w0, 4 * p.info.nrows, cudaMemcpyDeviceToDevice, st));
+    if (p.info.nrows) {
+        if (field == '2') DBT_TRY(gather_word(p.keys.str, p.keys.kw, 0, nullptr, d_keys, p.info.nrows, st));
+        else DBT_CUDA(cudaMemcpyAsync(d_keys, p.keys.w0, 4 * p.info.nrows, cudaMemcpyDeviceToDevice, st));
+    }
     if (nrows) *nrows = p.info.nrows;
     return finish(st);
 }

@@ -44,7 +44,7 @@ constexpr int kScanTile = kScanThreads * kScanItems;
 //          A tile's outputs are first compacted in shared memory and then written coalesced; a tile that emits
 //          more than it holds (field-'3' multiplicities) writes directly.
 template <class CountFn, class EmitFn>
-__global__ void __launch_bounds__(kScanThreads)
+__global__ void __launch_bounds__(kScanThreads, 2) // <= 64 registers: two 512-thread CTAs per SM (ncu: the compaction variant took 110)
 scan_emit_kernel(uint64_t n, CountFn cnt, EmitFn emit, ScanWs ws, unsigned long long *total_out) {
     __shared__ uint64_t s_wsum[kScanThreads / 32];
     __shared__ uint64_t s_prefix;
@@ -137,9 +137,9 @@ scan_emit_kernel(uint64_t n, CountFn cnt, EmitFn emit, ScanWs ws, unsigned long 
                 if (EmitFn::kTwo) emit.out2[g] = s_stage[kScanTile + i];
             }
         }
-    } else {
+    } else { // rare (a tile emitting more than it holds): keep this path small, it only costs registers
         uint64_t off = tile_prefix + pre + x - local;
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < kScanItems; ++k) {
             if (c[k]) {
                 const uint32_t a = emit.v1(i0 + k, pay[k]);

@@ -15,7 +15,8 @@ Per rank:   keys = extract(image)                                   [C-ABI, CUDA
 
 `LocalOps` is the CUDA backend (no fallback).  The orchestration in `DistOps` only needs the small
 interface below, which is what lets tests/test_dist_gloo.py drive it on CPU tensors over gloo with a
-test-side backend.  u32 keys (fields '0' and '1') in this round.
+test-side backend.  All four fields shard: rows are routed on the key's most significant word (equal keys share
+it); the columns-only strategies ("keys", "overlap") apply to the u32 fields '0' and '1'.
 """
 from __future__ import annotations
 
@@ -472,7 +473,7 @@ class DistOps:
 
     # -- operators ------------------------------------------------------------------------------
     def sort(self, img, nblocks: int, field: str):
-        if self.sort_mode in ("overlap", "keys"):
+        if self.sort_mode in ("overlap", "keys") and field in ("0", "1"):
             f = self._sort_overlap if self.sort_mode == "overlap" else self._sort_rows_stay_put
             r = f(img, nblocks, field, dedup=False)
             if r is not None:
@@ -481,7 +482,7 @@ class DistOps:
         return self.ops.run("sort", field, recv, nb)
 
     def dedup(self, img, nblocks: int, field: str):
-        if self.sort_mode in ("overlap", "keys"):
+        if self.sort_mode in ("overlap", "keys") and field in ("0", "1"):
             f = self._sort_overlap if self.sort_mode == "overlap" else self._sort_rows_stay_put
             r = f(img, nblocks, field, dedup=True)
             if r is not None:

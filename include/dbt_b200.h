@@ -128,9 +128,11 @@ int dbt_dev_hashjoin(const void *d_in_r, uint64_t nblocks_r, const void *d_in_s,
  * is globally ordered), joins by key hash.  Each rank: extract keys -> choose a destination per row ->
  * group its rows by destination -> gather each group into its own block image -> ONE all-to-all of
  * images (NCCL, issued by the caller) -> the ordinary device-scope operator on what it received.
- * u32 keys (fields '0' and '1') in this round.
+ * Routing uses the key's most significant word (recid, num, or the first four str bytes): equal keys share it, so
+ * every field shards; the columns-only strategies of dist.py ("keys", "overlap") are for the u32 fields '0'/'1'.
  * ---------------------------------------------------------------------------------------------- */
-/* key column of an image: d_keys[row] for the live rows in file order; *nrows receives the count */
+/* routing word of every live row in file order (recid | num | first 4 bytes of str, NUL-normalised, big-endian);
+ * *nrows receives the count */
 int dbt_dev_extract_keys_u32(const void *d_in, uint64_t nblocks, int field, uint32_t *d_keys, void *d_ws,
                              size_t ws_bytes, void *stream, uint64_t *nrows);
 /* Destination of every row and the rows grouped by destination (stable: file order inside a group).

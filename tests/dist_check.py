@@ -35,7 +35,7 @@ def main():
     t2 = to_dev(f2[rank * nb_local:(rank + 1) * nb_local])
     res = {}
     for rep in range(2):  # twice: buffer reuse across steps must be safe
-        for field in ("1", "0"):
+        for field in ("1", "0", "2", "3"):
             for op in ("sort", "dedup"):
                 out, info = getattr(d, op)(t1, nb_local, field)
                 res[f"{op}{field}"] = rows_of_image(out, info["out_rows"])
@@ -47,7 +47,7 @@ def main():
     dist.all_gather_object(gathered, res)
     ok = True
     if rank == 0:
-        for field in ("1", "0"):
+        for field in ("1", "0", "2", "3"):
             checks = {
                 f"sort{field}": (orc.rows_of(orc.sort(f1, field))["recid"], False),
                 f"dedup{field}": (orc.rows_of(orc.dedup(f1, field))["recid"], False),

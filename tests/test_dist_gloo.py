@@ -34,7 +34,13 @@ class OracleOps:
 
     def extract_keys(self, img, nblocks, field):
         rows = self.orc.rows_of(self._blocks(img, nblocks))
-        col = rows["recid"] if field == "0" else rows["num"]
+        if field == "2":  # routing word = first four str bytes, NUL-normalised, big-endian (as the CUDA extraction does)
+            raw = np.ascontiguousarray(rows["str"]).view(np.uint8).reshape(len(rows), 120)[:, :4].astype(np.uint32)
+            alive = np.cumprod(raw != 0, axis=1).astype(np.uint32)
+            raw = raw * alive
+            col = (raw[:, 0] << 24) | (raw[:, 1] << 16) | (raw[:, 2] << 8) | raw[:, 3]
+        else:
+            col = rows["recid"] if field == "0" else rows["num"]
         return torch.from_numpy(col.astype(np.uint32).view(np.int32).copy())
 
     def sample_keys(self, keys, nsamples):
@@ -117,7 +123,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world,field", [(2, "1"), (3, "1"), (2, "0")])
+@pytest.mark.parametrize("world,field", [(2, "1"), (3, "1"), (2, "0"), (2, "2"), (3, "3")])
 def test_sharded_operators_compose_to_the_single_node_result(orc, tmp_path, world, field):
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), field), nprocs=world, join=True)
     parts = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
