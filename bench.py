@@ -228,7 +228,6 @@ def main():
     launches = int(L.dbt_kernel_launches() - launches0)
     stages = dbt.stage_report()
     L.dbt_stage_timing_enable(0)
-    clocks = sampler.stop()
     ms_step = ms_total / args.steps
     value = n / (ms_step * 1e-3)
 
@@ -290,6 +289,8 @@ def main():
         del host_t, out_t
         L.dbt_host_free(h_in)
         L.dbt_host_free(h_out)
+
+    clocks = sampler.stop()  # sampled across both timed regions (device scope and e2e)
 
     # ---- cpu baseline: the reference itself on a bounded sample ------------------------------------
     cpu = None

@@ -157,6 +157,7 @@ extern "C" size_t dbt_dev_ws_bytes_kw(int op, uint64_t nbr, uint64_t nbs, int fi
     case DBT_OP_HASHJOIN:
         b += rel_bytes(nbr, field, kw, false) + rel_bytes(nbs, field, kw, false) + 2 * pad256(4 * hash_table_slots(nr)) +
              2 * pad256(4 * ns) + scan + 4096;
+        if (field == '0' || field == '1') b += (1ull << 29) + 4096; // room for the full-range key bitmap (512 MB)
         break;
     default: return 0;
     }

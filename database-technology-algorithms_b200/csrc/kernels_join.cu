@@ -202,6 +202,33 @@ bitmap_probe_kernel(const uint32_t *__restrict__ k, uint64_t n, uint32_t base, u
 }
 constexpr uint64_t kBitmapMaxSpan = 1ull << 29; // 64 MB bitmap: stays L2-resident next to the streamed columns
 
+// Wider key ranges: the range is cut into slices of 2^29 keys; for each slice one launch streams S's key column
+// and tests only the keys that fall into the slice, so the 64 MB of bitmap being hit is L2-resident during that
+// launch.  Every S row belongs to exactly one slice and is written exactly once.  The bitmap of the full 32-bit
+// range is 512 MB in HBM.
+__global__ void __launch_bounds__(256)
+bitmap_probe_slice_kernel(const uint32_t *__restrict__ k, uint64_t n, uint32_t base, uint32_t slice,
+                          const uint32_t *__restrict__ bm, uint32_t *__restrict__ counts) {
+    uint64_t nvec = n / 4;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint4 *kv = reinterpret_cast<const uint4 *>(k);
+    auto probe = [&](uint32_t key, uint64_t i) {
+        uint32_t v = key - base; // keys below base wrap to huge values: they land in a slice beyond the bitmap and are handled there
+        if ((v >> 29) == slice) counts[i] = (__ldg(&bm[v >> 5]) >> (v & 31)) & 1u;
+    };
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        uint4 a = kv[i];
+        probe(a.x, 4 * i);
+        probe(a.y, 4 * i + 1);
+        probe(a.z, 4 * i + 2);
+        probe(a.w, 4 * i + 3);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        uint64_t i = nvec * 4 + threadIdx.x;
+        probe(k[i], i);
+    }
+}
+
 size_t hash_table_slots(uint64_t nr) {
     uint64_t want = nr * 2 + 64, cap = 1024;
     while (cap < want) cap <<= 1;
@@ -236,6 +263,27 @@ int hash_join_counts(const KeyCols &r, const KeyCols &s, int field, uint32_t *d_
             DBT_CUDA(cudaStreamSynchronize(st));
         }
         const uint64_t span = (uint64_t)h_mm[1] - h_mm[0];
+        if (span >= kBitmapMaxSpan && getenv("DBT_JOIN_NO_SLICES") == nullptr) {
+            // sliced bitmap over [min, min + 2^32): one bit per possible key, cleared, filled from R, probed slice by slice
+            const uint64_t words = (1ull << 32) / 32;
+            uint32_t *bm = ws.take<uint32_t>(words);
+            if (bm) {
+                {
+                    StageScope sc(ST_HASH_BUILD, st);
+                    DBT_CUDA(cudaMemsetAsync(bm, 0, words * 4, st));
+                    bitmap_build_kernel<<<gb, 256, 0, st>>>(r.w0, r.n, h_mm[0], bm);
+                    count_launch();
+                    DBT_KERNEL_CHECK();
+                }
+                StageScope sc(ST_HASH_PROBE, st);
+                for (uint32_t slice = 0; slice < 8; ++slice) { // keys outside [min, max] hit zero bits: no match, as it must be
+                    bitmap_probe_slice_kernel<<<gp, 256, 0, st>>>(s.w0, s.n, h_mm[0], slice, bm, d_counts);
+                    count_launch();
+                }
+                DBT_KERNEL_CHECK();
+                return 0;
+            }
+        }
         if (span < kBitmapMaxSpan && (span / 32 + 1) <= slots) { // the table allocation doubles as the bitmap
             const uint64_t words = span / 32 + 1;
             {

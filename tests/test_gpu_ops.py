@@ -162,3 +162,26 @@ def test_sort_pairs_u32_full_range(dbt):
     ref_k, ref_i = torch.sort(keys.to(torch.int64), stable=True)
     assert torch.equal(ko.to(torch.int64), ref_k)
     assert torch.equal(vo.to(torch.int64), ref_i)
+
+
+def test_hashjoin_wide_key_range_and_table_fallback(dbt, orc, monkeypatch):
+    """u32 semi-join paths: L2-resident bitmap (narrow key range, the other tests), sliced full-range bitmap
+    (keys spread over 32 bits), and the linear-probing hash table (forced)."""
+    r, s = orc.gen_ref(21, 150)
+    rng = np.random.default_rng(8)
+    pool = rng.integers(0, 2**32, size=9000, dtype=np.uint64).astype(np.uint32)  # shared pool => plenty of matches
+    pool[:3] = [0, 0xFFFFFFFF, 0x80000000]                                        # extremes, incl. the table's sentinel value
+    for img in (r, s):
+        e = img["entries"]
+        e["num"] = pool[rng.integers(0, len(pool), size=e["num"].shape)]
+    want = orc.hashjoin(r, s, "1")
+    assert 0 < orc.count_rows(want) < orc.count_rows(s)
+    got, n = H.dev_hashjoin(dbt, orc, r, s, "1")          # sliced bitmap
+    assert H.same_image(got, want), H.first_diff(got, want)
+    monkeypatch.setenv("DBT_JOIN_NO_SLICES", "1")          # -> hash table (span too wide for the single bitmap)
+    got, n = H.dev_hashjoin(dbt, orc, r, s, "1")
+    assert H.same_image(got, want), H.first_diff(got, want)
+    monkeypatch.setenv("DBT_JOIN_NO_BITMAP", "1")
+    r2, s2 = orc.gen_ref(22, 80)
+    got, n = H.dev_hashjoin(dbt, orc, r2, s2, "1")        # narrow range, table forced
+    assert H.same_image(got, orc.hashjoin(r2, s2, "1"))
