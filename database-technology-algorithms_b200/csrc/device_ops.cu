@@ -20,14 +20,15 @@ struct Prepared {
 
 static bool field_ok(int f) { return f >= '0' && f <= '3'; }
 
-static int prepare(const void *d_img, uint64_t nblocks, int field, Arena &ws, cudaStream_t st, Prepared *out) {
+static int prepare(const void *d_img, uint64_t nblocks, int field, Arena &ws, cudaStream_t st, Prepared *out,
+                   uint32_t force_kw = 0) {
     memset(out, 0, sizeof *out);
     device_setup();
     DBT_TRY(image_info(d_img, nblocks, &out->row_slot, ws, st, &out->info));
     const uint64_t n = out->info.nrows;
     KeyCols &k = out->keys;
     k.n = n;
-    k.kw = 8;
+    k.kw = force_kw ? force_kw : 8;
     if (n == 0) return 0;
     const bool has_w0 = field != '2', has_str = field >= '2';
     ExtractStats *d_stats = ws.take<ExtractStats>(1);
@@ -422,8 +423,8 @@ extern "C" int dbt_dev_dedup(const void *d_in, uint64_t nblocks, int field, void
 
 // sort + unique of one relation; leaves the unique row list (and unique key column for 1-word keys)
 static int dedup_rel(const void *d_in, uint64_t nblocks, int field, Arena &ws, cudaStream_t st, Prepared *p,
-                     uint32_t **urows, uint32_t **ukeys, uint64_t *nu) {
-    DBT_TRY(prepare(d_in, nblocks, field, ws, st, p));
+                     uint32_t **urows, uint32_t **ukeys, uint64_t *nu, uint32_t force_kw = 0) {
+    DBT_TRY(prepare(d_in, nblocks, field, ws, st, p, force_kw));
     const uint64_t n = p->info.nrows;
     *urows = *ukeys = nullptr;
     *nu = 0;
@@ -455,6 +456,10 @@ extern "C" int dbt_dev_mergejoin(const void *d_in_r, uint64_t nbr, const void *d
     uint64_t nur, nus;
     DBT_TRY(dedup_rel(d_in_r, nbr, field, ws, st, &pr, &ur, &urk, &nur));
     DBT_TRY(dedup_rel(d_in_s, nbs, field, ws, st, &ps, &us, &usk, &nus));
+    if (field >= '2' && pr.keys.kw != ps.keys.kw && nur && nus) { // mixed key widths: redo the narrow side at full width
+        if (pr.keys.kw < ps.keys.kw) DBT_TRY(dedup_rel(d_in_r, nbr, field, ws, st, &pr, &ur, &urk, &nur, ps.keys.kw));
+        else DBT_TRY(dedup_rel(d_in_s, nbs, field, ws, st, &ps, &us, &usk, &nus, pr.keys.kw));
+    }
     // the side files "1outfile.bin" / "2outfile.bin" (DatabaseProject.cpp:385-394)
     if (d_out_ur) DBT_TRY(gather_records(d_in_r, ur, pr.row_slot, nur, d_out_ur, st));
     if (d_out_us) DBT_TRY(gather_records(d_in_s, us, ps.row_slot, nus, d_out_us, st));
@@ -492,14 +497,14 @@ extern "C" int dbt_dev_hashjoin(const void *d_in_r, uint64_t nbr, const void *d_
     Prepared pr, ps;
     DBT_TRY(prepare(d_in_r, nbr, field, ws, st, &pr));
     DBT_TRY(prepare(d_in_s, nbs, field, ws, st, &ps));
+    if (field >= '2' && pr.keys.kw != ps.keys.kw && pr.info.nrows && ps.info.nrows) {
+        // only one side has strings of 32+ bytes: widen the other side's keys to the full 120 bytes as well
+        if (pr.keys.kw < ps.keys.kw) DBT_TRY(prepare(d_in_r, nbr, field, ws, st, &pr, ps.keys.kw));
+        else DBT_TRY(prepare(d_in_s, nbs, field, ws, st, &ps, pr.keys.kw));
+    }
     *nres = 0;
     const uint64_t ns = ps.info.nrows;
     if (ns && pr.info.nrows) {
-        if (field >= '2' && pr.keys.kw != ps.keys.kw) {
-            // one side needed 120-byte keys, the other did not: widen the short side so the shapes agree
-            set_error("hashjoin: mixed string key widths are not supported yet");
-            return DBT_ERR_UNSUPPORTED;
-        }
         uint32_t *counts = ws.take<uint32_t>(ns);
         uint64_t cap = out_capacity_blocks * kRpb;
         uint32_t *rows = ws.take<uint32_t>(std::max<uint64_t>(std::min<uint64_t>(cap, (field == '3') ? cap : ns), 1));

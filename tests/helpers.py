@@ -39,10 +39,10 @@ def stream() -> int:
     return _torch().cuda.current_stream().cuda_stream
 
 
-def dev_sort(dbt, orc, blocks, field):
+def dev_sort(dbt, orc, blocks, field, kw=8):
     d_in = to_dev(blocks)
     d_out = dev_alloc(len(blocks) * BLOCK_BYTES)
-    wsb = dbt.dev_ws_bytes(dbt.OP_SORT, len(blocks), 0, field)
+    wsb = dbt.dev_ws_bytes(dbt.OP_SORT, len(blocks), 0, field, kw)
     ws = dev_alloc(wsb)
     n = dbt.dev_mergesort(d_in.data_ptr(), len(blocks), field, d_out.data_ptr(), ws.data_ptr(), wsb, stream())
     return to_host(d_out, nb(n), orc), n
@@ -57,22 +57,22 @@ def dev_dedup(dbt, orc, blocks, field, kw=8):
     return to_host(d_out, nb(u), orc), n, u
 
 
-def dev_hashjoin(dbt, orc, r, s, field, cap_blocks=None):
+def dev_hashjoin(dbt, orc, r, s, field, cap_blocks=None, kw=8):
     d_r, d_s = to_dev(r), to_dev(s)
     cap = len(s) if cap_blocks is None else cap_blocks
     d_out = dev_alloc(cap * BLOCK_BYTES)
-    wsb = dbt.dev_ws_bytes(dbt.OP_HASHJOIN, len(r), len(s), field)
+    wsb = dbt.dev_ws_bytes(dbt.OP_HASHJOIN, len(r), len(s), field, kw)
     ws = dev_alloc(wsb)
     n = dbt.dev_hashjoin(d_r.data_ptr(), len(r), d_s.data_ptr(), len(s), field, d_out.data_ptr(), cap, ws.data_ptr(),
                          wsb, stream())
     return to_host(d_out, nb(n), orc), n
 
 
-def dev_mergejoin(dbt, orc, r, s, field):
+def dev_mergejoin(dbt, orc, r, s, field, kw=8):
     d_r, d_s = to_dev(r), to_dev(s)
     d_ur, d_us = dev_alloc(len(r) * BLOCK_BYTES), dev_alloc(len(s) * BLOCK_BYTES)
     d_out = dev_alloc(min(len(r), len(s)) * BLOCK_BYTES)
-    wsb = dbt.dev_ws_bytes(dbt.OP_MERGEJOIN, len(r), len(s), field)
+    wsb = dbt.dev_ws_bytes(dbt.OP_MERGEJOIN, len(r), len(s), field, kw)
     ws = dev_alloc(wsb)
     info = dbt.dev_mergejoin(d_r.data_ptr(), len(r), d_s.data_ptr(), len(s), field, d_ur.data_ptr(), d_us.data_ptr(),
                              d_out.data_ptr(), ws.data_ptr(), wsb, stream())

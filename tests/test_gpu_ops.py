@@ -185,3 +185,23 @@ def test_hashjoin_wide_key_range_and_table_fallback(dbt, orc, monkeypatch):
     r2, s2 = orc.gen_ref(22, 80)
     got, n = H.dev_hashjoin(dbt, orc, r2, s2, "1")        # narrow range, table forced
     assert H.same_image(got, orc.hashjoin(r2, s2, "1"))
+
+
+def test_joins_with_long_strings_on_one_side_only(dbt, orc):
+    r, s = orc.gen_ref(31, 12)
+    rows = s["entries"].reshape(-1).copy()
+    long = np.zeros(120, np.uint8)
+    long[:60] = ord("z")
+    rows["str"][5] = long.view("V120")[0]              # S has one 60-byte string, R none
+    rows["str"][7] = r["entries"].reshape(-1)["str"][3]  # and a guaranteed match
+    s["entries"] = rows.reshape(len(s), 100)
+    for field in "23":
+        want = orc.hashjoin(r, s, field)
+        got, n = H.dev_hashjoin(dbt, orc, r, s, field, kw=30)
+        assert H.same_image(got, want), (field, H.first_diff(got, want))
+        want = orc.hashjoin(s, r, field)
+        got, n = H.dev_hashjoin(dbt, orc, s, r, field, kw=30)
+        assert H.same_image(got, want), (field, H.first_diff(got, want))
+        got, ur, us, info = H.dev_mergejoin(dbt, orc, r, s, field, kw=30)
+        want, wur, wus, winfo = orc.mergejoin(r, s, field)
+        assert info == winfo and H.same_image(got, want) and H.same_image(us, wus), field
