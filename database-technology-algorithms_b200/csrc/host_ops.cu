@@ -252,7 +252,17 @@ extern "C" int dbt_host_hashjoin(const void *h_in_r, uint64_t nbr, const void *h
 
 // =============================================================================================
 // File-based drop-in entry points (C++ linkage, declared in include/dbtproj.h).
+//
+// Staging pipeline: block files are read with parallel pread() straight into a
+// persistent pinned buffer, chunk by chunk, each chunk's H2D copy overlapping the read of the next; results
+// come back the same way (D2H of chunk k+1 overlaps the parallel pwrite() of chunk k).  Pinned buffers,
+// device buffers and the workspace are cached in the process and only ever grow: the first version allocated
+// and freed pinned memory per call, which cost more than the reference's whole sort at 1M records.
 // =============================================================================================
+#include <fcntl.h>
+#include <thread>
+#include <unistd.h>
+
 namespace {
 
 [[noreturn]] void die(const std::string &msg) {
@@ -262,43 +272,6 @@ namespace {
 }
 void must(int rc, const char *what) {
     if (rc != 0) die(std::string(what) + ": " + dbt_last_error());
-}
-
-// A block file read into pinned memory (the staging buffer the H2D copy reads from directly).
-struct PinnedFile {
-    void *p = nullptr;
-    uint64_t nblocks = 0;
-    ~PinnedFile() {
-        if (p) cudaFreeHost(p);
-    }
-    void read(const char *path) {
-        FILE *f = fopen(path, "rb");
-        if (!f) die(std::string("cannot open input file '") + path + "'");
-        struct stat sb;
-        if (fstat(fileno(f), &sb) != 0) die("fstat failed");
-        nblocks = (uint64_t)sb.st_size / DBT_BLOCK_BYTES; // a trailing partial block is ignored
-        size_t bytes = (size_t)nblocks * DBT_BLOCK_BYTES;
-        if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess)
-            die("cudaHostAlloc failed (no CUDA device? there is no CPU fallback)");
-        size_t got = bytes ? fread(p, 1, bytes, f) : 0;
-        fclose(f);
-        if (got != bytes) die(std::string("short read on '") + path + "'");
-    }
-};
-struct PinnedOut {
-    void *p = nullptr;
-    ~PinnedOut() {
-        if (p) cudaFreeHost(p);
-    }
-    void alloc(size_t bytes) {
-        if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) die("cudaHostAlloc failed");
-    }
-};
-void write_file(const char *path, const void *p, size_t bytes) {
-    FILE *f = fopen(path, "wb");
-    if (!f) die(std::string("cannot create output file '") + path + "'");
-    if (bytes && fwrite(p, 1, bytes, f) != bytes) die(std::string("short write on '") + path + "'");
-    fclose(f);
 }
 int device_from_env() {
     const char *e = getenv("DBT_DEVICE");
@@ -318,31 +291,139 @@ void check_nmem_or_exit(unsigned nmem) {
 }
 unsigned clamp32(uint64_t v) { return (unsigned)v; } // out-params are unsigned int
 
+constexpr size_t kIoChunk = (size_t)4096 * DBT_BLOCK_BYTES; // 57.4 MB pipeline chunks
+int io_threads() {
+    static int n = [] {
+        if (const char *e = getenv("DBT_IO_THREADS")) return std::max(1, atoi(e));
+        unsigned hc = std::thread::hardware_concurrency();
+        return (int)std::min<unsigned>(std::max<unsigned>(hc / 2, 1), 8);
+    }();
+    return n;
+}
+// parallel pread / pwrite of [off, off+len) between a file and memory
+void parallel_io(int fd, char *mem, size_t off, size_t len, bool write, const char *path) {
+    const int nt = (len < (8u << 20)) ? 1 : io_threads();
+    std::vector<std::thread> th;
+    std::vector<int> bad(nt, 0);
+    const size_t per = (len + nt - 1) / nt;
+    for (int t = 0; t < nt; ++t) {
+        size_t lo = (size_t)t * per, hi = std::min(len, lo + per);
+        if (lo >= hi) break;
+        th.emplace_back([=, &bad] {
+            size_t p = lo;
+            while (p < hi) {
+                ssize_t k = write ? pwrite(fd, mem + p, hi - p, (off_t)(off + p)) : pread(fd, mem + p, hi - p, (off_t)(off + p));
+                if (k <= 0) {
+                    bad[t] = 1;
+                    return;
+                }
+                p += (size_t)k;
+            }
+        });
+    }
+    for (auto &x : th) x.join();
+    for (int b : bad)
+        if (b) die(std::string(write ? "short write on '" : "short read on '") + path + "'");
+}
+
+struct FileCtx { // persistent pinned staging for the file entry points
+    Buf pin[5];
+    FileCtx() {
+        for (auto &b : pin) b.pinned = true;
+    }
+};
+FileCtx g_files;
+
+HostCtx &ctx() {
+    must(g_ctx.init(device_from_env()), "CUDA initialisation");
+    return g_ctx;
+}
+
+// file -> pinned (parallel pread) -> device, chunk-pipelined.  Returns the number of whole blocks.
+uint64_t load_file(const char *path, Buf &pinned, Buf &dev) {
+    HostCtx &c = ctx();
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) die(std::string("cannot open input file '") + path + "'");
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) die("fstat failed");
+    const uint64_t nblocks = (uint64_t)sb.st_size / DBT_BLOCK_BYTES; // a trailing partial block is ignored
+    const size_t bytes = (size_t)nblocks * DBT_BLOCK_BYTES;
+    must(pinned.ensure(bytes), "pinned staging");
+    must(dev.ensure(bytes), "device image");
+    {
+        StageScope sc(ST_H2D, c.st);
+        for (size_t off = 0; off < bytes; off += kIoChunk) {
+            const size_t len = std::min(kIoChunk, bytes - off);
+            parallel_io(fd, (char *)pinned.p, off, len, false, path);
+            if (cudaMemcpyAsync((char *)dev.p + off, (char *)pinned.p + off, len, cudaMemcpyHostToDevice, c.st) != cudaSuccess)
+                die("H2D copy failed");
+        }
+    }
+    close(fd);
+    return nblocks;
+}
+// device -> pinned -> file (parallel pwrite), chunk-pipelined
+void store_file(const char *path, const void *d, size_t bytes, Buf &pinned) {
+    HostCtx &c = ctx();
+    int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) die(std::string("cannot create output file '") + path + "'");
+    must(pinned.ensure(bytes), "pinned staging");
+    const size_t nchunks = (bytes + kIoChunk - 1) / kIoChunk;
+    std::vector<cudaEvent_t> ev(nchunks);
+    {
+        StageScope sc(ST_D2H, c.st);
+        for (size_t k = 0; k < nchunks; ++k) {
+            const size_t off = k * kIoChunk, len = std::min(kIoChunk, bytes - off);
+            if (cudaMemcpyAsync((char *)pinned.p + off, (const char *)d + off, len, cudaMemcpyDeviceToHost, c.st) != cudaSuccess)
+                die("D2H copy failed");
+            cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
+            cudaEventRecord(ev[k], c.st);
+        }
+    }
+    if (bytes && ftruncate(fd, (off_t)bytes) != 0) die("ftruncate failed");
+    for (size_t k = 0; k < nchunks; ++k) {
+        const size_t off = k * kIoChunk, len = std::min(kIoChunk, bytes - off);
+        cudaEventSynchronize(ev[k]);
+        cudaEventDestroy(ev[k]);
+        parallel_io(fd, (char *)pinned.p, off, len, true, path);
+    }
+    close(fd);
+}
+
+template <class F> int with_ws(int op, uint64_t nbr, uint64_t nbs, int field, F call) {
+    return with_workspace(ctx(), op, nbr, nbs, field, call);
+}
+
 struct SortOut {
     uint64_t segs, passes, nios, nrows;
 };
 
 // sort (or dedup) a file into `outpath`; returns counters
-SortOut sort_file(const char *infile, unsigned char field, unsigned nmem, const char *outpath, bool dedup,
-                  uint64_t *nunique) {
-    PinnedFile in;
-    in.read(infile);
+SortOut sort_file(const char *infile, unsigned char field, unsigned nmem, const char *outpath, bool dedup, uint64_t *nunique) {
+    HostCtx &c = ctx();
+    const uint64_t nblocks = load_file(infile, g_files.pin[0], c.in_r);
     SortOut o{};
-    if (in.nblocks == 0) { // the reference spins forever on an empty file; we define the obvious result
+    if (nblocks == 0) { // the reference spins forever on an empty file; we define the obvious result
         o.segs = 1;
         o.passes = 1;
         o.nios = 0;
     } else {
-        must(dbt_sort_counters(in.nblocks, nmem, &o.segs, &o.passes, &o.nios), "dbt_sort_counters");
+        must(dbt_sort_counters(nblocks, nmem, &o.segs, &o.passes, &o.nios), "dbt_sort_counters");
     }
-    PinnedOut out;
-    out.alloc((size_t)in.nblocks * DBT_BLOCK_BYTES);
+    must(c.out0.ensure((size_t)nblocks * DBT_BLOCK_BYTES), "device output");
     uint64_t n = 0, u = 0;
-    if (dedup) must(dbt_host_dedup(in.p, in.nblocks, field, out.p, device_from_env(), &n, &u), "dbt_host_dedup");
-    else must(dbt_host_mergesort(in.p, in.nblocks, field, out.p, device_from_env(), &n), "dbt_host_mergesort");
+    if (dedup)
+        must(with_ws(DBT_OP_DEDUP, nblocks, 0, field, [&](void *ws, size_t wb) {
+                 return dbt_dev_dedup(c.in_r.p, nblocks, field, c.out0.p, ws, wb, c.st, &n, &u);
+             }), "dbt_dev_dedup");
+    else
+        must(with_ws(DBT_OP_SORT, nblocks, 0, field, [&](void *ws, size_t wb) {
+                 return dbt_dev_mergesort(c.in_r.p, nblocks, field, c.out0.p, ws, wb, c.st, &n);
+             }), "dbt_dev_mergesort");
     o.nrows = n;
     if (nunique) *nunique = u;
-    if (outpath) write_file(outpath, out.p, blocks_for(dedup ? u : n) * DBT_BLOCK_BYTES);
+    if (outpath) store_file(outpath, c.out0.p, blocks_for(dedup ? u : n) * DBT_BLOCK_BYTES, g_files.pin[2]);
+    stage_resolve();
     return o;
 }
 
@@ -383,48 +464,52 @@ void MergeJoin(char *infile1, char *infile2, unsigned char field, block_t *, uns
     std::cout << "Merge Sorting..." << std::endl;
     check_nmem_or_exit(nmem_blocks);
     check_field_or_exit(field);
-    PinnedFile r, s;
-    r.read(infile1);
-    s.read(infile2);
-    PinnedOut ur, us, out;
-    ur.alloc((size_t)r.nblocks * DBT_BLOCK_BYTES);
-    us.alloc((size_t)s.nblocks * DBT_BLOCK_BYTES);
-    out.alloc((size_t)std::min(r.nblocks, s.nblocks) * DBT_BLOCK_BYTES);
+    HostCtx &c = ctx();
+    const uint64_t nbr = load_file(infile1, g_files.pin[0], c.in_r);
+    const uint64_t nbs = load_file(infile2, g_files.pin[1], c.in_s);
+    must(c.out0.ensure((size_t)nbr * DBT_BLOCK_BYTES), "device output");
+    must(c.out1.ensure((size_t)nbs * DBT_BLOCK_BYTES), "device output");
+    must(c.out2.ensure((size_t)std::min(nbr, nbs) * DBT_BLOCK_BYTES), "device output");
     uint64_t res[4] = {0, 0, 0, 0};
-    must(dbt_host_mergejoin(r.p, r.nblocks, s.p, s.nblocks, field, ur.p, us.p, out.p, device_from_env(), res),
-         "dbt_host_mergejoin");
+    must(with_ws(DBT_OP_MERGEJOIN, nbr, nbs, field, [&](void *ws, size_t wb) {
+             return dbt_dev_mergejoin(c.in_r.p, nbr, c.in_s.p, nbs, field, c.out0.p, c.out1.p, c.out2.p, ws, wb, c.st, res);
+         }), "dbt_dev_mergejoin");
     std::cout << "Eliminating Duplicates..." << std::endl << "Merge Sorting..." << std::endl
               << "Eliminating Duplicates..." << std::endl;
     // side files the reference leaves behind and main.cpp:121 consumes (DatabaseProject.cpp:385-386)
-    write_file("1outfile.bin", ur.p, blocks_for(res[1]) * DBT_BLOCK_BYTES);
-    write_file("2outfile.bin", us.p, blocks_for(res[2]) * DBT_BLOCK_BYTES);
-    write_file(outfile, out.p, blocks_for(res[0]) * DBT_BLOCK_BYTES);
+    store_file("1outfile.bin", c.out0.p, blocks_for(res[1]) * DBT_BLOCK_BYTES, g_files.pin[2]);
+    store_file("2outfile.bin", c.out1.p, blocks_for(res[2]) * DBT_BLOCK_BYTES, g_files.pin[3]);
+    store_file(outfile, c.out2.p, blocks_for(res[0]) * DBT_BLOCK_BYTES, g_files.pin[4]);
+    stage_resolve();
     *nres = clamp32(res[0]);
-    *nios = clamp32(dbt_mergejoin_nios(r.nblocks, s.nblocks, nmem_blocks, res));
+    *nios = clamp32(dbt_mergejoin_nios(nbr, nbs, nmem_blocks, res));
 }
 
 void HashJoin(char *infile1, char *infile2, unsigned char field, block_t *, unsigned int nmem_blocks, char *outfile,
               unsigned int *nres, unsigned int *nios) {
     if (nmem_blocks < 2) die("HashJoin: nmem_blocks must be >= 2");
-    PinnedFile r, s;
-    r.read(infile1);
-    s.read(infile2);
+    HostCtx &c = ctx();
+    const uint64_t nbr = load_file(infile1, g_files.pin[0], c.in_r);
+    const uint64_t nbs = load_file(infile2, g_files.pin[1], c.in_s);
     uint64_t n = 0;
-    PinnedOut out;
     if (field >= '0' && field <= '3') {
-        uint64_t cap = s.nblocks; // fields '0'..'2' emit each S row at most once
-        out.alloc((size_t)cap * DBT_BLOCK_BYTES);
-        int rc = dbt_host_hashjoin(r.p, r.nblocks, s.p, s.nblocks, field, out.p, cap, device_from_env(), &n);
+        uint64_t cap = nbs; // fields '0'..'2' emit each S row at most once
+        must(c.out0.ensure((size_t)cap * DBT_BLOCK_BYTES), "device output");
+        auto run = [&](uint64_t capb) {
+            return with_ws(DBT_OP_HASHJOIN, nbr, nbs, field, [&](void *ws, size_t wb) {
+                return dbt_dev_hashjoin(c.in_r.p, nbr, c.in_s.p, nbs, field, c.out0.p, capb, ws, wb, c.st, &n);
+            });
+        };
+        int rc = run(cap);
         if (rc == DBT_ERR_WORKSPACE && n > cap * kRpb) { // field '3' with many R duplicates: retry with the exact size
             cap = blocks_for(n);
-            cudaFreeHost(out.p);
-            out.p = nullptr;
-            out.alloc((size_t)cap * DBT_BLOCK_BYTES);
-            rc = dbt_host_hashjoin(r.p, r.nblocks, s.p, s.nblocks, field, out.p, cap, device_from_env(), &n);
+            must(c.out0.ensure((size_t)cap * DBT_BLOCK_BYTES), "device output");
+            rc = run(cap);
         }
-        must(rc, "dbt_host_hashjoin");
+        must(rc, "dbt_dev_hashjoin");
     } // else: the reference's if/else chains match nothing for an unknown field (no message, nres = 0)
-    write_file(outfile, out.p, blocks_for(n) * DBT_BLOCK_BYTES);
+    store_file(outfile, c.out0.p, blocks_for(n) * DBT_BLOCK_BYTES, g_files.pin[2]);
+    stage_resolve();
     *nres = clamp32(n);
-    *nios = clamp32(dbt_hashjoin_nios(r.nblocks, s.nblocks, nmem_blocks, n));
+    *nios = clamp32(dbt_hashjoin_nios(nbr, nbs, nmem_blocks, n));
 }
