@@ -519,6 +519,52 @@ def extra_measurements(dbt, torch, dev, peak):
         torch.cuda.empty_cache()
     except Exception as e:  # noqa: BLE001
         out["pair_sort_1B_u32"] = {"error": str(e)[:200]}
+    # BASELINE configs[0]: MergeSort field=num on a 1M-record block file, nmem_blocks=64, through the real
+    # file-based drop-in entry point (as main.o would call it), files in tmpfs; the reference binary beside it
+    try:
+        import shutil
+        import tempfile
+
+        n0 = 1_000_000
+        nb0 = n0 // RPB
+        img = torch.empty(nb0 * BLOCK_BYTES, dtype=torch.uint8, device=dev)
+        dbt.check(L.dbt_gen_syn(42, n0, 300_000, 1, 0, n0, 0, img.data_ptr(), sp))  # ~3.3 rows per key, like main.cpp:47
+        torch.cuda.synchronize()
+        root = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+        d = tempfile.mkdtemp(prefix="dbtcfg0_", dir=root)
+        cwd = os.getcwd()
+        try:
+            img.cpu().numpy().tofile(os.path.join(d, "file.bin"))
+            os.chdir(d)
+            f = getattr(L, dbt.CXX_ENTRY_POINTS["MergeSort"])
+            f.restype = None
+            a, b, c = C.c_uint(), C.c_uint(), C.c_uint()
+            name = C.create_string_buffer(64)
+            best = 1e9
+            for _ in range(4):
+                t0 = time.perf_counter()
+                f(b"file.bin", C.c_ubyte(ord(FIELD)), None, C.c_uint(NMEM), name, C.byref(a), C.byref(b), C.byref(c))
+                best = min(best, time.perf_counter() - t0)
+            entry = {"ms": best * 1e3, "records_per_s": n0 / best, "nsorted_segs": a.value, "npasses": b.value, "nios": c.value,
+                     "outfile": name.value.decode(), "path": "file -> pinned (parallel pread) -> HBM -> kernels -> pinned -> file"}
+            ref = None
+            try:  # cpu-baseline leg: the untouched reference on the same file
+                from oracle import pyoracle as orc
+
+                if orc.ref_available():
+                    p = subprocess.run([orc.REF_RUNNER, "sort", FIELD, str(NMEM), "file.bin"], cwd=d, capture_output=True, text=True)
+                    info = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
+                    ref = {"ms": info["seconds"] * 1e3, "records_per_s": n0 / info["seconds"], "nsorted_segs": info["a"],
+                           "npasses": info["b"], "nios": info["nios"], "cores": 1}
+            except Exception:  # noqa: BLE001
+                ref = None
+            out["cfg0_mergesort_1M_record_file"] = {"dbt_b200_entry_point": entry, "reference": ref}
+        finally:
+            os.chdir(cwd)
+            shutil.rmtree(d, ignore_errors=True)
+        del img
+    except Exception as e:  # noqa: BLE001
+        out["cfg0_mergesort_1M_record_file"] = {"error": str(e)[:200]}
     # HashJoin field=num, R=100M x S=400M rows (BASELINE configs[3] asks for S=1B: 140 GB of S records do not
     # fit beside R and the output on one 180 GB GPU, so the single-GPU figure uses the largest S that does)
     for kind, label in ((1, "uniform"), (2, "skewed")):

@@ -152,6 +152,12 @@ int intersect_sorted(const KeyCols &r, const uint32_t *d_ur, const uint32_t *d_u
                      const uint32_t *d_us, const uint32_t *d_uskeys, uint64_t nus, int field, uint32_t *d_flags,
                      uint64_t *d_later_reads, Arena &ws, cudaStream_t st);
 
+int match_ranges(const KeyCols &r, const uint32_t *d_rperm, const uint32_t *d_rsorted_w0, const KeyCols &s, int field,
+                 uint32_t *d_first, uint32_t *d_count, cudaStream_t st);
+int expand_pairs(const uint32_t *d_count, const uint32_t *d_first, uint64_t ns, const uint32_t *d_rperm,
+                 const uint32_t *d_r_recid, const uint32_t *d_s_recid, uint32_t *d_pairs, uint64_t cap, uint64_t *d_total,
+                 Arena &ws, cudaStream_t st);
+
 // generator (kernels_gen.cu)
 int gen_syn(uint64_t seed, uint64_t n_total, uint64_t U, int kind, uint64_t row0, uint64_t nrows, uint32_t recid0,
             void *d_image, cudaStream_t st);

@@ -487,6 +487,47 @@ extern "C" int dbt_dev_mergejoin(const void *d_in_r, uint64_t nbr, const void *d
     return finish(st);
 }
 
+extern "C" int dbt_dev_innerjoin_pairs(const void *d_in_r, uint64_t nbr, const void *d_in_s, uint64_t nbs, int field,
+                                       uint32_t *d_pairs, uint64_t pairs_capacity, void *d_ws, size_t ws_bytes, void *stream,
+                                       uint64_t *npairs) {
+    DBT_CHECK_ARGS(field_ok(field), "Wrong field! Please give a field between 0 and 3!");
+    DBT_CHECK_ARGS(d_ws && npairs, "dbt_dev_innerjoin_pairs: NULL buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    Arena ws(d_ws, ws_bytes);
+    Prepared pr, ps;
+    DBT_TRY(prepare(d_in_r, nbr, field, ws, st, &pr));
+    DBT_TRY(prepare(d_in_s, nbs, field, ws, st, &ps));
+    if (field >= '2' && pr.keys.kw != ps.keys.kw && pr.info.nrows && ps.info.nrows) {
+        if (pr.keys.kw < ps.keys.kw) DBT_TRY(prepare(d_in_r, nbr, field, ws, st, &pr, ps.keys.kw));
+        else DBT_TRY(prepare(d_in_s, nbs, field, ws, st, &ps, pr.keys.kw));
+    }
+    *npairs = 0;
+    const uint64_t nr = pr.info.nrows, ns = ps.info.nrows;
+    if (nr && ns) {
+        // the sort may clobber R's key column (1-word keys): keep the recid column, it is what the pairs carry
+        uint32_t *rperm, *rsorted;
+        DBT_TRY(sort_rows_by_key(pr.keys, field, ws, st, &rperm, &rsorted));
+        uint32_t *first = ws.take<uint32_t>(ns), *count = ws.take<uint32_t>(ns);
+        uint64_t *d_total = ws.take<uint64_t>(8);
+        if (!first || !count || !d_total) {
+            set_error("innerjoin: workspace too small");
+            return DBT_ERR_WORKSPACE;
+        }
+        DBT_TRY(match_ranges(pr.keys, rperm, rsorted, ps.keys, field, first, count, st));
+        DBT_TRY(expand_pairs(count, first, ns, rperm, pr.keys.recid, ps.keys.recid, d_pairs, d_pairs ? pairs_capacity : 0, d_total,
+                             ws, st));
+        uint64_t total = 0;
+        DBT_TRY(read_u64(d_total, &total, 1, st));
+        *npairs = total;
+        if (total > pairs_capacity) {
+            set_error("innerjoin: pair capacity too small (npairs returned)");
+            DBT_TRY(finish(st));
+            return DBT_ERR_WORKSPACE;
+        }
+    }
+    return finish(st);
+}
+
 extern "C" int dbt_dev_hashjoin(const void *d_in_r, uint64_t nbr, const void *d_in_s, uint64_t nbs, int field,
                                 void *d_out, uint64_t out_capacity_blocks, void *d_ws, size_t ws_bytes, void *stream,
                                 uint64_t *nres) {

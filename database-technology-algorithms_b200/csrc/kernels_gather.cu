@@ -107,7 +107,15 @@ scan_emit_kernel(uint64_t n, CountFn cnt, EmitFn emit, ScanWs ws, unsigned long 
     __syncthreads();
     extern __shared__ uint32_t s_stage[]; // [kScanTile] (+ [kScanTile] when EmitFn::kTwo)
     const uint64_t tile_prefix = s_prefix;
-    if constexpr (EmitFn::kIndexed) { // plain exclusive scan: every input row records its offset
+    if constexpr (EmitFn::kCustom) { // the functor writes its own (variable-length) output for row i at [off, off+c)
+        uint64_t off = tile_prefix + pre + x - local;
+#pragma unroll 1
+        for (int k = 0; k < kScanItems; ++k) {
+            if (c[k]) emit.expand(i0 + k, off, c[k], pay[k]);
+            off += c[k];
+        }
+        return;
+    } else if constexpr (EmitFn::kIndexed) { // plain exclusive scan: every input row records its offset
         uint64_t off = tile_prefix + pre + x - local;
 #pragma unroll
         for (int k = 0; k < kScanItems; ++k) {
@@ -279,11 +287,13 @@ template <bool TWO>
 struct EmitPerm { // out1 = the row (payload); out2 = its key from the sorted column (optional)
     static constexpr bool kTwo = TWO;
     static constexpr bool kIndexed = false;
+    static constexpr bool kCustom = false;
     uint32_t *out1;
     uint32_t *out2;
     const uint32_t *sorted;
     uint64_t cap;
     __device__ void at(uint64_t, uint64_t) const {}
+    __device__ void expand(uint64_t, uint64_t, uint32_t, uint32_t) const {}
     __device__ uint32_t v1(uint64_t, uint32_t row) const { return row; }
     __device__ uint32_t v2(uint64_t i, uint32_t) const { return sorted[i]; }
 };
@@ -318,10 +328,12 @@ struct CountFromArray {
 struct EmitRowRepeated {
     static constexpr bool kTwo = false;
     static constexpr bool kIndexed = false;
+    static constexpr bool kCustom = false;
     uint32_t *out1;
     uint32_t *out2;
     uint64_t cap;
     __device__ void at(uint64_t, uint64_t) const {}
+    __device__ void expand(uint64_t, uint64_t, uint32_t, uint32_t) const {}
     __device__ uint32_t v1(uint64_t, uint32_t v) const { return v; }
     __device__ uint32_t v2(uint64_t, uint32_t) const { return 0u; }
 };
@@ -331,14 +343,51 @@ int compact_select(const uint32_t *d_counts, const uint32_t *d_values, uint64_t 
     return run_scan_emit(n, CountFromArray{d_counts, d_values}, EmitRowRepeated{d_out, nullptr, out_cap}, d_total, ws, st);
 }
 
+// inner-join pair expansion: S row i with `c` matches starting at sorted-R position `first` emits
+// (recid_R[rperm[first+t]], recid_S[i]) for t < c
+struct EmitPairs {
+    static constexpr bool kTwo = false;
+    static constexpr bool kIndexed = false;
+    static constexpr bool kCustom = true;
+    const uint32_t *rperm, *r_recid, *s_recid;
+    uint32_t *pairs;
+    uint32_t *out1 = nullptr, *out2 = nullptr;
+    uint64_t cap;
+    __device__ void at(uint64_t, uint64_t) const {}
+    __device__ uint32_t v1(uint64_t, uint32_t) const { return 0u; }
+    __device__ uint32_t v2(uint64_t, uint32_t) const { return 0u; }
+    __device__ void expand(uint64_t i, uint64_t off, uint32_t c, uint32_t first) const {
+        const uint32_t sid = s_recid[i];
+        for (uint32_t t = 0; t < c; ++t)
+            if (off + t < cap) {
+                pairs[2 * (off + t)] = r_recid[rperm[first + t]];
+                pairs[2 * (off + t) + 1] = sid;
+            }
+    }
+};
+int expand_pairs(const uint32_t *d_count, const uint32_t *d_first, uint64_t ns, const uint32_t *d_rperm,
+                 const uint32_t *d_r_recid, const uint32_t *d_s_recid, uint32_t *d_pairs, uint64_t cap, uint64_t *d_total,
+                 Arena &ws, cudaStream_t st) {
+    StageScope sc(ST_COMPACT, st);
+    EmitPairs e;
+    e.rperm = d_rperm;
+    e.r_recid = d_r_recid;
+    e.s_recid = d_s_recid;
+    e.pairs = d_pairs;
+    e.cap = cap;
+    return run_scan_emit(ns, CountFromArray{d_count, d_first}, e, d_total, ws, st);
+}
+
 // exclusive prefix sums of a u32 array (offsets < 2^32): out[i] = sum(counts[0..i))
 struct EmitOffset {
     static constexpr bool kTwo = false;
     static constexpr bool kIndexed = true;
+    static constexpr bool kCustom = false;
     uint32_t *out;
     uint32_t *out1 = nullptr, *out2 = nullptr; // unused by the indexed mode
     uint64_t cap = 0;
     __device__ void at(uint64_t i, uint64_t off) const { out[i] = (uint32_t)off; }
+    __device__ void expand(uint64_t, uint64_t, uint32_t, uint32_t) const {}
     __device__ uint32_t v1(uint64_t, uint32_t) const { return 0u; }
     __device__ uint32_t v2(uint64_t, uint32_t) const { return 0u; }
 };

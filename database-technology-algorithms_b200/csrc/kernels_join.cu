@@ -482,6 +482,52 @@ gather_keys_kernel(KeyView kv, const uint32_t *__restrict__ rows, uint64_t n, ui
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Inner-join pairs: for every S row the range of equal keys in the sorted R list.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+match_range_kernel(SortedList r, KeyView sv, uint64_t ns, uint32_t *__restrict__ first, uint32_t *__restrict__ count) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < ns; q += stride) {
+        // lower and upper bound of S row q's key in the sorted R list
+        auto cmp_at = [&](uint64_t i) -> int { // key(R_sorted[i]) vs key(S[q])
+            if (r.keys) {
+                uint32_t x = r.keys[i], y = sv.w0[q];
+                return x < y ? -1 : (x > y ? 1 : 0);
+            }
+            return rows_cmp(r.kv, r.rows[i], sv, (uint32_t)q);
+        };
+        uint64_t lo = 0, hi = r.n;
+        while (lo < hi) {
+            uint64_t mid = (lo + hi) >> 1;
+            if (cmp_at(mid) < 0) lo = mid + 1;
+            else hi = mid;
+        }
+        uint64_t lb = lo;
+        hi = r.n;
+        while (lo < hi) {
+            uint64_t mid = (lo + hi) >> 1;
+            if (cmp_at(mid) <= 0) lo = mid + 1;
+            else hi = mid;
+        }
+        first[q] = (uint32_t)lb;
+        count[q] = (uint32_t)(lo - lb);
+    }
+}
+int match_ranges(const KeyCols &r, const uint32_t *d_rperm, const uint32_t *d_rsorted_w0, const KeyCols &s, int field,
+                 uint32_t *d_first, uint32_t *d_count, cudaStream_t st) {
+    if (!s.n) return 0;
+    StageScope sc(ST_HASH_PROBE, st);
+    const bool one = (field == '0' || field == '1');
+    SortedList rl{one ? d_rsorted_w0 : nullptr, d_rperm, KeyView{field == '2' ? nullptr : r.w0, r.str, r.kw}, r.n};
+    KeyView sv{field == '2' ? nullptr : s.w0, s.str, s.kw};
+    int grid = (int)std::min<uint64_t>((s.n + 255) / 256, 148 * 16);
+    match_range_kernel<<<grid, 256, 0, st>>>(rl, sv, s.n, d_first, d_count);
+    count_launch();
+    DBT_KERNEL_CHECK();
+    return 0;
+}
+
 int intersect_sorted(const KeyCols &r, const uint32_t *d_ur, const uint32_t *d_urkeys, uint64_t nur, const KeyCols &s,
                      const uint32_t *d_us, const uint32_t *d_uskeys, uint64_t nus, int field, uint32_t *d_flags,
                      uint64_t *d_later_reads, Arena &ws, cudaStream_t st) {

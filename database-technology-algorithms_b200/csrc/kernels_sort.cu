@@ -351,154 +351,155 @@ struct Os2Smem {
 
 template <int THREADS, int ITEMS, bool HAS_VALS, bool IOTA_VALS, int RANK, bool FULL>
 __device__ __forceinline__ void os2_process_tile(Os2Smem<THREADS, ITEMS> &sm, int stg, uint32_t tile,
-                                                 const uint32_t *__restrict__ kin, uint32_t *__restrict__ kout,
-                                                 const uint32_t *__restrict__ vin, uint32_t *__restrict__ vout,
-                                                 uint32_t n, int shift, const uint32_t *__restrict__ digit_base,
-                                                 uint32_t *state) {
+                                             const uint32_t *__restrict__ kin, uint32_t *__restrict__ kout,
+                                             const uint32_t *__restrict__ vin, uint32_t *__restrict__ vout,
+                                             uint32_t n, int shift, const uint32_t *__restrict__ digit_base,
+                                             uint32_t *state) {
     using Smem = Os2Smem<THREADS, ITEMS>;
     constexpr int WARPS = Smem::WARPS;
     constexpr int TILE = Smem::TILE;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = lanemask_lt();
-        const uint32_t base = tile * (uint32_t)TILE;
-        const uint32_t nvalid = FULL ? (uint32_t)TILE : n - base;
-        const uint32_t nbulk = FULL ? (uint32_t)TILE : (((nvalid * 4u) & ~15u) >> 2);
-        uint32_t *skeys = sm.keys[stg];
-        uint32_t *svals = sm.vals[stg];
-        const uint32_t li0 = warp * (ITEMS * 32) + lane; // warp-striped arrangement inside the tile
+    const uint32_t base = tile * (uint32_t)TILE;
+    const uint32_t nvalid = FULL ? (uint32_t)TILE : n - base;
+    const uint32_t nbulk = FULL ? (uint32_t)TILE : (((nvalid * 4u) & ~15u) >> 2);
+    uint32_t *skeys = sm.keys[stg];
+    uint32_t *svals = sm.vals[stg];
+    const uint32_t li0 = warp * (ITEMS * 32) + lane; // warp-striped arrangement inside the tile
 
-        uint32_t key[ITEMS];
+    uint32_t key[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const uint32_t li = li0 + j * 32;
+        if (FULL) key[j] = skeys[li];
+        else key[j] = (li < nbulk) ? skeys[li] : ((li < nvalid) ? kin[base + li] : 0xFFFFFFFFu);
+    }
+
+    // ---- rank inside the warp (positions fit 16 bits: two per register)
+    uint32_t rank2[(ITEMS + 1) / 2];
+#pragma unroll
+    for (int j = 0; j < (ITEMS + 1) / 2; ++j) rank2[j] = 0;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const uint32_t d = (key[j] >> shift) & 0xFFu;
+        bool valid = true;
+        uint32_t peers;
+        if (RANK == 0 || (RANK == 2 && (j & 1))) {
+            if (!FULL) valid = li0 + j * 32 < nvalid;
+            peers = __match_any_sync(0xFFFFFFFFu, valid ? d : 0x100u);
+        } else if (RANK >= 13 && RANK <= 15) {
+            // hybrid: match.any on the low K bits (cost ~ number of distinct values: <= 2^K groups, ADU pipe)
+            // and one ballot per remaining bit (ALU pipe): every item loads both pipes lightly
+            constexpr int K = RANK - 10;
+            if (!FULL) valid = li0 + j * 32 < nvalid;
+            peers = __match_any_sync(0xFFFFFFFFu, valid ? (d & ((1u << K) - 1u)) : (1u << K));
+#pragma unroll
+            for (int b = K; b < 8; ++b) {
+                const bool bit = (d >> b) & 1u;
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, bit);
+                peers &= bit ? m : ~m;
+            }
+        } else {
+            peers = 0xFFFFFFFFu;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const bool bit = (d >> b) & 1u;
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, bit);
+                peers &= bit ? m : ~m;
+            }
+            if (!FULL) {
+                valid = li0 + j * 32 < nvalid;
+                const uint32_t vm = __ballot_sync(0xFFFFFFFFu, valid);
+                peers &= valid ? vm : ~vm;
+            }
+        }
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (lane == leader && valid) {
+            old = sm.hist[warp][d];
+            sm.hist[warp][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xFFFFFFFFu, old, leader);
+        rank2[j >> 1] |= (old + __popc(peers & lt)) << ((j & 1) * 16);
+        __syncwarp();
+    }
+    uint32_t val[HAS_VALS ? ITEMS : 1];
+    if (HAS_VALS) {
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
             const uint32_t li = li0 + j * 32;
-            if (FULL) key[j] = skeys[li];
-            else key[j] = (li < nbulk) ? skeys[li] : ((li < nvalid) ? kin[base + li] : 0xFFFFFFFFu);
+            if (IOTA_VALS) val[j] = base + li;
+            else if (FULL) val[j] = svals[li];
+            else val[j] = (li < nbulk) ? svals[li] : ((li < nvalid) ? vin[base + li] : 0u);
         }
+    }
+    __syncthreads(); // every key/row of the tile is in registers; warp histograms are complete
 
-        // ---- rank inside the warp (positions fit 16 bits: two per register)
-        uint32_t rank2[(ITEMS + 1) / 2];
+    // ---- per digit: count, publish the aggregate at once, tile-local exclusive offsets
+    uint32_t count_d = 0, incl = 0;
+    if (tid < kRadix) {
 #pragma unroll
-        for (int j = 0; j < (ITEMS + 1) / 2; ++j) rank2[j] = 0;
+        for (int w = 0; w < WARPS; ++w) count_d += sm.hist[w][tid];
+        st_volatile(&state[(size_t)tile * kRadix + tid], (tile == 0 ? kFlagInc : kFlagAgg) | count_d);
+        incl = count_d;
 #pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-            const uint32_t d = (key[j] >> shift) & 0xFFu;
-            bool valid = true;
-            uint32_t peers;
-            if (RANK == 0 || (RANK == 2 && (j & 1))) {
-                if (!FULL) valid = li0 + j * 32 < nvalid;
-                peers = __match_any_sync(0xFFFFFFFFu, valid ? d : 0x100u);
-            } else if (RANK >= 13 && RANK <= 15) {
-                // hybrid: match.any on the low K bits (cost ~ number of distinct values: <= 2^K groups, ADU pipe)
-                // and one ballot per remaining bit (ALU pipe): every item loads both pipes lightly
-                constexpr int K = RANK - 10;
-                if (!FULL) valid = li0 + j * 32 < nvalid;
-                peers = __match_any_sync(0xFFFFFFFFu, valid ? (d & ((1u << K) - 1u)) : (1u << K));
-#pragma unroll
-                for (int b = K; b < 8; ++b) {
-                    const bool bit = (d >> b) & 1u;
-                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, bit);
-                    peers &= bit ? m : ~m;
-                }
-            } else {
-                peers = 0xFFFFFFFFu;
-#pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    const bool bit = (d >> b) & 1u;
-                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, bit);
-                    peers &= bit ? m : ~m;
-                }
-                if (!FULL) {
-                    valid = li0 + j * 32 < nvalid;
-                    const uint32_t vm = __ballot_sync(0xFFFFFFFFu, valid);
-                    peers &= valid ? vm : ~vm;
-                }
-            }
-            const int leader = __ffs(peers) - 1;
-            uint32_t old = 0;
-            if (lane == leader && valid) {
-                old = sm.hist[warp][d];
-                sm.hist[warp][d] = old + __popc(peers);
-            }
-            old = __shfl_sync(0xFFFFFFFFu, old, leader);
-            rank2[j >> 1] |= (old + __popc(peers & lt)) << ((j & 1) * 16);
-            __syncwarp();
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += t;
         }
-        uint32_t val[HAS_VALS ? ITEMS : 1];
-        if (HAS_VALS) {
+        if (lane == 31) sm.wsum[warp] = incl;
+    }
+    __syncthreads();
+    uint32_t excl_d = 0;
+    if (tid < kRadix) {
+        uint32_t pre = 0;
+        for (int w = 0; w < warp; ++w) pre += sm.wsum[w];
+        excl_d = pre + incl - count_d;
+        uint32_t acc = excl_d; // hist[w][d] := tile-local offset of warp w's first key with digit d
 #pragma unroll
-            for (int j = 0; j < ITEMS; ++j) {
-                const uint32_t li = li0 + j * 32;
-                if (IOTA_VALS) val[j] = base + li;
-                else if (FULL) val[j] = svals[li];
-                else val[j] = (li < nbulk) ? svals[li] : ((li < nvalid) ? vin[base + li] : 0u);
-            }
+        for (int w = 0; w < WARPS; ++w) {
+            const uint32_t t = sm.hist[w][tid];
+            sm.hist[w][tid] = acc;
+            acc += t;
         }
-        __syncthreads(); // every key/row of the tile is in registers; warp histograms are complete
+    }
+    __syncthreads();
 
-        // ---- per digit: count, publish the aggregate at once, tile-local exclusive offsets
-        uint32_t count_d = 0, incl = 0;
-        if (tid < kRadix) {
+    // ---- stage the tile ordered by digit, in place (the look-back latency hides behind this)
 #pragma unroll
-            for (int w = 0; w < WARPS; ++w) count_d += sm.hist[w][tid];
-            st_volatile(&state[(size_t)tile * kRadix + tid], (tile == 0 ? kFlagInc : kFlagAgg) | count_d);
-            incl = count_d;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            if (lane == 31) sm.wsum[warp] = incl;
+    for (int j = 0; j < ITEMS; ++j) {
+        const uint32_t d = (key[j] >> shift) & 0xFFu;
+        const uint32_t pos = sm.hist[warp][d] + ((rank2[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu);
+        if (FULL || (li0 + j * 32 < nvalid)) {
+            skeys[pos] = key[j];
+            if (HAS_VALS) svals[pos] = val[j];
         }
-        __syncthreads();
-        uint32_t excl_d = 0;
-        if (tid < kRadix) {
-            uint32_t pre = 0;
-            for (int w = 0; w < warp; ++w) pre += sm.wsum[w];
-            excl_d = pre + incl - count_d;
-            uint32_t acc = excl_d; // hist[w][d] := tile-local offset of warp w's first key with digit d
-#pragma unroll
-            for (int w = 0; w < WARPS; ++w) {
-                const uint32_t t = sm.hist[w][tid];
-                sm.hist[w][tid] = acc;
-                acc += t;
-            }
+    }
+    if (tid < kRadix) { // decoupled look-back, one thread per digit
+        uint32_t excl_prefix = 0;
+        if (tile > 0) {
+            excl_prefix = lookback_exclusive(state, tile, tid);
+            st_volatile(&state[(size_t)tile * kRadix + tid], kFlagInc | (excl_prefix + count_d));
         }
-        __syncthreads();
+        sm.goff[tid] = digit_base[tid] + excl_prefix - excl_d;
+    }
+    __syncthreads();
 
-        // ---- stage the tile ordered by digit, in place (the look-back latency hides behind this)
+    // ---- coalesced writes of the digit runs
 #pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-            const uint32_t d = (key[j] >> shift) & 0xFFu;
-            const uint32_t pos = sm.hist[warp][d] + ((rank2[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu);
-            if (FULL || (li0 + j * 32 < nvalid)) {
-                skeys[pos] = key[j];
-                if (HAS_VALS) svals[pos] = val[j];
-            }
+    for (int j = 0; j < ITEMS; ++j) {
+        const uint32_t i = tid + j * THREADS;
+        if (FULL || i < nvalid) {
+            const uint32_t k = skeys[i];
+            const uint32_t dst = sm.goff[(k >> shift) & 0xFFu] + i;
+            kout[dst] = k;
+            if (HAS_VALS) vout[dst] = svals[i];
         }
-        if (tid < kRadix) { // decoupled look-back, one thread per digit
-            uint32_t excl_prefix = 0;
-            if (tile > 0) {
-                excl_prefix = lookback_exclusive(state, tile, tid);
-                st_volatile(&state[(size_t)tile * kRadix + tid], kFlagInc | (excl_prefix + count_d));
-            }
-            sm.goff[tid] = digit_base[tid] + excl_prefix - excl_d;
-        }
-        __syncthreads();
-
-        // ---- coalesced writes of the digit runs
-#pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-            const uint32_t i = tid + j * THREADS;
-            if (FULL || i < nvalid) {
-                const uint32_t k = skeys[i];
-                const uint32_t dst = sm.goff[(k >> shift) & 0xFFu] + i;
-                kout[dst] = k;
-                if (HAS_VALS) vout[dst] = svals[i];
-            }
-        }
+    }
 }
 
-// RANK: 0 = match.any, 1 = 8 ballots, 2 = mixed (even items ballots, odd items match.any)
+// RANK: 0 = match.any, 1 = 8 ballots, 2 = alternating (even items ballots, odd items match.any),
+//       10+K = match.any on the K low digit bits + (8-K) ballots (13 is the tuned default)
 template <int THREADS, int ITEMS, bool HAS_VALS, bool IOTA_VALS, int RANK>
 __global__ void __launch_bounds__(THREADS, (THREADS * ITEMS <= 4096) ? 3 : ((THREADS * ITEMS <= 6144) ? 2 : 1))
 onesweep2_kernel(const uint32_t *__restrict__ kin, uint32_t *__restrict__ kout, const uint32_t *__restrict__ vin,

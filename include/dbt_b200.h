@@ -122,6 +122,14 @@ int dbt_dev_hashjoin(const void *d_in_r, uint64_t nblocks_r, const void *d_in_s,
                      void *d_out, uint64_t out_capacity_blocks, void *d_ws, size_t ws_bytes, void *stream,
                      uint64_t *nres);
 
+/* Pair-producing inner join -- an EXTENSION (north_star compares joins as (recid_R, recid_S) multisets; the
+ * reference itself only emits records).  d_pairs[2k] = recid of the R row, d_pairs[2k+1] = recid of
+ * the S row, for every pair of rows with equal key(field); S file order, then R rows by (key, recid).
+ * pairs_capacity bounds d_pairs (in pairs); *npairs is always the true count (DBT_ERR_WORKSPACE if it did not fit). */
+int dbt_dev_innerjoin_pairs(const void *d_in_r, uint64_t nblocks_r, const void *d_in_s, uint64_t nblocks_s, int field,
+                            uint32_t *d_pairs, uint64_t pairs_capacity, void *d_ws, size_t ws_bytes, void *stream,
+                            uint64_t *npairs);
+
 /* ----------------------------------------------------------------------------------------------
  * Multi-GPU building blocks.  The operators shard by KEY: sort / dedup by key range
  * (sample-sort splitters, so equal keys meet on one GPU and the concatenation of the ranks' outputs

@@ -285,6 +285,32 @@ int64_t orc_hashjoin(const void *inR, int64_t nbR, const void *inS, int64_t nbS,
     return k;
 }
 
+/* Pair-producing inner join (EXTENSION: north_star's comparison format; the reference never emits pairs,
+ * SURVEY.md F9).  pairs[2k] = recid of the R row, pairs[2k+1] = recid of the S row, for every (R row, S row)
+ * with equal key(field); order: S file order, then R rows by (key, recid).  Call with pairs=NULL to count.
+ * Consistency with the reference: the distinct S recids of the pairs are HashJoin's output for
+ * fields '0'..'2'; the number of pairs is HashJoin's nres for field '3'. */
+int64_t orc_innerjoin_pairs(const void *inR, int64_t nbR, const void *inS, int64_t nbS, int field, uint32_t *pairs) {
+    const orc_record **r, **s;
+    int64_t nr = collect_rows((const orc_block *)inR, nbR, &r);
+    int64_t ns = collect_rows((const orc_block *)inS, nbS, &s);
+    sort_rows(r, nr, field);
+    int64_t k = 0;
+    for (int64_t q = 0; q < ns; ++q) {
+        int64_t lo = 0, hi = nr;
+        while (lo < hi) {
+            int64_t mid = (lo + hi) / 2;
+            if (cmp_key(r[mid], s[q], field) < 0) lo = mid + 1; else hi = mid;
+        }
+        for (int64_t t = lo; t < nr && cmp_key(r[t], s[q], field) == 0; ++t) {
+            if (pairs) { pairs[2 * k] = r[t]->recid; pairs[2 * k + 1] = s[q]->recid; }
+            ++k;
+        }
+    }
+    free(r); free(s);
+    return k;
+}
+
 /* ------------------------------------------------------------------------------------------
  * Counters.  B input blocks, M = nmem_blocks, F = M-1.
  * reference: DatabaseProject.cpp:191-233 (runs of M blocks, each written as exactly M blocks),

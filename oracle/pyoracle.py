@@ -76,6 +76,8 @@ def lib() -> C.CDLL:
         L.orc_mergejoin.argtypes = [vp, i64, vp, i64, ci, vp, vp, vp, C.POINTER(i64)]
         L.orc_hashjoin.restype = i64
         L.orc_hashjoin.argtypes = [vp, i64, vp, i64, ci, vp]
+        L.orc_innerjoin_pairs.restype = i64
+        L.orc_innerjoin_pairs.argtypes = [vp, i64, vp, i64, ci, vp]
         L.orc_sort_counters.restype = None
         L.orc_sort_counters.argtypes = [i64, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
         L.orc_dedup_nios.restype = i64
@@ -173,6 +175,14 @@ def hashjoin(r: np.ndarray, s: np.ndarray, field) -> np.ndarray:
     k = lib().orc_hashjoin(_p(r), len(r), _p(s), len(s), _fld(field), None)
     out = new_blocks((k + RPB - 1) // RPB)
     lib().orc_hashjoin(_p(r), len(r), _p(s), len(s), _fld(field), _p(out))
+    return out
+
+
+def innerjoin_pairs(r: np.ndarray, s: np.ndarray, field) -> np.ndarray:
+    """(recid_R, recid_S) for every matching row pair (extension)."""
+    k = lib().orc_innerjoin_pairs(_p(r), len(r), _p(s), len(s), _fld(field), None)
+    out = np.zeros((k, 2), dtype=np.uint32)
+    lib().orc_innerjoin_pairs(_p(r), len(r), _p(s), len(s), _fld(field), _p(out))
     return out
 
 

@@ -205,3 +205,27 @@ def test_joins_with_long_strings_on_one_side_only(dbt, orc):
         got, ur, us, info = H.dev_mergejoin(dbt, orc, r, s, field, kw=30)
         want, wur, wus, winfo = orc.mergejoin(r, s, field)
         assert info == winfo and H.same_image(got, want) and H.same_image(us, wus), field
+
+
+@pytest.mark.parametrize("field", FIELDS)
+def test_innerjoin_pairs_match_the_oracle(dbt, orc, files, field):
+    import ctypes as C
+    import torch
+
+    r, s = orc.gen_ref(5, 60, num_mod=700)  # ~8.6 rows per key: real multiplicities on both sides
+    want = orc.innerjoin_pairs(r, s, field)
+    d_r, d_s = H.to_dev(r), H.to_dev(s)
+    cap = max(len(want), 1)
+    d_pairs = torch.empty(cap * 2, dtype=torch.int32, device="cuda")
+    wsb = dbt.dev_ws_bytes(dbt.OP_MERGEJOIN, len(r), len(s), field)
+    ws = H.dev_alloc(wsb)
+    n = C.c_uint64()
+    dbt.check(dbt.lib().dbt_dev_innerjoin_pairs(d_r.data_ptr(), len(r), d_s.data_ptr(), len(s), ord(field), d_pairs.data_ptr(), cap,
+                                                ws.data_ptr(), wsb, H.stream(), C.byref(n)))
+    assert n.value == len(want)
+    got = d_pairs.cpu().numpy().view(np.uint32).reshape(-1, 2)[: n.value]
+    assert np.array_equal(got, want)  # same order too: S file order, then R rows by (key, recid)
+    if len(want) > 1:
+        rc = dbt.lib().dbt_dev_innerjoin_pairs(d_r.data_ptr(), len(r), d_s.data_ptr(), len(s), ord(field), d_pairs.data_ptr(), 1,
+                                               ws.data_ptr(), wsb, H.stream(), C.byref(n))
+        assert rc == -3 and n.value == len(want)  # capacity too small: loud, with the needed size

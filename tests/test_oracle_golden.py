@@ -143,3 +143,24 @@ def test_syn_generator_duplicate_structure(orc):
     assert np.array_equal(rows["recid"], np.arange(n))
     sub = orc.rows_of(orc.gen_syn(42, n, U, 0, row0=5000, nrows=300))
     assert np.array_equal(sub["num"], rows["num"][5000:5300])  # any sub-range is reproducible
+
+
+@pytest.mark.parametrize("field", "0123")
+def test_inner_join_pairs_are_consistent_with_the_reference(orc, golden, inputs, field):
+    """The pair-producing inner join is an extension (the reference never emits pairs); its oracle is
+    pinned to the reference through the two consistency rules of SURVEY 8c."""
+    meta, arr = golden
+    pairs = orc.innerjoin_pairs(inputs[0], inputs[1], field)
+    ref_nres = meta["counters"][f"hjoin_f{field}"]["nres"]
+    if field == "3":
+        assert len(pairs) == ref_nres                       # |pairs| == REF HashJoin nres for field '3'
+    else:
+        distinct_s = np.unique(pairs[:, 1])
+        assert np.array_equal(distinct_s, np.sort(arr[f"hjoin_f{field}"]))  # distinct recid_S == REF HashJoin output
+    # and with CANON's own hash join: S recids of the pairs (with multiplicity) == field-'3'-style expansion
+    r_rows, s_rows = orc.rows_of(inputs[0]), orc.rows_of(inputs[1])
+    key = {"0": lambda x: x["recid"], "1": lambda x: x["num"]}.get(field)
+    if key is not None:
+        rk, sk = key(r_rows), key(s_rows)
+        cnt = {k: c for k, c in zip(*np.unique(rk, return_counts=True))}
+        assert len(pairs) == sum(cnt.get(k, 0) for k in sk.tolist())
