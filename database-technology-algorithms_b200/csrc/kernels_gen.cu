@@ -60,11 +60,25 @@ gen_syn_kernel(uint64_t seed, uint64_t n_total, uint64_t U, int kind, uint64_t r
 #pragma unroll
                 for (int i = 0; i < (int)kRecWords; ++i) w[i] = 0;
                 w[0] = recid0 + (uint32_t)r;
-                w[1] = syn_num(seed, n_total, U, kind, r);
+                // kind 3: with probability 1/2 this row copies the (num, str) of a pseudo-random row of the PARTNER
+                // relation (generated with kind 1 and seed ^ 0x5EED), so that about half of the composite keys match
+                uint64_t kseed = seed, krow = r;
+                int kkind = kind;
+                if (kind == 3) {
+                    const uint64_t h3 = mix64(seed * 0x100000001B3ull + r + 0x777ull);
+                    kkind = 1;
+                    if (h3 & 1) {
+                        kseed = seed ^ 0x5EEDull;
+                        krow = (h3 >> 1) % n_total;
+                    }
+                }
+                w[1] = syn_num(kseed, n_total, U, kkind, krow);
+                r = krow; // the string below follows the same (seed, row)
+                const uint64_t seed_s = kseed;
                 if (r % kRpb == 1) {
                     w[2] = 0x616C6F48u; // "Hola" little-endian
                 } else {
-                    uint64_t h = mix64((seed ^ 0x5bd1e995ull) * 0x100000001B3ull + r);
+                    uint64_t h = mix64((seed_s ^ 0x5bd1e995ull) * 0x100000001B3ull + r);
                     uint32_t c0 = 'a' + (uint32_t)(h % 26); h /= 26;
                     uint32_t c1 = 'a' + (uint32_t)(h % 26); h /= 26;
                     uint32_t c2 = 'a' + (uint32_t)(h % 26); h /= 26;

@@ -203,7 +203,8 @@ int dbt_host_free(void *p);
  * Synthetic inputs generated directly in HBM (SURVEY.md 8d "G_syn"; the distribution follows
  * the reference generator main.cpp:41-77: 100 live rows per block, recid = row index, 5-letter
  * strings, "Hola" at row 1 of every block).  kind: 0 = exactly U distinct num keys over n rows,
- * 1 = uniform over [0,U), 2 = heavy-head power law over [0,U).  Same arithmetic as
+ * 1 = uniform over [0,U), 2 = heavy-head power law over [0,U), 3 = half of the rows copy (num, str) of a random
+ * row of the partner relation (kind 1, seed ^ 0x5EED) so that composite-key joins match.  Same arithmetic as
  * oracle/dbt_oracle.c orc_gen_syn so any sub-range can be reproduced on the CPU.
  * ---------------------------------------------------------------------------------------------- */
 int dbt_gen_syn(uint64_t seed, uint64_t n_total, uint64_t U, int kind, uint64_t row0, uint64_t nrows, uint32_t recid0,

@@ -446,8 +446,18 @@ void orc_gen_syn(uint64_t seed, uint64_t n_total, uint64_t U, int kind, uint64_t
         uint64_t r = row0 + k;
         orc_record *rec = &bl[k / ORC_RPB].entries[k % ORC_RPB];
         rec->recid = recid0 + (uint32_t)r;
-        rec->num = orc_syn_num(seed, n_total, U, kind, r);
-        uint64_t h = mix64((seed ^ 0x5bd1e995ull) * 0x100000001B3ull + r);
+        /* kind 3: with probability 1/2 the row copies (num, str) of a pseudo-random row of the partner relation
+         * (kind 1, seed ^ 0x5EED): about half of the composite keys of the two relations match */
+        uint64_t kseed = seed, krow = r;
+        int kkind = kind;
+        if (kind == 3) {
+            uint64_t h3 = mix64(seed * 0x100000001B3ull + r + 0x777ull);
+            kkind = 1;
+            if (h3 & 1) { kseed = seed ^ 0x5EEDull; krow = (h3 >> 1) % n_total; }
+        }
+        rec->num = orc_syn_num(kseed, n_total, U, kkind, krow);
+        r = krow;
+        uint64_t h = mix64((kseed ^ 0x5bd1e995ull) * 0x100000001B3ull + r);
         if (r % ORC_RPB == 1) { memcpy(rec->str, "Hola", 5); }
         else for (int i = 0; i < 5; ++i) { rec->str[i] = (char)('a' + (h % 26)); h /= 26; }
         rec->valid = 1;

@@ -229,3 +229,20 @@ def test_innerjoin_pairs_match_the_oracle(dbt, orc, files, field):
         rc = dbt.lib().dbt_dev_innerjoin_pairs(d_r.data_ptr(), len(r), d_s.data_ptr(), len(s), ord(field), d_pairs.data_ptr(), 1,
                                                ws.data_ptr(), wsb, H.stream(), C.byref(n))
         assert rc == -3 and n.value == len(want)  # capacity too small: loud, with the needed size
+
+
+def test_device_generator_matches_the_cpu_restatement_for_every_kind(dbt, orc):
+    import torch
+
+    n, U = 30000, 9000
+    for kind, seed in ((0, 42), (1, 7), (2, 9), (3, 21 ^ 0x5EED)):
+        d = H.dev_alloc(n // 100 * H.BLOCK_BYTES)
+        dbt.check(dbt.lib().dbt_gen_syn(seed, n, U, kind, 0, n, 0, d.data_ptr(), H.stream()))
+        torch.cuda.synchronize()
+        got = H.to_host(d, n // 100, orc)
+        want = orc.gen_syn(seed, n, U, kind)
+        assert H.same_image(got, want), (kind, H.first_diff(got, want))
+    r = orc.gen_syn(21, n, U, 1)
+    s = orc.gen_syn(21 ^ 0x5EED, n, U, 3)
+    matched = orc.count_rows(orc.hashjoin(r, s, "3"))
+    assert 0.35 * n < matched < 0.9 * n  # about half of S's rows carry a composite key of R (plus multiplicities)
