@@ -28,7 +28,7 @@ C_ABI_SYMBOLS = [
     "dbt_sort_counters", "dbt_dedup_nios", "dbt_hashjoin_nios", "dbt_mergejoin_nios",
     "dbt_sort_pairs_ws_bytes", "dbt_sort_pairs_u32", "dbt_gather_records", "dbt_gather_records_limited",
     "dbt_dev_extract_keys_u32", "dbt_dev_partition_rows", "dbt_dev_partition_ws_bytes",
-    "dbt_dev_ws_bytes", "dbt_dev_ws_bytes_kw", "dbt_dev_mergesort", "dbt_dev_dedup", "dbt_dev_mergejoin", "dbt_dev_hashjoin", "dbt_dev_innerjoin_pairs",
+    "dbt_dev_ws_bytes", "dbt_dev_ws_bytes_kw", "dbt_dev_mergesort", "dbt_dev_dedup", "dbt_dev_mergejoin", "dbt_dev_hashjoin", "dbt_dev_innerjoin_pairs", "dbt_dev_semijoin_keys",
     "dbt_host_mergesort", "dbt_host_dedup", "dbt_host_mergejoin", "dbt_host_hashjoin",
     "dbt_dev_extract_key_recid_u32", "dbt_dev_take_u32", "dbt_dev_order_columns", "dbt_dev_order_columns_ws_bytes",
     "dbt_gather_records_multi", "dbt_ipc_export",
@@ -89,6 +89,7 @@ def lib() -> C.CDLL:
     L.dbt_dev_dedup.argtypes = [vp, u64, ci, vp, vp, sz, vp, pu64, pu64]
     L.dbt_dev_mergejoin.argtypes = [vp, u64, vp, u64, ci, vp, vp, vp, vp, sz, vp, pu64]
     L.dbt_dev_hashjoin.argtypes = [vp, u64, vp, u64, ci, vp, u64, vp, sz, vp, pu64]
+    L.dbt_dev_semijoin_keys.argtypes = [vp, u64, vp, u64, ci, vp, u64, vp, sz, vp, pu64]
     L.dbt_dev_innerjoin_pairs.argtypes = [vp, u64, vp, u64, ci, vp, u64, vp, sz, vp, pu64]
     L.dbt_dev_extract_keys_u32.argtypes = [vp, u64, ci, vp, vp, sz, vp, pu64]
     L.dbt_dev_partition_rows.argtypes = [vp, u64, ci, C.POINTER(u32), u32, vp, pu64, vp, sz, vp]

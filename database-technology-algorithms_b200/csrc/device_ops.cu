@@ -487,6 +487,46 @@ extern "C" int dbt_dev_mergejoin(const void *d_in_r, uint64_t nbr, const void *d
     return finish(st);
 }
 
+extern "C" int dbt_dev_semijoin_keys(const uint32_t *d_rkeys, uint64_t nr, const void *d_in_s, uint64_t nbs, int field,
+                                     void *d_out, uint64_t out_capacity_blocks, void *d_ws, size_t ws_bytes, void *stream,
+                                     uint64_t *nres) {
+    DBT_CHECK_ARGS(field == '0' || field == '1', "dbt_dev_semijoin_keys: u32 keys only (fields '0' and '1')");
+    DBT_CHECK_ARGS(d_ws && nres && (d_rkeys || nr == 0), "dbt_dev_semijoin_keys: NULL buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    Arena ws(d_ws, ws_bytes);
+    Prepared ps;
+    DBT_TRY(prepare(d_in_s, nbs, field, ws, st, &ps));
+    *nres = 0;
+    const uint64_t ns = ps.info.nrows;
+    if (ns && nr) {
+        KeyCols rk;
+        memset(&rk, 0, sizeof rk);
+        rk.w0 = const_cast<uint32_t *>(d_rkeys);
+        rk.n = nr;
+        rk.kw = 8;
+        uint32_t *counts = ws.take<uint32_t>(ns);
+        const uint64_t cap = out_capacity_blocks * kRpb;
+        const uint64_t rows_cap = std::max<uint64_t>(std::min<uint64_t>(cap, ns), 1);
+        uint32_t *rows = ws.take<uint32_t>(rows_cap);
+        uint64_t *d_total = ws.take<uint64_t>(8);
+        if (!counts || !rows || !d_total) {
+            set_error("semijoin: workspace too small");
+            return DBT_ERR_WORKSPACE;
+        }
+        DBT_TRY(hash_join_counts(rk, ps.keys, field, counts, ws, st));
+        DBT_TRY(compact_select(counts, nullptr, ns, rows, rows_cap, d_total, ws, st));
+        uint64_t total = 0;
+        DBT_TRY(read_u64(d_total, &total, 1, st));
+        *nres = total;
+        if (total > cap) {
+            set_error("semijoin: output capacity too small (nres returned)");
+            return DBT_ERR_WORKSPACE;
+        }
+        DBT_TRY(gather_records(d_in_s, rows, ps.row_slot, total, d_out, st));
+    }
+    return finish(st);
+}
+
 extern "C" int dbt_dev_innerjoin_pairs(const void *d_in_r, uint64_t nbr, const void *d_in_s, uint64_t nbs, int field,
                                        uint32_t *d_pairs, uint64_t pairs_capacity, void *d_ws, size_t ws_bytes, void *stream,
                                        uint64_t *npairs) {

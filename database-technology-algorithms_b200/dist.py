@@ -154,6 +154,17 @@ class LocalOps:
         idx = (self.torch.arange(nsamples, device=self.device, dtype=self.torch.int64) * n) // nsamples  # exact (float32 linspace is not)
         return keys[idx].to(self.torch.int64) & 0xFFFFFFFF
 
+    def semijoin_keys(self, rkeys, img_s, nb_s: int, field: str):
+        """S rows (S order) whose key is in the key column `rkeys` (fields '0'/'1')."""
+        dbt = self.dbt
+        out = self.alloc(nb_s * BLOCK_BYTES)
+        # the workspace bound of a hash join whose build side has as many rows as there are keys
+        wsb = dbt.dev_ws_bytes(dbt.OP_HASHJOIN, (rkeys.numel() + RPB - 1) // RPB + 1, nb_s, field)
+        n = C.c_uint64()
+        dbt.check(self.L.dbt_dev_semijoin_keys(rkeys.data_ptr(), rkeys.numel(), img_s.data_ptr(), nb_s, ord(field), out.data_ptr(),
+                                               nb_s, self.workspace(wsb).data_ptr(), wsb, self._stream(), C.byref(n)))
+        return out, {"out_rows": n.value}
+
     def run(self, op: str, field: str, img_r, nb_r: int, img_s=None, nb_s: int = 0):
         """The ordinary device-scope operator on (possibly ragged) images; returns (out image, info)."""
         dbt = self.dbt
@@ -223,6 +234,7 @@ class DistOps:
         self.sort_mode = os.environ.get("DBT_DIST_SORT", default_mode) if self.peer_exchange else "records"
         self.rows_stay_put = self.sort_mode == "keys"
         self._side = None
+        self.join_mode = os.environ.get("DBT_DIST_JOIN", "replicate")  # u32 semi-joins: "replicate" R's keys | "partition" both sides
         self.push_ctas = int(os.environ.get("DBT_DIST_PUSH_CTAS", "296"))  # link-bound: 2 CTAs per SM leave room for the main stream
 
     def _peer_image_bases(self, img):
@@ -491,9 +503,37 @@ class DistOps:
         return self.ops.run("dedup", field, recv, nb)
 
     def hashjoin(self, img_r, nb_r: int, img_s, nb_s: int, field: str):
+        if field in ("0", "1") and hasattr(self.ops, "semijoin_keys") and self.join_mode == "replicate":
+            return self._hashjoin_replicated_keys(img_r, nb_r, img_s, nb_s, field)
         rr, nbr = self.exchange(img_r, nb_r, field, mode=1)
         rs, nbs = self.exchange(img_s, nb_s, field, mode=1, slot=1)
         return self.ops.run("hashjoin", field, rr, nbr, rs, nbs)
+
+    def _hashjoin_replicated_keys(self, img_r, nb_r: int, img_s, nb_s: int, field: str):
+        """Semi-join by replicating the build side's KEYS: one all-gather of 4 bytes per R row, then every rank
+        probes its own S shard in place.  No S record moves, key skew cannot unbalance the ranks, and the ranks'
+        outputs concatenate in S file order (what the reference's HashJoin produces)."""
+        torch, dist, P = self.torch, self.dist, self.world
+        keys = self.ops.extract_keys(img_r, nb_r, field)
+        n_local = torch.tensor([keys.numel()], dtype=torch.int64, device=keys.device)
+        sizes = [torch.empty_like(n_local) for _ in range(P)]
+        dist.all_gather(sizes, n_local, group=self.group)
+        sizes = [int(x.item()) for x in sizes]
+        mx = max(max(sizes), 1)
+        padded = torch.zeros(mx, dtype=keys.dtype, device=keys.device)
+        padded[: keys.numel()] = keys
+        allk = torch.empty(mx * P, dtype=keys.dtype, device=keys.device)
+        ev = None
+        if keys.is_cuda:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        dist.all_gather_into_tensor(allk, padded, group=self.group)
+        if ev:
+            ev[1].record()
+        rkeys = torch.cat([allk[r * mx: r * mx + sizes[r]] for r in range(P)]) if any(s != mx for s in sizes) else allk
+        self.last_exchange = {"bytes_sent_remote": 4 * keys.numel() * (P - 1), "bytes_sent": 4 * keys.numel() * P, "events": ev,
+                              "mode": "replicated build keys (all-gather), S probed in place"}
+        return self.ops.semijoin_keys(rkeys, img_s, nb_s, field)
 
     def mergejoin(self, img_r, nb_r: int, img_s, nb_s: int, field: str):
         # both relations must use the SAME splitters so that equal keys of R and S meet

@@ -122,6 +122,14 @@ int dbt_dev_hashjoin(const void *d_in_r, uint64_t nblocks_r, const void *d_in_s,
                      void *d_out, uint64_t out_capacity_blocks, void *d_ws, size_t ws_bytes, void *stream,
                      uint64_t *nres);
 
+/* HashJoin with the build side given as a key column instead of an image (fields '0' and '1'): the S rows, in S
+ * file order, whose key is in d_rkeys[0..nr).  This is what a multi-GPU semi-join wants: the ranks all-gather R's
+ * KEYS (4 bytes each) and probe their own shard of S in place -- no S record crosses the fabric, key skew cannot
+ * unbalance anything, and the concatenation of the ranks' outputs is in S file order like the reference's. */
+int dbt_dev_semijoin_keys(const uint32_t *d_rkeys, uint64_t nr, const void *d_in_s, uint64_t nblocks_s, int field,
+                          void *d_out, uint64_t out_capacity_blocks, void *d_ws, size_t ws_bytes, void *stream,
+                          uint64_t *nres);
+
 /* Pair-producing inner join -- an EXTENSION (north_star compares joins as (recid_R, recid_S) multisets; the
  * reference itself only emits records).  d_pairs[2k] = recid of the R row, d_pairs[2k+1] = recid of
  * the S row, for every pair of rows with equal key(field); S file order, then R rows by (key, recid).

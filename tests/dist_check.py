@@ -51,7 +51,9 @@ def main():
             checks = {
                 f"sort{field}": (orc.rows_of(orc.sort(f1, field))["recid"], False),
                 f"dedup{field}": (orc.rows_of(orc.dedup(f1, field))["recid"], False),
-                f"hashjoin{field}": (orc.rows_of(orc.hashjoin(f1, f2, field))["recid"], True),
+                # u32 keys: replicated build keys => the ranks' outputs concatenate in S file order (exact compare);
+                # str / composite keys: hash partition => compare as sorted multisets
+                f"hashjoin{field}": (orc.rows_of(orc.hashjoin(f1, f2, field))["recid"], field in ("2", "3")),
                 f"mergejoin{field}": (orc.rows_of(orc.mergejoin(f1, f2, field)[0])["recid"], False),
             }
             for name, (want, as_set) in checks.items():
