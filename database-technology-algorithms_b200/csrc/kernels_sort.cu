@@ -110,8 +110,10 @@ __global__ void __launch_bounds__(512) hist_kernel(const uint32_t *__restrict__ 
     __shared__ uint32_t sh[4][kRadix];
     for (int i = threadIdx.x; i < 4 * kRadix; i += blockDim.x) (&sh[0][0])[i] = 0;
     __syncthreads();
-    uint64_t nvec = n / 4;
-    const uint4 *kv = reinterpret_cast<const uint4 *>(keys);
+    // the caller's buffer may be only 4-byte aligned: scalar head up to the first 16-byte boundary, vector body, scalar tail
+    const uint64_t head = min(n, (uint64_t)(((16u - (uint32_t)((uintptr_t)keys & 15u)) & 15u) >> 2));
+    const uint64_t nvec = (n - head) / 4;
+    const uint4 *kv = reinterpret_cast<const uint4 *>(keys + head);
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
         uint4 v = kv[i];
@@ -126,10 +128,16 @@ __global__ void __launch_bounds__(512) hist_kernel(const uint32_t *__restrict__ 
             }
         }
     }
-    // tail (n % 4) by the first threads of block 0
-    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
-        uint32_t k = keys[nvec * 4 + threadIdx.x];
-        for (int p = 0; p < plan.npass; ++p) atomicAdd(&sh[p][(k >> plan.shift[p]) & 0xFF], 1u);
+    // head and tail elements (at most 3 + 3) by the first threads of block 0
+    if (blockIdx.x == 0 && threadIdx.x < 8) {
+        const uint64_t ntail = (n - head) & 3;
+        uint64_t idx = n; // none
+        if (threadIdx.x < head) idx = threadIdx.x;
+        else if (threadIdx.x >= 4 && threadIdx.x - 4 < ntail) idx = head + nvec * 4 + (threadIdx.x - 4);
+        if (idx < n) {
+            uint32_t k = keys[idx];
+            for (int p = 0; p < plan.npass; ++p) atomicAdd(&sh[p][(k >> plan.shift[p]) & 0xFF], 1u);
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < plan.npass * kRadix; i += blockDim.x) {

@@ -246,3 +246,31 @@ def test_device_generator_matches_the_cpu_restatement_for_every_kind(dbt, orc):
     s = orc.gen_syn(21 ^ 0x5EED, n, U, 3)
     matched = orc.count_rows(orc.hashjoin(r, s, "3"))
     assert 0.35 * n < matched < 0.9 * n  # about half of S's rows carry a composite key of R (plus multiplicities)
+
+
+def test_sort_pairs_unaligned_buffers_take_the_fallback_kernel(dbt):
+    """cp.async.bulk needs 16-byte aligned sources; buffers that are only 4-byte aligned go through the
+    one-tile-per-CTA onesweep kernel instead.  Same result either way (also covers a partial last tile)."""
+    import ctypes as C
+    import torch
+
+    n = 1_234_567
+    g = torch.Generator(device="cuda").manual_seed(11)
+    base = torch.randint(0, 2**32, (n + 8,), dtype=torch.int64, device="cuda", generator=g).to(torch.uint32)
+    keys = base[1:n + 1]                                  # data_ptr is 4 bytes past a 16-byte boundary
+    assert keys.data_ptr() % 16 == 4
+    k1 = torch.empty(n + 8, dtype=torch.uint32, device="cuda")[1:n + 1]
+    k1.copy_(keys)
+    k2 = torch.empty(n + 8, dtype=torch.uint32, device="cuda")[1:n + 1]
+    v1 = torch.arange(n + 8, dtype=torch.int32, device="cuda")[1:n + 1].clone()
+    v1b = torch.empty(n + 8, dtype=torch.int32, device="cuda")[1:n + 1]
+    v1b.copy_(torch.arange(n, dtype=torch.int32, device="cuda"))
+    v2 = torch.empty(n + 8, dtype=torch.int32, device="cuda")[1:n + 1]
+    wsb = dbt.lib().dbt_sort_pairs_ws_bytes(n)
+    ws = H.dev_alloc(wsb)
+    alt = C.c_int()
+    dbt.check(dbt.lib().dbt_sort_pairs_u32(k1.data_ptr(), k2.data_ptr(), v1b.data_ptr(), v2.data_ptr(), n, 0, 32, ws.data_ptr(), wsb,
+                                           H.stream(), C.byref(alt)))
+    ko, vo = (k2, v2) if alt.value else (k1, v1b)
+    ref_k, ref_i = torch.sort(keys.to(torch.int64), stable=True)
+    assert torch.equal(ko.to(torch.int64), ref_k) and torch.equal(vo.to(torch.int64), ref_i)
