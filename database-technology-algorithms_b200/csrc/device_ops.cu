@@ -12,6 +12,8 @@
 
 namespace dbt {
 
+static inline bool is_aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
+
 struct Prepared {
     ImageInfo info;
     uint32_t *row_slot; // nullptr when slot == row
@@ -168,6 +170,17 @@ extern "C" size_t dbt_dev_ws_bytes(int op, uint64_t nbr, uint64_t nbs, int field
     return dbt_dev_ws_bytes_kw(op, nbr, nbs, field, 8);
 }
 
+static inline bool aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
+#define DBT_CHECK_ALIGNED(...)                                                                        \
+    do {                                                                                              \
+        const void *ptrs__[] = {__VA_ARGS__};                                                         \
+        for (const void *q__ : ptrs__)                                                                \
+            if (!aligned16(q__)) {                                                                    \
+                set_error("device buffers (images, columns, workspace) must be 16-byte aligned");    \
+                return DBT_ERR_ARG;                                                                   \
+            }                                                                                         \
+    } while (0)
+
 #define DBT_CHECK_ARGS(cond, msg)  \
     do {                           \
         if (!(cond)) {             \
@@ -290,6 +303,10 @@ extern "C" size_t dbt_dev_order_columns_ws_bytes(uint64_t m) { return 5 * pad256
 
 extern "C" int dbt_dev_order_columns(uint32_t *d_keys, const uint32_t *d_recids, uint64_t m, int dedup, uint32_t *d_order,
                                      uint64_t *count, void *d_ws, size_t ws_bytes, void *stream) {
+    if (!is_aligned16(d_keys) || !is_aligned16(d_recids) || !is_aligned16(d_order) || !is_aligned16(d_ws)) {
+        set_error("dbt_dev_order_columns: buffers must be 16-byte aligned");
+        return DBT_ERR_ARG;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     Arena ws(d_ws, ws_bytes);
     if (count) *count = 0;
@@ -343,6 +360,10 @@ extern "C" int dbt_dev_partition_rows(const uint32_t *d_keys, uint64_t n, int mo
         set_error("dbt_dev_partition_rows: bad arguments (1 <= nparts <= 64)");
         return DBT_ERR_ARG;
     }
+    if (!is_aligned16(d_keys) || !is_aligned16(d_rows_grouped) || !is_aligned16(d_ws)) {
+        set_error("dbt_dev_partition_rows: buffers must be 16-byte aligned");
+        return DBT_ERR_ARG;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     Arena ws(d_ws, ws_bytes);
     for (uint32_t i = 0; i < nparts; ++i) h_counts[i] = 0;
@@ -382,6 +403,7 @@ extern "C" int dbt_dev_mergesort(const void *d_in, uint64_t nblocks, int field, 
                                  void *stream, uint64_t *nrows) {
     DBT_CHECK_ARGS(field_ok(field), "Wrong field! Please give a field between 0 and 3!");
     DBT_CHECK_ARGS((d_in && d_out && d_ws) || nblocks == 0, "dbt_dev_mergesort: NULL buffer");
+    DBT_CHECK_ALIGNED(d_in, d_out, d_ws);
     cudaStream_t st = (cudaStream_t)stream;
     Arena ws(d_ws, ws_bytes);
     Prepared p;
@@ -397,6 +419,7 @@ extern "C" int dbt_dev_dedup(const void *d_in, uint64_t nblocks, int field, void
                              void *stream, uint64_t *nrows, uint64_t *nunique) {
     DBT_CHECK_ARGS(field_ok(field), "Wrong field! Please give a field between 0 and 3!");
     DBT_CHECK_ARGS((d_in && d_out && d_ws) || nblocks == 0, "dbt_dev_dedup: NULL buffer");
+    DBT_CHECK_ALIGNED(d_in, d_out, d_ws);
     cudaStream_t st = (cudaStream_t)stream;
     Arena ws(d_ws, ws_bytes);
     Prepared p;
@@ -449,6 +472,7 @@ extern "C" int dbt_dev_mergejoin(const void *d_in_r, uint64_t nbr, const void *d
                                  uint64_t *res) {
     DBT_CHECK_ARGS(field_ok(field), "Wrong field! Please give a field between 0 and 3!");
     DBT_CHECK_ARGS(d_ws && res, "dbt_dev_mergejoin: NULL buffer");
+    DBT_CHECK_ALIGNED(d_in_r, d_in_s, d_out_ur, d_out_us, d_out, d_ws);
     cudaStream_t st = (cudaStream_t)stream;
     Arena ws(d_ws, ws_bytes);
     Prepared pr, ps;
@@ -492,6 +516,7 @@ extern "C" int dbt_dev_semijoin_keys(const uint32_t *d_rkeys, uint64_t nr, const
                                      uint64_t *nres) {
     DBT_CHECK_ARGS(field == '0' || field == '1', "dbt_dev_semijoin_keys: u32 keys only (fields '0' and '1')");
     DBT_CHECK_ARGS(d_ws && nres && (d_rkeys || nr == 0), "dbt_dev_semijoin_keys: NULL buffer");
+    DBT_CHECK_ALIGNED(d_rkeys, d_in_s, d_out, d_ws);
     cudaStream_t st = (cudaStream_t)stream;
     Arena ws(d_ws, ws_bytes);
     Prepared ps;
@@ -532,6 +557,7 @@ extern "C" int dbt_dev_innerjoin_pairs(const void *d_in_r, uint64_t nbr, const v
                                        uint64_t *npairs) {
     DBT_CHECK_ARGS(field_ok(field), "Wrong field! Please give a field between 0 and 3!");
     DBT_CHECK_ARGS(d_ws && npairs, "dbt_dev_innerjoin_pairs: NULL buffer");
+    DBT_CHECK_ALIGNED(d_in_r, d_in_s, d_pairs, d_ws);
     cudaStream_t st = (cudaStream_t)stream;
     Arena ws(d_ws, ws_bytes);
     Prepared pr, ps;
@@ -573,6 +599,7 @@ extern "C" int dbt_dev_hashjoin(const void *d_in_r, uint64_t nbr, const void *d_
                                 uint64_t *nres) {
     DBT_CHECK_ARGS(field_ok(field), "Wrong field! Please give a field between 0 and 3!");
     DBT_CHECK_ARGS(d_ws && nres, "dbt_dev_hashjoin: NULL buffer");
+    DBT_CHECK_ALIGNED(d_in_r, d_in_s, d_out, d_ws);
     cudaStream_t st = (cudaStream_t)stream;
     Arena ws(d_ws, ws_bytes);
     Prepared pr, ps;

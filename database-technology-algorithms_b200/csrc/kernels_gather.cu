@@ -583,13 +583,17 @@ extern "C" int dbt_gather_records(const void *d_in_image, const uint32_t *d_rows
         dbt::set_error("dbt_gather_records: NULL image");
         return DBT_ERR_ARG;
     }
+    if (((uintptr_t)d_in_image & 3) || ((uintptr_t)d_out_image & 15)) {
+        dbt::set_error("dbt_gather_records: the output image must be 16-byte aligned (the input 4-byte)");
+        return DBT_ERR_ARG;
+    }
     return dbt::gather_records(d_in_image, d_rows, d_row_slot, nrows_out, d_out_image, (cudaStream_t)stream, 0);
 }
 
 extern "C" int dbt_gather_records_limited(const void *d_in_image, const uint32_t *d_rows, const uint32_t *d_row_slot,
                                           uint64_t nrows_out, void *d_out_image, void *stream, int max_ctas) {
-    if (!d_in_image || !d_out_image) {
-        dbt::set_error("dbt_gather_records_limited: NULL image");
+    if (!d_in_image || !d_out_image || ((uintptr_t)d_out_image & 15)) {
+        dbt::set_error("dbt_gather_records_limited: NULL or misaligned image (output must be 16-byte aligned)");
         return DBT_ERR_ARG;
     }
     return dbt::gather_records(d_in_image, d_rows, d_row_slot, nrows_out, d_out_image, (cudaStream_t)stream, max_ctas);

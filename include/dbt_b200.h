@@ -16,6 +16,9 @@
  *     synchronise that stream before returning (they hand row counts back to the host);
  *   - host-scope operators (dbt_host_*) take host pointers and do the host<->device copies
  *     themselves (pinned staging when the caller's memory is pageable);
+ *   - device images, column buffers and workspaces must be 16-byte aligned (anything from cudaMalloc is; a block
+ *     offset inside an image keeps it, 14016 = 876 x 16); misaligned pointers fail with DBT_ERR_ARG.  Only
+ *     dbt_sort_pairs_u32 accepts 4-byte aligned buffers (it then runs its non-TMA kernel);
  *   - there is NO CPU fallback anywhere: without a CUDA device every entry fails with
  *     DBT_ERR_CUDA.
  */

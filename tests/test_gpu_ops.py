@@ -274,3 +274,19 @@ def test_sort_pairs_unaligned_buffers_take_the_fallback_kernel(dbt):
     ko, vo = (k2, v2) if alt.value else (k1, v1b)
     ref_k, ref_i = torch.sort(keys.to(torch.int64), stable=True)
     assert torch.equal(ko.to(torch.int64), ref_k) and torch.equal(vo.to(torch.int64), ref_i)
+
+
+def test_misaligned_images_are_rejected_not_faulted(dbt, orc):
+    f1 = orc.gen_ref(1, 4, two=False)
+    raw = H.dev_alloc(len(f1) * H.BLOCK_BYTES + 64)
+    src = H.to_dev(f1)
+    mis = raw[4:4 + len(f1) * H.BLOCK_BYTES]
+    mis.copy_(src[: len(f1) * H.BLOCK_BYTES])
+    out = H.dev_alloc(len(f1) * H.BLOCK_BYTES)
+    wsb = dbt.dev_ws_bytes(dbt.OP_SORT, len(f1), 0, "1")
+    ws = H.dev_alloc(wsb)
+    with pytest.raises(dbt.DbtError) as e:
+        dbt.dev_mergesort(mis.data_ptr(), len(f1), "1", out.data_ptr(), ws.data_ptr(), wsb, H.stream())
+    assert e.value.code == -1 and "aligned" in str(e.value)
+    got, n = H.dev_sort(dbt, orc, f1, "1")  # and the context is still healthy afterwards
+    assert H.same_image(got, orc.sort(f1, "1"))
