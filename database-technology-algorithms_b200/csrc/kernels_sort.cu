@@ -44,14 +44,14 @@ __device__ __forceinline__ uint32_t lookback_exclusive(const uint32_t *state, ui
         uint32_t s[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-            s[q] = (p - q >= 0) ? ld_volatile(&state[(size_t)(p - q) * 256 + col]) : 0x80000000u;
+            s[q] = (p - q >= 0) ? ld_volatile(&state[(size_t)(p - q) * kRadix + col]) : kFlagInc;
         int q = 0;
         bool done = false;
 #pragma unroll
         for (; q < 4; ++q) {
             if ((s[q] >> 30) == 0) break; // not published yet: poll again from here
-            excl += s[q] & 0x3FFFFFFFu;
-            if (s[q] & 0x80000000u) {
+            excl += s[q] & kValMask;
+            if (s[q] & kFlagInc) {
                 done = true;
                 break;
             }
@@ -188,7 +188,7 @@ onesweep_kernel(const uint32_t *__restrict__ kin, uint32_t *__restrict__ kout, c
     using Smem = OnesweepSmem<THREADS, ITEMS>;
     constexpr int WARPS = Smem::WARPS;
     constexpr int TILE = Smem::TILE;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -398,7 +398,7 @@ __device__ __forceinline__ void os2_process_tile(Os2Smem<THREADS, ITEMS> &sm, in
         } else if (RANK >= 13 && RANK <= 15) {
             // hybrid: match.any on the low K bits (cost ~ number of distinct values: <= 2^K groups, ADU pipe)
             // and one ballot per remaining bit (ALU pipe): every item loads both pipes lightly
-            constexpr int K = RANK - 10;
+            constexpr int K = (RANK >= 13 && RANK <= 15) ? RANK - 10 : 3; // (the other instantiations never run this branch)
             if (!FULL) valid = li0 + j * 32 < nvalid;
             peers = __match_any_sync(0xFFFFFFFFu, valid ? (d & ((1u << K) - 1u)) : (1u << K));
 #pragma unroll
@@ -519,9 +519,8 @@ onesweep2_kernel(const uint32_t *__restrict__ kin, uint32_t *__restrict__ kout, 
     constexpr bool LOAD_VALS = HAS_VALS && !IOTA_VALS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const uint32_t ntiles = (n + TILE - 1) / TILE;
-    const uint32_t lt = lanemask_lt();
 
     auto issue = [&](uint32_t t, int stg) { // thread 0: start the bulk copies of tile t into stage stg
         const uint32_t base = t * (uint32_t)TILE;
