@@ -17,6 +17,7 @@ LIB = os.path.join(HERE, "libdbt_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr"]
+CFLAGS += os.environ.get("DBT_NVCC_EXTRA", "").split()  # tuning hook, e.g. -DDBT_LOOKBACK_WINDOW=8
 
 
 def sources():
