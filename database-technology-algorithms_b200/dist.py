@@ -234,6 +234,11 @@ class DistOps:
         self.sort_mode = os.environ.get("DBT_DIST_SORT", default_mode) if self.peer_exchange else "records"
         self.rows_stay_put = self.sort_mode == "keys"
         self._side = None
+        if self.peer_exchange and not self._probe_peer_memory():
+            # CUDA IPC / peer access is not usable here (agreed on collectively): the record exchange over NCCL needs neither
+            self.peer_exchange = False
+            self.sort_mode = "records"
+            self.rows_stay_put = False
         self.join_mode = os.environ.get("DBT_DIST_JOIN", "replicate")  # u32 semi-joins: "replicate" R's keys | "partition" both sides
         self.push_ctas = int(os.environ.get("DBT_DIST_PUSH_CTAS", "296"))  # link-bound: 2 CTAs per SM leave room for the main stream
 
@@ -387,6 +392,26 @@ class DistOps:
                               "events": ev, "gather_events": gev, "mode": "keys+remote-gather",
                               "remote_record_bytes_read": int(remote_rows * (cnt / max(m, 1)) * 140), "splitters": splitters}
         return out, {"rows": m, "out_rows": cnt}
+
+    def _probe_peer_memory(self) -> bool:
+        """One-time check, agreed on by all ranks: can every rank map a buffer of every other rank and write to it?"""
+        torch, dist, P = self.torch, self.dist, self.world
+        ok = 1
+        try:
+            cap, own, peers = self._peer_buffers(-1, 1 << 20)
+            probe = torch.full((64,), self.rank + 1, dtype=torch.uint8, device=self.ops.device)
+            dist.barrier(group=self.group)
+            for r in range(P):  # every rank writes its id into its own 64-byte slot of everybody's buffer
+                self.ops.view(peers[r], 1 << 20)[self.rank * 64:(self.rank + 1) * 64].copy_(probe)
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            mine = self.ops.view(own, 1 << 20)[: P * 64].cpu().view(P, 64)
+            ok = int(all(int(mine[r, 0]) == r + 1 for r in range(P)))
+        except Exception:  # noqa: BLE001
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.ops.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        return bool(int(flag.item()))
 
     def _peer_buffers(self, slot: int, need_bytes: int):
         """Receive buffer `slot` of every rank, mapped here; (re)allocated collectively when too small."""
