@@ -186,9 +186,9 @@ class LocalOps:
             return out, {"out_rows": k}
         if op == "mergejoin":
             out = self.alloc(min(nb_r, nb_s) * BLOCK_BYTES)
-            ur, us = self.alloc(nb_r * BLOCK_BYTES), self.alloc(nb_s * BLOCK_BYTES)
             wsb = dbt.dev_ws_bytes(dbt.OP_MERGEJOIN, nb_r, nb_s, field)
-            info = dbt.dev_mergejoin(img_r.data_ptr(), nb_r, img_s.data_ptr(), nb_s, field, ur.data_ptr(), us.data_ptr(),
+            # no side images here: "1outfile.bin"/"2outfile.bin" belong to the file API (NULL skips their two gathers)
+            info = dbt.dev_mergejoin(img_r.data_ptr(), nb_r, img_s.data_ptr(), nb_s, field, None, None,
                                      out.data_ptr(), self.workspace(wsb).data_ptr(), wsb, self._stream())
             return out, {"out_rows": info["nres"], **info}
         raise ValueError(op)
