@@ -102,6 +102,7 @@ struct KeyCols {
     // host copies of the OR/AND statistics gathered during extraction
     uint32_t vary_w0, vary_recid, vary_str[30];
     int recid_unsorted;
+    const uint32_t *w0_byte_hist; // [4][256] histogram of w0's bytes made during extraction (or nullptr)
 };
 
 // ---- launchers implemented in the .cu files --------------------------------------------------
@@ -120,13 +121,15 @@ struct ExtractStats { // device-side
 };
 int extract_keys(const void *d_image, uint64_t nblocks_img, uint64_t nrows, const uint32_t *d_row_slot,
                  const uint32_t *d_blk_nres, const uint32_t *d_blk_row_off, int field, uint32_t kw, uint32_t *d_w0,
-                 uint32_t *d_str, uint32_t *d_recid, ExtractStats *d_stats, cudaStream_t st);
+                 uint32_t *d_str, uint32_t *d_recid, ExtractStats *d_stats, cudaStream_t st,
+                 uint32_t *d_byte_hist = nullptr, int *hist_done = nullptr);
 
 // radix sort (kernels_sort.cu)
 size_t sort_ws_bytes(uint64_t n);
 // sorts pairs over the key bits set in `varying_mask` (digits covering only constant bits are skipped)
 int sort_pairs_masked(uint32_t *&keys, uint32_t *&keys_alt, uint32_t *&vals, uint32_t *&vals_alt, uint64_t n,
-                      uint32_t varying_mask, bool iota_vals, Arena &ws, cudaStream_t st);
+                      uint32_t varying_mask, bool iota_vals, Arena &ws, cudaStream_t st,
+                      const uint32_t *byte_hist = nullptr /* [4][256] counts of the keys' bytes, if already known */);
 int or_and_reduce(const uint32_t *d_words, uint64_t n, uint32_t *d_or_and /*2 words*/, cudaStream_t st);
 int gather_word(const uint32_t *d_src, uint32_t stride, uint32_t word, const uint32_t *d_perm, uint32_t *d_out,
                 uint64_t n, cudaStream_t st);

@@ -42,8 +42,11 @@ static int prepare(const void *d_img, uint64_t nblocks, int field, Arena &ws, cu
         return DBT_ERR_WORKSPACE;
     }
     ExtractStats h;
+    uint32_t *d_byte_hist = has_w0 && !has_str ? ws.take<uint32_t>(4 * 256) : nullptr;
+    int hist_done = 0;
     DBT_TRY(extract_keys(d_img, nblocks, n, out->row_slot, out->info.blk_nres, out->info.blk_row_off, field, k.kw, k.w0, k.str,
-                         k.recid, d_stats, st));
+                         k.recid, d_stats, st, d_byte_hist, &hist_done));
+    k.w0_byte_hist = hist_done ? d_byte_hist : nullptr;
     DBT_CUDA(cudaMemcpyAsync(&h, d_stats, sizeof h, cudaMemcpyDeviceToHost, st));
     DBT_CUDA(cudaStreamSynchronize(st));
     if (has_str && h.str_overflow) {
@@ -103,7 +106,8 @@ static int sort_rows_by_key(KeyCols &k, int field, Arena &ws, cudaStream_t st, u
             StageScope sc(ST_WORD_GATHER, st);
             DBT_TRY(gather_word(w.src, w.stride, w.idx, first ? nullptr : vv, kk, n, st));
         }
-        DBT_TRY(sort_pairs_masked(kk, kk_alt, vv, vv_alt, n, w.vary, first, ws, st));
+        // the byte histogram made during extraction describes w0 in any order (a histogram is order-free)
+        DBT_TRY(sort_pairs_masked(kk, kk_alt, vv, vv_alt, n, w.vary, first, ws, st, (w.src == k.w0) ? k.w0_byte_hist : nullptr));
         first = false;
     }
     if (first) DBT_TRY(iota_u32(vv, n, st)); // nothing varied: identity order

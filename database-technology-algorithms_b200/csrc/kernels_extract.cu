@@ -231,13 +231,17 @@ __global__ void __launch_bounds__(kExThreads)
 extract_stream_kernel(const uint32_t *__restrict__ img, uint64_t nblocks, uint64_t nrows, uint32_t kw,
                       const uint32_t *__restrict__ blk_nres, const uint32_t *__restrict__ blk_row_off,
                       uint32_t *__restrict__ out_w0, uint32_t *__restrict__ out_str, uint32_t *__restrict__ out_recid,
-                      ExtractStats *stats) {
+                      ExtractStats *stats, uint32_t *__restrict__ byte_hist /*[4][256] or null: histogram of w0's bytes*/) {
     extern __shared__ __align__(128) unsigned char ex_raw[];
     uint32_t(*stage)[kBlockWords] = reinterpret_cast<uint32_t(*)[kBlockWords]>(ex_raw);
     uint64_t *mbar = reinterpret_cast<uint64_t *>(ex_raw + sizeof(uint32_t) * kBlockWords * kExStages);
     __shared__ uint32_t s_or[34], s_and[34], s_flags[2];
+    __shared__ uint32_t s_hist[4][256]; // bytes of w0 (the sort's digits when its plan is byte-aligned)
     const bool HAS_STR = (FIELD >= 2);
+    const bool HIST = (FIELD == 0 || FIELD == 1) && byte_hist != nullptr;
     const int tid = threadIdx.x, lane = tid & 31;
+    if (HIST)
+        for (int i = tid; i < 4 * 256; i += kExThreads) (&s_hist[0][0])[i] = 0;
     for (int i = tid; i < 34; i += kExThreads) {
         s_or[i] = 0;
         s_and[i] = 0xFFFFFFFFu;
@@ -286,6 +290,12 @@ extract_stream_kernel(const uint32_t *__restrict__ img, uint64_t nblocks, uint64
             const uint32_t w0 = (FIELD == 0) ? recid : ((FIELD == 2) ? 0u : rec[1]);
             out_recid[row] = recid;
             if (FIELD != 2) out_w0[row] = w0;
+            if (HIST) { // this kernel waits on DRAM: four shared-memory atomics per row are free here
+                atomicAdd(&s_hist[0][w0 & 0xFF], 1u);
+                atomicAdd(&s_hist[1][(w0 >> 8) & 0xFF], 1u);
+                atomicAdd(&s_hist[2][(w0 >> 16) & 0xFF], 1u);
+                atomicAdd(&s_hist[3][w0 >> 24], 1u);
+            }
             o_w0 |= w0;
             a_w0 &= w0;
             o_id |= recid;
@@ -336,6 +346,11 @@ extract_stream_kernel(const uint32_t *__restrict__ img, uint64_t nblocks, uint64
     }
     __syncthreads();
     if (my_blocks == 0) return;
+    if (HIST)
+        for (int i = tid; i < 4 * 256; i += kExThreads) {
+            const uint32_t c = (&s_hist[0][0])[i];
+            if (c) atomicAdd(&byte_hist[i], c);
+        }
     if (tid == 0) {
         atomicOr(&stats->or_w0, s_or[0]);
         atomicAnd(&stats->and_w0, s_and[0]);
@@ -353,40 +368,49 @@ extract_stream_kernel(const uint32_t *__restrict__ img, uint64_t nblocks, uint64
 template <int FIELD>
 static int launch_extract_stream(const uint32_t *img, uint64_t nblocks, uint64_t nrows, uint32_t kw,
                                  const uint32_t *blk_nres, const uint32_t *blk_row_off, uint32_t *d_w0,
-                                 uint32_t *d_str, uint32_t *d_recid, ExtractStats *d_stats, cudaStream_t st) {
+                                 uint32_t *d_str, uint32_t *d_recid, ExtractStats *d_stats, uint32_t *d_byte_hist,
+                                 cudaStream_t st) {
     size_t smem = sizeof(uint32_t) * kBlockWords * kExStages + 8 * kExStages + 128;
     auto kfn = extract_stream_kernel<FIELD>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static int per_sm = 0; // resident CTAs per SM: the grid is exactly one wave of them
+    if (!per_sm) {
         DBT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        int occ = 0;
+        DBT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, kExThreads, smem));
+        if (const char *e = getenv("DBT_EXTRACT_CTAS")) occ = std::min(occ, atoi(e));
+        per_sm = std::max(occ, 1);
     }
-    int grid = (int)std::min<uint64_t>(nblocks, 148 * 5);
-    kfn<<<grid, kExThreads, smem, st>>>(img, nblocks, nrows, kw, blk_nres, blk_row_off, d_w0, d_str, d_recid, d_stats);
+    int grid = (int)std::min<uint64_t>(nblocks, (uint64_t)148 * per_sm);
+    kfn<<<grid, kExThreads, smem, st>>>(img, nblocks, nrows, kw, blk_nres, blk_row_off, d_w0, d_str, d_recid, d_stats, d_byte_hist);
     return 0;
 }
 
 int extract_keys(const void *d_image, uint64_t nblocks_img, uint64_t nrows, const uint32_t *d_row_slot,
                  const uint32_t *d_blk_nres, const uint32_t *d_blk_row_off, int field, uint32_t kw, uint32_t *d_w0,
-                 uint32_t *d_str, uint32_t *d_recid, ExtractStats *d_stats, cudaStream_t st) {
+                 uint32_t *d_str, uint32_t *d_recid, ExtractStats *d_stats, cudaStream_t st, uint32_t *d_byte_hist,
+                 int *hist_done) {
     StageScope sc(ST_EXTRACT, st);
+    if (hist_done) *hist_done = 0;
     init_stats_kernel<<<1, 128, 0, st>>>(d_stats);
     count_launch();
     const bool ragged = d_row_slot != nullptr;
     const bool stream_ok = (!ragged || (d_blk_nres && d_blk_row_off)) && ((uintptr_t)d_image % 16 == 0) &&
                            getenv("DBT_EXTRACT_STRIDED") == nullptr;
+    if (d_byte_hist && stream_ok && nrows && (field == '0' || field == '1'))
+        DBT_CUDA(cudaMemsetAsync(d_byte_hist, 0, 4 * 256 * 4, st));
     if (nrows && stream_ok) {
         const uint32_t *img = (const uint32_t *)d_image;
         const uint64_t nblocks = ragged ? nblocks_img : (nrows + kRpb - 1) / kRpb;
         const uint32_t *bn = ragged ? d_blk_nres : nullptr, *bo = ragged ? d_blk_row_off : nullptr;
         switch (field) {
-        case '0': DBT_TRY(launch_extract_stream<0>(img, nblocks, nrows, kw, bn, bo, d_w0, d_str, d_recid, d_stats, st)); break;
-        case '1': DBT_TRY(launch_extract_stream<1>(img, nblocks, nrows, kw, bn, bo, d_w0, d_str, d_recid, d_stats, st)); break;
-        case '2': DBT_TRY(launch_extract_stream<2>(img, nblocks, nrows, kw, bn, bo, d_w0, d_str, d_recid, d_stats, st)); break;
-        case '3': DBT_TRY(launch_extract_stream<3>(img, nblocks, nrows, kw, bn, bo, d_w0, d_str, d_recid, d_stats, st)); break;
+        case '0': DBT_TRY(launch_extract_stream<0>(img, nblocks, nrows, kw, bn, bo, d_w0, d_str, d_recid, d_stats, d_byte_hist, st)); break;
+        case '1': DBT_TRY(launch_extract_stream<1>(img, nblocks, nrows, kw, bn, bo, d_w0, d_str, d_recid, d_stats, d_byte_hist, st)); break;
+        case '2': DBT_TRY(launch_extract_stream<2>(img, nblocks, nrows, kw, bn, bo, d_w0, d_str, d_recid, d_stats, d_byte_hist, st)); break;
+        case '3': DBT_TRY(launch_extract_stream<3>(img, nblocks, nrows, kw, bn, bo, d_w0, d_str, d_recid, d_stats, d_byte_hist, st)); break;
         default: set_error("bad field"); return DBT_ERR_ARG;
         }
         count_launch();
+        if (hist_done && d_byte_hist && (field == '0' || field == '1')) *hist_done = 1;
     } else if (nrows) {
         int grid = (int)((nrows + 255) / 256);
         const uint32_t *img = (const uint32_t *)d_image;

@@ -729,7 +729,7 @@ static DigitPlan plan_digits(uint32_t varying) {
 // first pass synthesises them, saving one read and one write of the row column).
 // On return keys/vals point at the buffers holding the result (swapped as needed).
 int sort_pairs_masked(uint32_t *&keys, uint32_t *&keys_alt, uint32_t *&vals, uint32_t *&vals_alt, uint64_t n,
-                      uint32_t varying_mask, bool iota_vals, Arena &ws, cudaStream_t st) {
+                      uint32_t varying_mask, bool iota_vals, Arena &ws, cudaStream_t st, const uint32_t *byte_hist) {
     if (n >= (1ull << 30)) {
         set_error("sort_pairs: n must be < 2^30 per call");
         return DBT_ERR_UNSUPPORTED;
@@ -748,13 +748,22 @@ int sort_pairs_masked(uint32_t *&keys, uint32_t *&keys_alt, uint32_t *&vals, uin
         set_error("sort_pairs: workspace too small");
         return DBT_ERR_WORKSPACE;
     }
+    bool byte_aligned = byte_hist != nullptr;
+    for (int p = 0; p < plan.npass; ++p) byte_aligned = byte_aligned && (plan.shift[p] % 8 == 0);
     {
         StageScope sc(ST_HIST, st);
-        DBT_CUDA(cudaMemsetAsync(ghist, 0, 4 * kRadix * 4, st));
-        int grid = (int)std::min<uint64_t>((n / 4 + 511) / 512 + 1, 148 * 4);
-        hist_kernel<<<grid, 512, 0, st>>>(keys, n, plan, ghist);
+        if (byte_aligned) { // the extraction already counted the key bytes: pick the planned digit positions, no key read
+            for (int p = 0; p < plan.npass; ++p)
+                DBT_CUDA(cudaMemcpyAsync(ghist + p * kRadix, byte_hist + (plan.shift[p] / 8) * kRadix, kRadix * 4,
+                                         cudaMemcpyDeviceToDevice, st));
+        } else {
+            DBT_CUDA(cudaMemsetAsync(ghist, 0, 4 * kRadix * 4, st));
+            int grid = (int)std::min<uint64_t>((n / 4 + 511) / 512 + 1, 148 * 4);
+            hist_kernel<<<grid, 512, 0, st>>>(keys, n, plan, ghist);
+            count_launch();
+        }
         hist_scan_kernel<<<plan.npass, kRadix, 0, st>>>(ghist);
-        count_launch(2);
+        count_launch();
         DBT_KERNEL_CHECK();
     }
     for (int p = 0; p < plan.npass; ++p) {

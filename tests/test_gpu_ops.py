@@ -290,3 +290,31 @@ def test_misaligned_images_are_rejected_not_faulted(dbt, orc):
     assert e.value.code == -1 and "aligned" in str(e.value)
     got, n = H.dev_sort(dbt, orc, f1, "1")  # and the context is still healthy afterwards
     assert H.same_image(got, orc.sort(f1, "1"))
+
+
+@pytest.mark.parametrize("shape", ["full_range", "shifted3", "high_byte_only", "two_middle_bytes"])
+def test_digit_plans_with_and_without_the_extraction_histogram(dbt, orc, shape):
+    """Byte-aligned digit plans reuse the histogram made while the keys were extracted; plans whose
+    digits straddle byte boundaries count the keys again.  Both must order rows like the oracle."""
+    f1 = orc.gen_ref(5, 300, two=False)
+    rows = f1["entries"].reshape(-1)
+    rng = np.random.default_rng(7)
+    raw = rng.integers(0, 1 << 32, size=len(rows), dtype=np.uint64)
+    if shape == "full_range":
+        num = raw
+    elif shape == "shifted3":                       # varying bits 3..14: digits start at bit 3 and 11
+        num = (raw & 0xFFF) << 3 | 0x5
+    elif shape == "high_byte_only":                 # one aligned pass, on byte 3
+        num = (raw & 0xFF) << 24 | 0x00ABCDEF
+    else:                                           # bytes 1 and 2 vary, byte 0 and 3 constant
+        num = (raw & 0xFFFF) << 8 | 0x7F000011
+    rows["num"] = num.astype(np.uint32)
+    f1["entries"][:] = rows.reshape(f1["entries"].shape)
+    f1["nreserved"][-1] = 37                        # ragged tail block
+    f1["entries"]["valid"][-1, 37:] = 0
+    for field in ("0", "1"):
+        got, n = H.dev_sort(dbt, orc, f1, field)
+        want = orc.sort(f1, field)
+        assert n == orc.count_rows(f1) and H.same_image(got, want), (shape, field, H.first_diff(got, want))
+        got, n, u = H.dev_dedup(dbt, orc, f1, field)
+        assert H.same_image(got, orc.dedup(f1, field)), (shape, field)
