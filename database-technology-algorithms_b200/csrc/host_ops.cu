@@ -45,6 +45,14 @@ struct Buf {
         cap = want;
         return 0;
     }
+    void release() {
+        if (p) {
+            if (pinned) cudaFreeHost(p);
+            else cudaFree(p);
+        }
+        p = nullptr;
+        cap = 0;
+    }
 };
 struct HostCtx {
     Buf in_r, in_s, out0, out1, out2, ws;
@@ -116,8 +124,7 @@ static int download(HostCtx &c, const void *d, void *h, size_t bytes) {
     StageScope sc(ST_D2H, c.st);
     if (!bytes) return 0;
     if (is_device_accessible_host(h)) {
-        DBT_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c.st));
-        DBT_CUDA(cudaStreamSynchronize(c.st));
+        DBT_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c.st)); // completes at the job's wait
         return 0;
     }
     const size_t chunk = kChunkBlocks * DBT_BLOCK_BYTES;
@@ -164,10 +171,38 @@ template <class F> static int with_workspace(HostCtx &c, int op, uint64_t nbr, u
     return rc;
 }
 
-extern "C" int dbt_host_mergesort(const void *h_in, uint64_t nblocks, int field, void *h_out, int device,
-                                  uint64_t *nrows) {
-    HostCtx &c = g_ctx;
-    DBT_TRY(c.init(device));
+// ---- job slots ----------------------------------------------------------------------------------
+// Every host-scope operator is "begin" (upload, kernels, download enqueued on the slot's own stream, into the
+// slot's own device buffers) followed by "wait" (the result is in host memory).  The synchronous calls are
+// begin + wait on slot 0.  With pinned host buffers two slots in flight overlap job i's download with job i+1's
+// upload: PCIe is full duplex, and a single job cannot use both directions at once because the first output
+// record is only known after the last input record has arrived.
+namespace dbt {
+struct Job {
+    bool active = false;
+    uint64_t r[4] = {0, 0, 0, 0};
+};
+static Job g_jobs[DBT_HOST_SLOTS];
+static HostCtx g_extra_slots[DBT_HOST_SLOTS - 1]; // slots 1.. (slot 0 is g_ctx, shared with the file entry points)
+static HostCtx &slot_ctx(int slot) { return slot == 0 ? g_ctx : g_extra_slots[slot - 1]; }
+
+static int slot_begin(int slot, int device, HostCtx **c) {
+    if (slot < 0 || slot >= DBT_HOST_SLOTS) {
+        set_error("bad job slot");
+        return DBT_ERR_ARG;
+    }
+    if (g_jobs[slot].active) {
+        set_error("job slot is busy: call dbt_host_job_wait on it first");
+        return DBT_ERR_ARG;
+    }
+    *c = &slot_ctx(slot);
+    return (*c)->init(device);
+}
+
+static int sort_begin(int slot, const void *h_in, uint64_t nblocks, int field, void *h_out, int device) {
+    HostCtx *cp;
+    DBT_TRY(slot_begin(slot, device, &cp));
+    HostCtx &c = *cp;
     size_t bytes = (size_t)nblocks * DBT_BLOCK_BYTES;
     DBT_TRY(c.in_r.ensure(bytes));
     DBT_TRY(c.out0.ensure(bytes));
@@ -177,16 +212,14 @@ extern "C" int dbt_host_mergesort(const void *h_in, uint64_t nblocks, int field,
         return dbt_dev_mergesort(c.in_r.p, nblocks, field, c.out0.p, ws, wb, c.st, &n);
     }));
     DBT_TRY(download(c, c.out0.p, h_out, blocks_for(n) * DBT_BLOCK_BYTES));
-    DBT_CUDA(cudaStreamSynchronize(c.st));
-    stage_resolve();
-    if (nrows) *nrows = n;
+    g_jobs[slot] = Job{true, {n, 0, 0, 0}};
     return 0;
 }
 
-extern "C" int dbt_host_dedup(const void *h_in, uint64_t nblocks, int field, void *h_out, int device, uint64_t *nrows,
-                              uint64_t *nunique) {
-    HostCtx &c = g_ctx;
-    DBT_TRY(c.init(device));
+static int dedup_begin(int slot, const void *h_in, uint64_t nblocks, int field, void *h_out, int device) {
+    HostCtx *cp;
+    DBT_TRY(slot_begin(slot, device, &cp));
+    HostCtx &c = *cp;
     size_t bytes = (size_t)nblocks * DBT_BLOCK_BYTES;
     DBT_TRY(c.in_r.ensure(bytes));
     DBT_TRY(c.out0.ensure(bytes));
@@ -196,17 +229,15 @@ extern "C" int dbt_host_dedup(const void *h_in, uint64_t nblocks, int field, voi
         return dbt_dev_dedup(c.in_r.p, nblocks, field, c.out0.p, ws, wb, c.st, &n, &u);
     }));
     DBT_TRY(download(c, c.out0.p, h_out, blocks_for(u) * DBT_BLOCK_BYTES));
-    DBT_CUDA(cudaStreamSynchronize(c.st));
-    stage_resolve();
-    if (nrows) *nrows = n;
-    if (nunique) *nunique = u;
+    g_jobs[slot] = Job{true, {n, u, 0, 0}};
     return 0;
 }
 
-extern "C" int dbt_host_mergejoin(const void *h_in_r, uint64_t nbr, const void *h_in_s, uint64_t nbs, int field,
-                                  void *h_out_ur, void *h_out_us, void *h_out, int device, uint64_t *res) {
-    HostCtx &c = g_ctx;
-    DBT_TRY(c.init(device));
+static int mergejoin_begin(int slot, const void *h_in_r, uint64_t nbr, const void *h_in_s, uint64_t nbs, int field,
+                           void *h_out_ur, void *h_out_us, void *h_out, int device) {
+    HostCtx *cp;
+    DBT_TRY(slot_begin(slot, device, &cp));
+    HostCtx &c = *cp;
     size_t br = (size_t)nbr * DBT_BLOCK_BYTES, bs = (size_t)nbs * DBT_BLOCK_BYTES;
     DBT_TRY(c.in_r.ensure(br));
     DBT_TRY(c.in_s.ensure(bs));
@@ -222,16 +253,15 @@ extern "C" int dbt_host_mergejoin(const void *h_in_r, uint64_t nbr, const void *
     if (h_out_ur) DBT_TRY(download(c, c.out0.p, h_out_ur, blocks_for(r[1]) * DBT_BLOCK_BYTES));
     if (h_out_us) DBT_TRY(download(c, c.out1.p, h_out_us, blocks_for(r[2]) * DBT_BLOCK_BYTES));
     if (h_out) DBT_TRY(download(c, c.out2.p, h_out, blocks_for(r[0]) * DBT_BLOCK_BYTES));
-    DBT_CUDA(cudaStreamSynchronize(c.st));
-    stage_resolve();
-    if (res) memcpy(res, r, sizeof r);
+    g_jobs[slot] = Job{true, {r[0], r[1], r[2], r[3]}};
     return 0;
 }
 
-extern "C" int dbt_host_hashjoin(const void *h_in_r, uint64_t nbr, const void *h_in_s, uint64_t nbs, int field,
-                                 void *h_out, uint64_t out_capacity_blocks, int device, uint64_t *nres) {
-    HostCtx &c = g_ctx;
-    DBT_TRY(c.init(device));
+static int hashjoin_begin(int slot, const void *h_in_r, uint64_t nbr, const void *h_in_s, uint64_t nbs, int field,
+                          void *h_out, uint64_t out_capacity_blocks, int device, uint64_t *nres_on_error) {
+    HostCtx *cp;
+    DBT_TRY(slot_begin(slot, device, &cp));
+    HostCtx &c = *cp;
     size_t br = (size_t)nbr * DBT_BLOCK_BYTES, bs = (size_t)nbs * DBT_BLOCK_BYTES;
     DBT_TRY(c.in_r.ensure(br));
     DBT_TRY(c.in_s.ensure(bs));
@@ -242,11 +272,99 @@ extern "C" int dbt_host_hashjoin(const void *h_in_r, uint64_t nbr, const void *h
     int rc = with_workspace(c, DBT_OP_HASHJOIN, nbr, nbs, field, [&](void *ws, size_t wb) {
         return dbt_dev_hashjoin(c.in_r.p, nbr, c.in_s.p, nbs, field, c.out0.p, out_capacity_blocks, ws, wb, c.st, &n);
     });
-    if (nres) *nres = n;
+    if (nres_on_error) *nres_on_error = n; // on DBT_ERR_CAPACITY this is the size the caller must provide
     DBT_TRY(rc);
     DBT_TRY(download(c, c.out0.p, h_out, blocks_for(n) * DBT_BLOCK_BYTES));
-    DBT_CUDA(cudaStreamSynchronize(c.st));
+    g_jobs[slot] = Job{true, {n, 0, 0, 0}};
+    return 0;
+}
+
+static int job_wait(int slot, uint64_t *result4) {
+    if (slot < 0 || slot >= DBT_HOST_SLOTS) {
+        set_error("bad job slot");
+        return DBT_ERR_ARG;
+    }
+    Job &j = g_jobs[slot];
+    if (!j.active) {
+        set_error("no job in flight on this slot");
+        return DBT_ERR_ARG;
+    }
+    j.active = false;
+    DBT_CUDA(cudaStreamSynchronize(slot_ctx(slot).st));
     stage_resolve();
+    if (result4) memcpy(result4, j.r, sizeof j.r);
+    return 0;
+}
+} // namespace dbt
+
+extern "C" int dbt_host_mergesort_begin(int slot, const void *h_in, uint64_t nblocks, int field, void *h_out, int device) {
+    return sort_begin(slot, h_in, nblocks, field, h_out, device);
+}
+extern "C" int dbt_host_dedup_begin(int slot, const void *h_in, uint64_t nblocks, int field, void *h_out, int device) {
+    return dedup_begin(slot, h_in, nblocks, field, h_out, device);
+}
+extern "C" int dbt_host_mergejoin_begin(int slot, const void *h_in_r, uint64_t nbr, const void *h_in_s, uint64_t nbs,
+                                        int field, void *h_out_ur, void *h_out_us, void *h_out, int device) {
+    return mergejoin_begin(slot, h_in_r, nbr, h_in_s, nbs, field, h_out_ur, h_out_us, h_out, device);
+}
+extern "C" int dbt_host_hashjoin_begin(int slot, const void *h_in_r, uint64_t nbr, const void *h_in_s, uint64_t nbs,
+                                       int field, void *h_out, uint64_t out_capacity_blocks, int device) {
+    return hashjoin_begin(slot, h_in_r, nbr, h_in_s, nbs, field, h_out, out_capacity_blocks, device, nullptr);
+}
+extern "C" int dbt_host_job_wait(int slot, uint64_t *result4) { return job_wait(slot, result4); }
+extern "C" int dbt_host_job_slots(void) { return DBT_HOST_SLOTS; }
+
+// Release every cached device / pinned staging buffer of the host-scope operators (all slots idle).
+extern "C" int dbt_host_trim(void) {
+    for (int s = 0; s < DBT_HOST_SLOTS; ++s) {
+        if (g_jobs[s].active) {
+            set_error("dbt_host_trim: a job is still in flight");
+            return DBT_ERR_ARG;
+        }
+        HostCtx &c = slot_ctx(s);
+        if (c.device < 0) continue;
+        DBT_CUDA(cudaSetDevice(c.device));
+        DBT_CUDA(cudaStreamSynchronize(c.st));
+        Buf *bufs[] = {&c.in_r, &c.in_s, &c.out0, &c.out1, &c.out2, &c.ws, &c.stage[0], &c.stage[1]};
+        for (Buf *b : bufs) b->release();
+    }
+    return 0;
+}
+
+extern "C" int dbt_host_mergesort(const void *h_in, uint64_t nblocks, int field, void *h_out, int device,
+                                  uint64_t *nrows) {
+    DBT_TRY(sort_begin(0, h_in, nblocks, field, h_out, device));
+    uint64_t r[4];
+    DBT_TRY(job_wait(0, r));
+    if (nrows) *nrows = r[0];
+    return 0;
+}
+
+extern "C" int dbt_host_dedup(const void *h_in, uint64_t nblocks, int field, void *h_out, int device, uint64_t *nrows,
+                              uint64_t *nunique) {
+    DBT_TRY(dedup_begin(0, h_in, nblocks, field, h_out, device));
+    uint64_t r[4];
+    DBT_TRY(job_wait(0, r));
+    if (nrows) *nrows = r[0];
+    if (nunique) *nunique = r[1];
+    return 0;
+}
+
+extern "C" int dbt_host_mergejoin(const void *h_in_r, uint64_t nbr, const void *h_in_s, uint64_t nbs, int field,
+                                  void *h_out_ur, void *h_out_us, void *h_out, int device, uint64_t *res) {
+    DBT_TRY(mergejoin_begin(0, h_in_r, nbr, h_in_s, nbs, field, h_out_ur, h_out_us, h_out, device));
+    uint64_t r[4];
+    DBT_TRY(job_wait(0, r));
+    if (res) memcpy(res, r, sizeof r);
+    return 0;
+}
+
+extern "C" int dbt_host_hashjoin(const void *h_in_r, uint64_t nbr, const void *h_in_s, uint64_t nbs, int field,
+                                 void *h_out, uint64_t out_capacity_blocks, int device, uint64_t *nres) {
+    DBT_TRY(hashjoin_begin(0, h_in_r, nbr, h_in_s, nbs, field, h_out, out_capacity_blocks, device, nres));
+    uint64_t r[4];
+    DBT_TRY(job_wait(0, r));
+    if (nres) *nres = r[0];
     return 0;
 }
 

@@ -206,6 +206,31 @@ int dbt_host_mergejoin(const void *h_in_r, uint64_t nblocks_r, const void *h_in_
 int dbt_host_hashjoin(const void *h_in_r, uint64_t nblocks_r, const void *h_in_s, uint64_t nblocks_s, int field,
                       void *h_out, uint64_t out_capacity_blocks, int device, uint64_t *nres);
 
+/* Pipelined host-scope jobs.  A query engine runs operators back to back; one job cannot use both
+ * directions of the PCIe link at once (its first output record is known only after its last input
+ * record has arrived -- the reference's MergeSort has the same barrier between run formation and
+ * merging, DatabaseProject.cpp:192-236 vs 245-369), but two jobs can: job i's download overlaps
+ * job i+1's upload.  Each of the DBT_HOST_SLOTS slots owns a stream, device buffers and a workspace.
+ *   dbt_host_*_begin(slot, ...)  same arguments as the synchronous call minus the result pointers;
+ *                                returns once upload, kernels and download are enqueued (the device
+ *                                operators read small counters back, so the kernels have run).
+ *   dbt_host_job_wait(slot, r)   blocks until the slot's result is in h_out; r[4] receives
+ *                                sort {nrows}, dedup {nrows, nunique}, mergejoin {nres, nunique_r,
+ *                                nunique_s, later_reads}, hashjoin {nres}.
+ * The host buffers should be pinned (dbt_host_alloc); pageable memory works but is copied through
+ * staging synchronously, so nothing overlaps.  The synchronous calls above are begin + wait on
+ * slot 0.  One host thread drives the slots.  dbt_host_trim() frees every cached buffer. */
+#define DBT_HOST_SLOTS 4
+int dbt_host_mergesort_begin(int slot, const void *h_in, uint64_t nblocks, int field, void *h_out, int device);
+int dbt_host_dedup_begin(int slot, const void *h_in, uint64_t nblocks, int field, void *h_out, int device);
+int dbt_host_mergejoin_begin(int slot, const void *h_in_r, uint64_t nblocks_r, const void *h_in_s, uint64_t nblocks_s,
+                             int field, void *h_out_ur, void *h_out_us, void *h_out, int device);
+int dbt_host_hashjoin_begin(int slot, const void *h_in_r, uint64_t nblocks_r, const void *h_in_s, uint64_t nblocks_s,
+                            int field, void *h_out, uint64_t out_capacity_blocks, int device);
+int dbt_host_job_wait(int slot, uint64_t result[4]);
+int dbt_host_job_slots(void);
+int dbt_host_trim(void);
+
 /* pinned host memory helpers for callers that want zero-staging copies */
 int dbt_host_alloc(void **p, size_t bytes);
 int dbt_host_free(void *p);

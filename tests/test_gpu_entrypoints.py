@@ -188,6 +188,70 @@ def test_host_scope_operators_with_pageable_and_pinned_buffers(dbt, orc):
     L.dbt_host_free(hout)
 
 
+def test_pipelined_host_jobs_on_several_slots(dbt, orc):
+    """begin/wait: jobs on different slots are in flight together (own stream, buffers, workspace) and
+    every one lands the oracle's image in its own pinned output."""
+    L = dbt.lib()
+    assert L.dbt_host_job_slots() >= 2
+    inputs = [orc.gen_ref(21 + i, 120 + 40 * i, two=False, num_mod=3000) for i in range(3)]
+    pins = []
+    for f in inputs:
+        nbytes = len(f) * H.BLOCK_BYTES
+        hin, hout = C.c_void_p(), C.c_void_p()
+        dbt.check(L.dbt_host_alloc(C.byref(hin), nbytes))
+        dbt.check(L.dbt_host_alloc(C.byref(hout), nbytes))
+        C.memmove(hin, f.ctypes.data, nbytes)
+        pins.append((hin, hout, nbytes))
+
+    def image(hout, nblocks):
+        return orc.as_blocks(np.ctypeslib.as_array((C.c_uint8 * (nblocks * H.BLOCK_BYTES)).from_address(hout.value)).copy())
+
+    for rnd in range(2):  # second round reuses the slots' cached buffers
+        dbt.check(L.dbt_host_dedup_begin(0, pins[0][0], len(inputs[0]), ord("1"), pins[0][1], 0))
+        dbt.check(L.dbt_host_mergesort_begin(1, pins[1][0], len(inputs[1]), ord("2"), pins[1][1], 0))
+        dbt.check(L.dbt_host_dedup_begin(2, pins[2][0], len(inputs[2]), ord("3"), pins[2][1], 0))
+        with pytest.raises(dbt.DbtError) as e:   # a busy slot refuses a second job
+            dbt.check(L.dbt_host_dedup_begin(1, pins[0][0], len(inputs[0]), ord("1"), pins[0][1], 0))
+        assert "busy" in str(e.value)
+        r = (C.c_uint64 * 4)()
+        dbt.check(L.dbt_host_job_wait(2, r))
+        want = orc.dedup(inputs[2], "3")
+        assert (r[0], r[1]) == (orc.count_rows(inputs[2]), orc.count_rows(want))
+        assert H.same_image(image(pins[2][1], len(want)), want)
+        dbt.check(L.dbt_host_job_wait(0, r))
+        want = orc.dedup(inputs[0], "1")
+        assert r[1] == orc.count_rows(want) and H.same_image(image(pins[0][1], len(want)), want)
+        dbt.check(L.dbt_host_job_wait(1, r))
+        assert r[0] == orc.count_rows(inputs[1]) and H.same_image(image(pins[1][1], len(inputs[1])), orc.sort(inputs[1], "2"))
+    with pytest.raises(dbt.DbtError):            # nothing in flight any more
+        dbt.check(L.dbt_host_job_wait(1, None))
+    with pytest.raises(dbt.DbtError):
+        dbt.check(L.dbt_host_dedup_begin(99, pins[0][0], 1, ord("1"), pins[0][1], 0))
+    # join jobs, then trim and run again from cold buffers
+    f1, f2 = orc.gen_ref(9, 100)
+    out = orc.new_blocks(len(f2))
+    dbt.check(L.dbt_host_hashjoin_begin(3, f1.ctypes.data, len(f1), f2.ctypes.data, len(f2), ord("1"), out.ctypes.data, len(f2), 0))
+    o3 = orc.new_blocks(len(f1))
+    dbt.check(L.dbt_host_mergejoin_begin(1, f1.ctypes.data, len(f1), f2.ctypes.data, len(f2), ord("1"), None, None, o3.ctypes.data, 0))
+    with pytest.raises(dbt.DbtError):
+        dbt.check(L.dbt_host_trim())             # refused while jobs are in flight
+    r = (C.c_uint64 * 4)()
+    dbt.check(L.dbt_host_job_wait(3, r))
+    want = orc.hashjoin(f1, f2, "1")
+    assert r[0] == orc.count_rows(want) and H.same_image(out[: len(want)], want)
+    dbt.check(L.dbt_host_job_wait(1, r))
+    want, _, _, info = orc.mergejoin(f1, f2, "1")
+    assert r[0] == info["nres"] and H.same_image(o3[: len(want)], want)
+    dbt.check(L.dbt_host_trim())
+    n, u = C.c_uint64(), C.c_uint64()
+    dbt.check(L.dbt_host_dedup(pins[0][0], len(inputs[0]), ord("1"), pins[0][1], 0, C.byref(n), C.byref(u)))
+    want = orc.dedup(inputs[0], "1")
+    assert u.value == orc.count_rows(want) and H.same_image(image(pins[0][1], len(want)), want)
+    for hin, hout, _ in pins:
+        L.dbt_host_free(hin)
+        L.dbt_host_free(hout)
+
+
 def test_large_dedup_properties_and_cpu_spot_checks(dbt, orc):
     """20M rows of the bench distribution (generated on the device): size-independent properties checked
     with torch as an independent checker, plus oracle spot checks of the generator on sub-ranges."""
