@@ -648,6 +648,58 @@ def extra_measurements(dbt, torch, dev, peak):
             torch.cuda.empty_cache()
         except Exception as e:  # noqa: BLE001
             out[f"hashjoin_R100M_S400M_{label}"] = {"error": str(e)[:200]}
+    # BASELINE configs[3] at ONE GPU: HashJoin field=num, R = 100M x S = 1B records.  S (140 GB) cannot be resident beside
+    # R and the output, so it streams through HBM in 10 chunks of 100M records (generated in place between the timed
+    # probes, the way a chunk would arrive from storage); R's key column is extracted once and stays resident.
+    for kind, label in ((1, "uniform"), (2, "skewed")):
+        try:
+            nr, ns, D, nchunk = 100_000_000, 1_000_000_000, 100_000_000, 10
+            rows_c = ns // nchunk
+            nbr, nbc = nr // RPB, rows_c // RPB
+            d_r = torch.empty(nbr * BLOCK_BYTES, dtype=torch.uint8, device=dev)
+            dbt.check(L.dbt_gen_syn(7, nr, D, 1, 0, nr, 0, d_r.data_ptr(), sp))
+            wsb = dbt.dev_ws_bytes(dbt.OP_HASHJOIN, nbr, nbc, FIELD)
+            ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            rkeys = torch.empty(nr, dtype=torch.int32, device=dev)
+            nrows = C.c_uint64()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            dbt.check(L.dbt_dev_extract_keys_u32(d_r.data_ptr(), nbr, ord(FIELD), rkeys.data_ptr(), ws.data_ptr(), wsb, sp,
+                                                 C.byref(nrows)))
+            e1.record()
+            torch.cuda.synchronize()
+            ms_r = e0.elapsed_time(e1)
+            del d_r
+            torch.cuda.empty_cache()
+            d_s = torch.empty(nbc * BLOCK_BYTES, dtype=torch.uint8, device=dev)
+            d_o = torch.empty(nbc * BLOCK_BYTES, dtype=torch.uint8, device=dev)
+            total, ms_s = 0, 0.0
+            k = C.c_uint64()
+            for c in range(nchunk + 1):  # chunk 0 runs twice: the first run is the warm-up
+                cc = max(c - 1, 0)
+                dbt.check(L.dbt_gen_syn(9, ns, D, kind, cc * rows_c, rows_c, 0, d_s.data_ptr(), sp))
+                torch.cuda.synchronize()
+                e0.record()
+                dbt.check(L.dbt_dev_semijoin_keys(rkeys.data_ptr(), nr, d_s.data_ptr(), nbc, ord(FIELD), d_o.data_ptr(), nbc,
+                                                  ws.data_ptr(), wsb, sp, C.byref(k)))
+                e1.record()
+                torch.cuda.synchronize()
+                if c:
+                    ms_s += e0.elapsed_time(e1)
+                    total += k.value
+            ms = ms_r + ms_s
+            out[f"hashjoin_R100M_S1B_streamed_{label}"] = {
+                "probe_tuples_per_s": ns / (ms * 1e-3), "ms": ms, "ms_extract_R_keys": ms_r, "ms_probe_chunks": ms_s,
+                "chunks": nchunk, "nres": total, "selectivity": total / ns,
+                "note": "BASELINE configs[3] at 1 GPU, device scope: S streams through HBM in 10 chunks of 100M records "
+                        "(dbt_dev_semijoin_keys per chunk: extraction, bitmap build + probe, compaction, gather of the "
+                        "matching S records), R's keys resident; same generator and seeds as the 8-GPU run of "
+                        "profiles/dist_configs.py, so nres must equal that run's"}
+            del d_s, d_o, ws, rkeys
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            out[f"hashjoin_R100M_S1B_streamed_{label}"] = {"error": str(e)[:200]}
     return out
 
 
