@@ -103,6 +103,8 @@ struct KeyCols {
     uint32_t vary_w0, vary_recid, vary_str[30];
     int recid_unsorted;
     const uint32_t *w0_byte_hist; // [4][256] histogram of w0's bytes made during extraction (or nullptr)
+    // the raw OR / AND words behind the vary_* masks (out-of-core: combined over all runs before the global sort)
+    uint32_t or_w0, and_w0, or_recid, and_recid, or_str[30], and_str[30];
 };
 
 // ---- launchers implemented in the .cu files --------------------------------------------------
@@ -143,8 +145,23 @@ int compact_select(const uint32_t *d_counts, const uint32_t *d_values, uint64_t 
                    uint64_t *d_total, Arena &ws, cudaStream_t st);
 int exclusive_offsets(const uint32_t *d_counts, uint64_t n, uint32_t *d_off, uint64_t *d_total, Arena &ws,
                       cudaStream_t st);
+// blockid0: blockid of the first output block (a chunk of a larger image continues the numbering)
 int gather_records(const void *d_in, const uint32_t *d_rows, const uint32_t *d_row_slot, uint64_t nrows_out,
-                   void *d_out, cudaStream_t st, int max_ctas = 0);
+                   void *d_out, cudaStream_t st, int max_ctas = 0, uint32_t blockid0 = 0);
+
+// device-scope pipeline steps shared with the out-of-core host operators (device_ops.cu)
+struct Prepared {
+    ImageInfo info;
+    uint32_t *row_slot; // nullptr when slot == row
+    KeyCols keys;
+};
+// headers + key extraction of one image into columns taken from `ws`; force_kw: words per str key (0 = 8, widened
+// to 30 automatically when a string has no NUL in its first 32 bytes)
+int prepare(const void *d_img, uint64_t nblocks, int field, Arena &ws, cudaStream_t st, Prepared *out,
+            uint32_t force_kw = 0);
+// rows ordered by (key(field), recid), remaining ties in file order: the row permutation and, for one-word keys,
+// the sorted key column
+int sort_rows_by_key(KeyCols &k, int field, Arena &ws, cudaStream_t st, uint32_t **perm_out, uint32_t **sorted_w0_out);
 
 // joins (kernels_join.cu)
 size_t hash_table_slots(uint64_t nr);

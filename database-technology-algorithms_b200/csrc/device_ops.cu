@@ -14,16 +14,9 @@ namespace dbt {
 
 static inline bool is_aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
 
-struct Prepared {
-    ImageInfo info;
-    uint32_t *row_slot; // nullptr when slot == row
-    KeyCols keys;
-};
-
 static bool field_ok(int f) { return f >= '0' && f <= '3'; }
 
-static int prepare(const void *d_img, uint64_t nblocks, int field, Arena &ws, cudaStream_t st, Prepared *out,
-                   uint32_t force_kw = 0) {
+int prepare(const void *d_img, uint64_t nblocks, int field, Arena &ws, cudaStream_t st, Prepared *out, uint32_t force_kw) {
     memset(out, 0, sizeof *out);
     device_setup();
     DBT_TRY(image_info(d_img, nblocks, &out->row_slot, ws, st, &out->info));
@@ -66,13 +59,20 @@ static int prepare(const void *d_img, uint64_t nblocks, int field, Arena &ws, cu
     k.vary_recid = h.or_recid ^ h.and_recid;
     for (uint32_t j = 0; j < 30; ++j) k.vary_str[j] = (has_str && j < k.kw) ? (h.str_or[j] ^ h.str_and[j]) : 0;
     k.recid_unsorted = (int)h.recid_unsorted;
+    k.or_w0 = h.or_w0;
+    k.and_w0 = h.and_w0;
+    k.or_recid = h.or_recid;
+    k.and_recid = h.and_recid;
+    for (uint32_t j = 0; j < 30; ++j) {
+        k.or_str[j] = h.str_or[j];
+        k.and_str[j] = h.str_and[j];
+    }
     return 0;
 }
 
 // Order the rows by (key(field), recid); ties beyond that keep file order (LSD passes are stable).
 // Returns the row permutation and, for 1-word keys, the sorted key column.
-static int sort_rows_by_key(KeyCols &k, int field, Arena &ws, cudaStream_t st, uint32_t **perm_out,
-                            uint32_t **sorted_w0_out) {
+int sort_rows_by_key(KeyCols &k, int field, Arena &ws, cudaStream_t st, uint32_t **perm_out, uint32_t **sorted_w0_out) {
     const uint64_t n = k.n;
     *perm_out = nullptr;
     *sorted_w0_out = nullptr;

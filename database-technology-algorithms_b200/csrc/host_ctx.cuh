@@ -1,0 +1,95 @@
+// host_ctx.cuh -- state shared by the host-scope operators (host_ops.cu) and their out-of-core forms (host_ooc.cu).
+#pragma once
+#include "dbt_internal.cuh"
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+namespace dbt {
+
+// ---- cached device / pinned buffers (grown on demand, reused across calls) ------------------
+struct Buf {
+    void *p = nullptr;
+    size_t cap = 0;
+    bool pinned = false;
+    bool malloced = false; // plain host memory (the out-of-core runs when pinned memory is short)
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        release();
+        size_t want = bytes + bytes / 8 + (1 << 20);
+        if (pinned) DBT_CUDA(cudaHostAlloc(&p, want, cudaHostAllocDefault));
+        else DBT_CUDA(cudaMalloc(&p, want));
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) {
+            if (malloced) free(p);
+            else if (pinned) cudaFreeHost(p);
+            else cudaFree(p);
+        }
+        p = nullptr;
+        cap = 0;
+        malloced = false;
+    }
+};
+struct HostCtx {
+    Buf in_r, in_s, out0, out1, out2, ws;
+    Buf cols, runs; // out-of-core: resident key columns (device), sorted runs (pinned host)
+    Buf stage[2];
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int device = -1;
+    int init(int dev) {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0) {
+            cudaGetLastError();
+            set_error("no CUDA device visible: libdbt_b200 has no CPU fallback");
+            return DBT_ERR_CUDA;
+        }
+        if (dev < 0 || dev >= n) {
+            set_error("bad device index");
+            return DBT_ERR_ARG;
+        }
+        DBT_CUDA(cudaSetDevice(dev));
+        if (device != dev) {
+            if (device >= 0) { // moving to another GPU: drop the old device's buffers
+                set_error("host-scope operators are bound to the first device they were used on");
+                return DBT_ERR_UNSUPPORTED;
+            }
+            device = dev;
+            DBT_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            DBT_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+            DBT_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+            stage[0].pinned = stage[1].pinned = true;
+        }
+        return 0;
+    }
+};
+
+int upload(HostCtx &c, const void *h, void *d, size_t bytes);
+int download(HostCtx &c, const void *d, void *h, size_t bytes);
+inline size_t blocks_for(uint64_t rows) { return (size_t)((rows + kRpb - 1) / kRpb); }
+
+// out-of-core forms (host_ooc.cu).  chunk_blocks: the largest image that is processed in one piece.
+uint64_t ooc_chunk_blocks(int op, uint64_t nbr, uint64_t nbs, int field); // 0 = the job fits, run it in-core
+int ooc_sort(HostCtx &c, const void *h_in, uint64_t nblocks, int field, void *h_out, bool dedup, uint64_t chunk_blocks,
+             uint64_t *nrows, uint64_t *nunique);
+int ooc_hashjoin(HostCtx &c, const void *h_in_r, uint64_t nbr, const void *h_in_s, uint64_t nbs, int field, void *h_out,
+                 uint64_t out_capacity_blocks, uint64_t chunk_blocks, uint64_t *nres);
+
+} // namespace dbt
+
+extern "C" size_t dbt_dev_ws_bytes_kw(int op, uint64_t nbr, uint64_t nbs, int field, uint32_t kw);
+
+// run `call(ws_ptr, ws_bytes)`; when it reports 120-byte string keys are needed, retry once with a larger workspace
+template <class F> static int with_workspace(dbt::HostCtx &c, int op, uint64_t nbr, uint64_t nbs, int field, F call) {
+    DBT_TRY(c.ws.ensure(dbt_dev_ws_bytes_kw(op, nbr, nbs, field, 8)));
+    int rc = call(c.ws.p, c.ws.cap);
+    if (rc == DBT_ERR_WORKSPACE && field >= '2' && strstr(dbt_last_error(), "120-byte")) {
+        DBT_TRY(c.ws.ensure(dbt_dev_ws_bytes_kw(op, nbr, nbs, field, 30)));
+        rc = call(c.ws.p, c.ws.cap);
+    }
+    return rc;
+}

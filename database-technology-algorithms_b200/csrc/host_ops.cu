@@ -13,7 +13,7 @@
 //   * nsorted_segs / npasses / nios come from the Appendix-B formulae (dbt_sort_counters &c).
 // Deliberate differences: output block headers are sane (CANON), a missing input file or
 // a missing CUDA device is a loud error (stderr + exit(1)) instead of a segfault.
-#include "dbt_internal.cuh"
+#include "host_ctx.cuh"
 #include "../../include/dbtproj.h"
 #include <algorithm>
 #include <cstdio>
@@ -26,67 +26,6 @@
 
 namespace dbt {
 
-// ---- cached device / pinned buffers (grown on demand, reused across calls) ------------------
-struct Buf {
-    void *p = nullptr;
-    size_t cap = 0;
-    bool pinned = false;
-    int ensure(size_t bytes) {
-        if (bytes <= cap) return 0;
-        if (p) {
-            if (pinned) cudaFreeHost(p);
-            else cudaFree(p);
-            p = nullptr;
-            cap = 0;
-        }
-        size_t want = bytes + bytes / 8 + (1 << 20);
-        if (pinned) DBT_CUDA(cudaHostAlloc(&p, want, cudaHostAllocDefault));
-        else DBT_CUDA(cudaMalloc(&p, want));
-        cap = want;
-        return 0;
-    }
-    void release() {
-        if (p) {
-            if (pinned) cudaFreeHost(p);
-            else cudaFree(p);
-        }
-        p = nullptr;
-        cap = 0;
-    }
-};
-struct HostCtx {
-    Buf in_r, in_s, out0, out1, out2, ws;
-    Buf stage[2];
-    cudaStream_t st = nullptr;
-    cudaEvent_t ev[2] = {nullptr, nullptr};
-    int device = -1;
-    int init(int dev) {
-        int n = 0;
-        cudaError_t e = cudaGetDeviceCount(&n);
-        if (e != cudaSuccess || n == 0) {
-            cudaGetLastError();
-            set_error("no CUDA device visible: libdbt_b200 has no CPU fallback");
-            return DBT_ERR_CUDA;
-        }
-        if (dev < 0 || dev >= n) {
-            set_error("bad device index");
-            return DBT_ERR_ARG;
-        }
-        DBT_CUDA(cudaSetDevice(dev));
-        if (device != dev) {
-            if (device >= 0) { // moving to another GPU: drop the old device's buffers
-                set_error("host-scope operators are bound to the first device they were used on");
-                return DBT_ERR_UNSUPPORTED;
-            }
-            device = dev;
-            DBT_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-            DBT_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-            DBT_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
-            stage[0].pinned = stage[1].pinned = true;
-        }
-        return 0;
-    }
-};
 static HostCtx g_ctx;
 constexpr size_t kChunkBlocks = 4096; // 57.4 MB staging chunks
 
@@ -100,7 +39,7 @@ static bool is_device_accessible_host(const void *p) {
 }
 
 // host image -> device (direct when the caller's memory is pinned, else through pinned staging)
-static int upload(HostCtx &c, const void *h, void *d, size_t bytes) {
+int upload(HostCtx &c, const void *h, void *d, size_t bytes) {
     StageScope sc(ST_H2D, c.st);
     if (!bytes) return 0;
     if (is_device_accessible_host(h)) {
@@ -120,7 +59,7 @@ static int upload(HostCtx &c, const void *h, void *d, size_t bytes) {
     }
     return 0;
 }
-static int download(HostCtx &c, const void *d, void *h, size_t bytes) {
+int download(HostCtx &c, const void *d, void *h, size_t bytes) {
     StageScope sc(ST_D2H, c.st);
     if (!bytes) return 0;
     if (is_device_accessible_host(h)) {
@@ -152,24 +91,10 @@ static int download(HostCtx &c, const void *d, void *h, size_t bytes) {
     return 0;
 }
 
-static size_t blocks_for(uint64_t rows) { return (size_t)((rows + kRpb - 1) / kRpb); }
 
 } // namespace dbt
 
 using namespace dbt;
-
-extern "C" size_t dbt_dev_ws_bytes_kw(int op, uint64_t nbr, uint64_t nbs, int field, uint32_t kw);
-
-// run `call(ws_ptr, ws_bytes)`; when it reports 120-byte string keys are needed, retry once with a larger workspace
-template <class F> static int with_workspace(HostCtx &c, int op, uint64_t nbr, uint64_t nbs, int field, F call) {
-    DBT_TRY(c.ws.ensure(dbt_dev_ws_bytes_kw(op, nbr, nbs, field, 8)));
-    int rc = call(c.ws.p, c.ws.cap);
-    if (rc == DBT_ERR_WORKSPACE && field >= '2' && strstr(dbt_last_error(), "120-byte")) {
-        DBT_TRY(c.ws.ensure(dbt_dev_ws_bytes_kw(op, nbr, nbs, field, 30)));
-        rc = call(c.ws.p, c.ws.cap);
-    }
-    return rc;
-}
 
 // ---- job slots ----------------------------------------------------------------------------------
 // Every host-scope operator is "begin" (upload, kernels, download enqueued on the slot's own stream, into the
@@ -203,6 +128,12 @@ static int sort_begin(int slot, const void *h_in, uint64_t nblocks, int field, v
     HostCtx *cp;
     DBT_TRY(slot_begin(slot, device, &cp));
     HostCtx &c = *cp;
+    if (const uint64_t chunk = ooc_chunk_blocks(DBT_OP_SORT, nblocks, 0, field)) { // larger than the device: runs + merge
+        uint64_t n = 0, u = 0;
+        DBT_TRY(ooc_sort(c, h_in, nblocks, field, h_out, false, chunk, &n, &u));
+        g_jobs[slot] = Job{true, {n, 0, 0, 0}};
+        return 0;
+    }
     size_t bytes = (size_t)nblocks * DBT_BLOCK_BYTES;
     DBT_TRY(c.in_r.ensure(bytes));
     DBT_TRY(c.out0.ensure(bytes));
@@ -220,6 +151,12 @@ static int dedup_begin(int slot, const void *h_in, uint64_t nblocks, int field, 
     HostCtx *cp;
     DBT_TRY(slot_begin(slot, device, &cp));
     HostCtx &c = *cp;
+    if (const uint64_t chunk = ooc_chunk_blocks(DBT_OP_DEDUP, nblocks, 0, field)) {
+        uint64_t n = 0, u = 0;
+        DBT_TRY(ooc_sort(c, h_in, nblocks, field, h_out, true, chunk, &n, &u));
+        g_jobs[slot] = Job{true, {n, u, 0, 0}};
+        return 0;
+    }
     size_t bytes = (size_t)nblocks * DBT_BLOCK_BYTES;
     DBT_TRY(c.in_r.ensure(bytes));
     DBT_TRY(c.out0.ensure(bytes));
@@ -238,6 +175,11 @@ static int mergejoin_begin(int slot, const void *h_in_r, uint64_t nbr, const voi
     HostCtx *cp;
     DBT_TRY(slot_begin(slot, device, &cp));
     HostCtx &c = *cp;
+    if (ooc_chunk_blocks(DBT_OP_MERGEJOIN, nbr, nbs, field)) {
+        set_error("MergeJoin of images larger than the device is not implemented: deduplicate both sides out of core "
+                  "(dbt_host_dedup) and join the results");
+        return DBT_ERR_UNSUPPORTED;
+    }
     size_t br = (size_t)nbr * DBT_BLOCK_BYTES, bs = (size_t)nbs * DBT_BLOCK_BYTES;
     DBT_TRY(c.in_r.ensure(br));
     DBT_TRY(c.in_s.ensure(bs));
@@ -262,6 +204,14 @@ static int hashjoin_begin(int slot, const void *h_in_r, uint64_t nbr, const void
     HostCtx *cp;
     DBT_TRY(slot_begin(slot, device, &cp));
     HostCtx &c = *cp;
+    if (const uint64_t chunk = ooc_chunk_blocks(DBT_OP_HASHJOIN, nbr, nbs, field)) { // R's keys resident, S streams
+        uint64_t n = 0;
+        int rc = ooc_hashjoin(c, h_in_r, nbr, h_in_s, nbs, field, h_out, out_capacity_blocks, chunk, &n);
+        if (nres_on_error) *nres_on_error = n;
+        DBT_TRY(rc);
+        g_jobs[slot] = Job{true, {n, 0, 0, 0}};
+        return 0;
+    }
     size_t br = (size_t)nbr * DBT_BLOCK_BYTES, bs = (size_t)nbs * DBT_BLOCK_BYTES;
     DBT_TRY(c.in_r.ensure(br));
     DBT_TRY(c.in_s.ensure(bs));
@@ -325,7 +275,7 @@ extern "C" int dbt_host_trim(void) {
         if (c.device < 0) continue;
         DBT_CUDA(cudaSetDevice(c.device));
         DBT_CUDA(cudaStreamSynchronize(c.st));
-        Buf *bufs[] = {&c.in_r, &c.in_s, &c.out0, &c.out1, &c.out2, &c.ws, &c.stage[0], &c.stage[1]};
+        Buf *bufs[] = {&c.in_r, &c.in_s, &c.out0, &c.out1, &c.out2, &c.ws, &c.stage[0], &c.stage[1], &c.cols, &c.runs};
         for (Buf *b : bufs) b->release();
     }
     return 0;
@@ -508,6 +458,30 @@ void store_file(const char *path, const void *d, size_t bytes, Buf &pinned) {
     close(fd);
 }
 
+// whole file <-> pinned host memory (the out-of-core operators take host images)
+uint64_t file_blocks(const char *path) {
+    struct stat sb;
+    if (stat(path, &sb) != 0) die(std::string("cannot open input file '") + path + "'");
+    return (uint64_t)sb.st_size / DBT_BLOCK_BYTES;
+}
+uint64_t read_file(const char *path, Buf &pinned) {
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) die(std::string("cannot open input file '") + path + "'");
+    const uint64_t nblocks = file_blocks(path);
+    const size_t bytes = (size_t)nblocks * DBT_BLOCK_BYTES;
+    must(pinned.ensure(bytes), "pinned staging");
+    if (bytes) parallel_io(fd, (char *)pinned.p, 0, bytes, false, path);
+    close(fd);
+    return nblocks;
+}
+void write_file(const char *path, const void *h, size_t bytes) {
+    int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) die(std::string("cannot create output file '") + path + "'");
+    if (bytes && ftruncate(fd, (off_t)bytes) != 0) die("ftruncate failed");
+    if (bytes) parallel_io(fd, (char *)const_cast<void *>(h), 0, bytes, true, path);
+    close(fd);
+}
+
 template <class F> int with_ws(int op, uint64_t nbr, uint64_t nbs, int field, F call) {
     return with_workspace(ctx(), op, nbr, nbs, field, call);
 }
@@ -519,6 +493,21 @@ struct SortOut {
 // sort (or dedup) a file into `outpath`; returns counters
 SortOut sort_file(const char *infile, unsigned char field, unsigned nmem, const char *outpath, bool dedup, uint64_t *nunique) {
     HostCtx &c = ctx();
+    const int op_id = dedup ? DBT_OP_DEDUP : DBT_OP_SORT;
+    if (const uint64_t chunk = ooc_chunk_blocks(op_id, file_blocks(infile), 0, field)) {
+        // larger than the device: the file is sorted out of core through host memory (runs + merge, host_ooc.cu)
+        const uint64_t nblocks = read_file(infile, g_files.pin[0]);
+        SortOut o{};
+        must(dbt_sort_counters(nblocks, nmem, &o.segs, &o.passes, &o.nios), "dbt_sort_counters");
+        must(g_files.pin[2].ensure((size_t)nblocks * DBT_BLOCK_BYTES), "pinned staging");
+        uint64_t n = 0, u = 0;
+        must(ooc_sort(c, g_files.pin[0].p, nblocks, field, g_files.pin[2].p, dedup, chunk, &n, &u), "out-of-core sort");
+        o.nrows = n;
+        if (nunique) *nunique = u;
+        if (outpath) write_file(outpath, g_files.pin[2].p, blocks_for(dedup ? u : n) * DBT_BLOCK_BYTES);
+        stage_resolve();
+        return o;
+    }
     const uint64_t nblocks = load_file(infile, g_files.pin[0], c.in_r);
     SortOut o{};
     if (nblocks == 0) { // the reference spins forever on an empty file; we define the obvious result
@@ -583,6 +572,9 @@ void MergeJoin(char *infile1, char *infile2, unsigned char field, block_t *, uns
     check_nmem_or_exit(nmem_blocks);
     check_field_or_exit(field);
     HostCtx &c = ctx();
+    if (ooc_chunk_blocks(DBT_OP_MERGEJOIN, file_blocks(infile1), file_blocks(infile2), field))
+        die("MergeJoin: the two files do not fit on the device together (out-of-core MergeJoin is not implemented; "
+            "EliminateDuplicates on each file works out of core)");
     const uint64_t nbr = load_file(infile1, g_files.pin[0], c.in_r);
     const uint64_t nbs = load_file(infile2, g_files.pin[1], c.in_s);
     must(c.out0.ensure((size_t)nbr * DBT_BLOCK_BYTES), "device output");
@@ -607,6 +599,26 @@ void HashJoin(char *infile1, char *infile2, unsigned char field, block_t *, unsi
               unsigned int *nres, unsigned int *nios) {
     if (nmem_blocks < 2) die("HashJoin: nmem_blocks must be >= 2");
     HostCtx &c = ctx();
+    if (field >= '0' && field <= '3')
+        if (const uint64_t chunk = ooc_chunk_blocks(DBT_OP_HASHJOIN, file_blocks(infile1), file_blocks(infile2), field)) {
+            // larger than the device: R's keys stay resident, S streams through in chunks (host_ooc.cu)
+            const uint64_t nbr = read_file(infile1, g_files.pin[0]);
+            const uint64_t nbs = read_file(infile2, g_files.pin[1]);
+            uint64_t cap = nbs, n = 0;
+            must(g_files.pin[2].ensure((size_t)cap * DBT_BLOCK_BYTES), "pinned staging");
+            int rc = ooc_hashjoin(c, g_files.pin[0].p, nbr, g_files.pin[1].p, nbs, field, g_files.pin[2].p, cap, chunk, &n);
+            if (rc == DBT_ERR_WORKSPACE && n > cap * kRpb) {
+                cap = blocks_for(n);
+                must(g_files.pin[2].ensure((size_t)cap * DBT_BLOCK_BYTES), "pinned staging");
+                rc = ooc_hashjoin(c, g_files.pin[0].p, nbr, g_files.pin[1].p, nbs, field, g_files.pin[2].p, cap, chunk, &n);
+            }
+            must(rc, "out-of-core hash join");
+            write_file(outfile, g_files.pin[2].p, blocks_for(n) * DBT_BLOCK_BYTES);
+            stage_resolve();
+            *nres = clamp32(n);
+            *nios = clamp32(dbt_hashjoin_nios(nbr, nbs, nmem_blocks, n));
+            return;
+        }
     const uint64_t nbr = load_file(infile1, g_files.pin[0], c.in_r);
     const uint64_t nbs = load_file(infile2, g_files.pin[1], c.in_s);
     uint64_t n = 0;

@@ -407,7 +407,7 @@ constexpr int kGatherThreads = 256;
 
 __global__ void __launch_bounds__(kGatherThreads)
 gather_kernel(const uint32_t *__restrict__ in, const uint32_t *__restrict__ rows, const uint32_t *__restrict__ row_slot,
-              uint64_t nrows_out, uint4 *__restrict__ out, uint64_t nblocks_out) {
+              uint64_t nrows_out, uint4 *__restrict__ out, uint64_t nblocks_out, uint32_t blockid0) {
     __shared__ __align__(16) uint32_t stage[kBlockWords];
     __shared__ uint64_t src[kRpb];
     const int tid = threadIdx.x;
@@ -420,7 +420,7 @@ gather_kernel(const uint32_t *__restrict__ in, const uint32_t *__restrict__ rows
             src[tid] = slot_word(slot);
         }
         if (tid == 0) {
-            stage[0] = (uint32_t)ob; // blockid
+            stage[0] = (uint32_t)ob + blockid0; // blockid
             stage[1] = cnt;          // nreserved
             stage[kTrailerWord] = 1; // valid=1, misc=0, padding 0
             stage[kTrailerWord + 1] = cnt; // dummy
@@ -531,13 +531,13 @@ take_kernel(const uint32_t *__restrict__ src, const uint32_t *__restrict__ idx, 
 }
 
 int gather_records(const void *d_in, const uint32_t *d_rows, const uint32_t *d_row_slot, uint64_t nrows_out, void *d_out,
-                   cudaStream_t st, int max_ctas) {
+                   cudaStream_t st, int max_ctas, uint32_t blockid0) {
     StageScope sc(ST_GATHER, st);
     if (nrows_out == 0) return 0;
     uint64_t nb = (nrows_out + kRpb - 1) / kRpb;
     int grid = (int)std::min<uint64_t>(nb, max_ctas > 0 ? (uint64_t)max_ctas : 148 * 8 * 4);
     gather_kernel<<<grid, kGatherThreads, 0, st>>>((const uint32_t *)d_in, d_rows, d_row_slot, nrows_out, (uint4 *)d_out,
-                                                   nb);
+                                                   nb, blockid0);
     count_launch();
     DBT_KERNEL_CHECK();
     return 0;

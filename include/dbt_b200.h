@@ -231,6 +231,15 @@ int dbt_host_job_wait(int slot, uint64_t result[4]);
 int dbt_host_job_slots(void);
 int dbt_host_trim(void);
 
+/* Out-of-core mode (the analogue of the reference's nmem_blocks-bounded external sort,
+ * DatabaseProject.cpp:182-369, and chunked join reads, :521,:564).  Host-scope MergeSort / EliminateDuplicates /
+ * HashJoin (and the file entry points above them) switch to it when their images do not fit on the device:
+ * sort/dedup = in-core sort of chunk-sized runs + one global sort of the resident key columns + chunked gather from
+ * the runs; hash join = R's key columns resident, S streamed in chunks.  `blocks` (> 0) forces the chunk size (the
+ * tests use this to drive the path with small images; env DBT_OOC_CHUNK_BLOCKS does the same), 0 restores the
+ * automatic choice from the device's memory size.  Limits: < 2^30 rows per sort, MergeJoin is in-core only. */
+int dbt_host_set_chunk_blocks(uint64_t blocks);
+
 /* pinned host memory helpers for callers that want zero-staging copies */
 int dbt_host_alloc(void **p, size_t bytes);
 int dbt_host_free(void *p);
