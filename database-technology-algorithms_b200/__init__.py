@@ -34,7 +34,7 @@ C_ABI_SYMBOLS = [
     "dbt_gather_records_multi", "dbt_ipc_export",
     "dbt_ipc_alloc", "dbt_ipc_open", "dbt_ipc_close", "dbt_ipc_free",
     "dbt_host_mergesort_begin", "dbt_host_dedup_begin", "dbt_host_mergejoin_begin", "dbt_host_hashjoin_begin",
-    "dbt_host_job_wait", "dbt_host_job_slots", "dbt_host_trim", "dbt_host_set_chunk_blocks",
+    "dbt_host_job_wait", "dbt_host_job_slots", "dbt_host_trim", "dbt_host_set_chunk_blocks", "dbt_host_ooc_stats",
     "dbt_host_alloc", "dbt_host_free", "dbt_gen_syn",
     "dbt_stage_timing_enable", "dbt_stage_timing_reset", "dbt_stage_count", "dbt_stage_name", "dbt_stage_ms",
     "dbt_stage_launches", "dbt_kernel_launches",
@@ -120,6 +120,7 @@ def lib() -> C.CDLL:
     L.dbt_host_job_slots.argtypes = []
     L.dbt_host_trim.argtypes = []
     L.dbt_host_set_chunk_blocks.argtypes = [u64]
+    L.dbt_host_ooc_stats.argtypes = [pu64]
     L.dbt_host_alloc.argtypes = [C.POINTER(vp), sz]
     L.dbt_host_free.argtypes = [vp]
     L.dbt_gen_syn.argtypes = [u64, u64, u64, ci, u64, u64, u32, vp, vp]

@@ -38,7 +38,9 @@ struct HostCtx {
     Buf cols, runs; // out-of-core: resident key columns (device), sorted runs (pinned host)
     Buf stage[2];
     cudaStream_t st = nullptr;
+    cudaStream_t st2 = nullptr;            // out-of-core: results go home on this stream while the next chunk comes in
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaEvent_t packed[2] = {nullptr, nullptr}, landed[2] = {nullptr, nullptr}; // out-of-core double buffering
     int device = -1;
     int init(int dev) {
         int n = 0;
@@ -60,6 +62,11 @@ struct HostCtx {
             }
             device = dev;
             DBT_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            DBT_CUDA(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i) {
+                DBT_CUDA(cudaEventCreateWithFlags(&packed[i], cudaEventDisableTiming));
+                DBT_CUDA(cudaEventCreateWithFlags(&landed[i], cudaEventDisableTiming));
+            }
             DBT_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
             DBT_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
             stage[0].pinned = stage[1].pinned = true;
@@ -68,8 +75,9 @@ struct HostCtx {
     }
 };
 
-int upload(HostCtx &c, const void *h, void *d, size_t bytes);
-int download(HostCtx &c, const void *d, void *h, size_t bytes);
+// `on`: the stream to copy on (default: the context's main stream)
+int upload(HostCtx &c, const void *h, void *d, size_t bytes, cudaStream_t on = nullptr);
+int download(HostCtx &c, const void *d, void *h, size_t bytes, cudaStream_t on = nullptr);
 inline size_t blocks_for(uint64_t rows) { return (size_t)((rows + kRpb - 1) / kRpb); }
 
 // out-of-core forms (host_ooc.cu).  chunk_blocks: the largest image that is processed in one piece.

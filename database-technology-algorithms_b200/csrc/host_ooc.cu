@@ -26,6 +26,10 @@ namespace dbt {
 
 static uint64_t g_chunk_override = 0;
 constexpr uint32_t kMaxRuns = 2048;
+// what the last out-of-core call did: runs (or R chunks), output chunks, chunk shrinks, key-width restarts,
+// blocks staged for the gathers, S chunks
+static uint64_t g_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+enum { OS_RUNS, OS_CHUNKS, OS_SHRINKS, OS_WIDENED, OS_STAGED, OS_SCHUNKS };
 
 uint64_t ooc_chunk_blocks(int op, uint64_t nbr, uint64_t nbs, int field) {
     uint64_t c = g_chunk_override;
@@ -219,6 +223,10 @@ static int sync(cudaStream_t st) {
     DBT_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
+static int sync_event(cudaEvent_t e) {
+    DBT_CUDA(cudaEventSynchronize(e));
+    return 0;
+}
 
 // Upload the image [h, h + nb blocks), prepare it at key width `kw` and append its columns.  *widened is set
 // (and nothing appended) when the image has strings that need the full 120-byte key while kw is 8.
@@ -247,10 +255,17 @@ int ooc_sort(HostCtx &c, const void *h_in, uint64_t nblocks, int field, void *h_
         return DBT_ERR_UNSUPPORTED;
     }
     cudaStream_t st = c.st;
+    memset(g_stats, 0, sizeof g_stats);
+    g_stats[OS_RUNS] = R;
     const int op = dedup ? DBT_OP_DEDUP : DBT_OP_SORT;
     const uint64_t S = C + 2 * R + 2; // staging blocks: a chunk's rows plus two partial blocks per run
-    DBT_TRY(c.in_r.ensure(S * DBT_BLOCK_BYTES));
-    DBT_TRY(c.out0.ensure(C * DBT_BLOCK_BYTES));
+    // double buffering: while chunk k's result goes home on st2, chunk k+1 comes in and is processed on st
+    Buf *in[2] = {&c.in_r, &c.in_s}, *out[2] = {&c.out0, &c.out1};
+    for (int k = 0; k < 2; ++k) {
+        DBT_TRY(in[k]->ensure(S * DBT_BLOCK_BYTES));
+        DBT_TRY(out[k]->ensure(C * DBT_BLOCK_BYTES));
+    }
+    cudaStream_t st2 = c.st2;
     void *runs = nullptr;
     DBT_TRY(runs_scratch(c, (size_t)nblocks * DBT_BLOCK_BYTES, &runs));
     Columns cols;
@@ -261,27 +276,34 @@ int ooc_sort(HostCtx &c, const void *h_in, uint64_t nblocks, int field, void *h_
 
     // ---- phase 1: runs ----------------------------------------------------------------------------
     for (uint64_t r = 0; r < R; ++r) {
+        const int k = (int)(r & 1);
         const uint64_t nb = std::min<uint64_t>(C, nblocks - r * C);
-        DBT_TRY(upload(c, (const char *)h_in + r * C * DBT_BLOCK_BYTES, c.in_r.p, nb * DBT_BLOCK_BYTES));
+        if (r >= 2) DBT_CUDA(cudaStreamWaitEvent(st, c.landed[k], 0)); // out[k] still holds run r-2 until it is home
+        DBT_TRY(upload(c, (const char *)h_in + r * C * DBT_BLOCK_BYTES, in[k]->p, nb * DBT_BLOCK_BYTES));
         uint64_t n = 0, u = 0;
         DBT_TRY(with_workspace(c, op, nb, 0, field, [&](void *ws, size_t wb) {
-            return dedup ? dbt_dev_dedup(c.in_r.p, nb, field, c.out0.p, ws, wb, st, &n, &u)
-                         : dbt_dev_mergesort(c.in_r.p, nb, field, c.out0.p, ws, wb, st, &n);
+            return dedup ? dbt_dev_dedup(in[k]->p, nb, field, out[k]->p, ws, wb, st, &n, &u)
+                         : dbt_dev_mergesort(in[k]->p, nb, field, out[k]->p, ws, wb, st, &n);
         }));
         n_in += n;
         run_rows[r] = dedup ? u : n;
-        DBT_TRY(download(c, c.out0.p, (char *)runs + r * C * DBT_BLOCK_BYTES, blocks_for(run_rows[r]) * DBT_BLOCK_BYTES));
-        if (!widened) DBT_TRY(collect_columns(c, c.out0.p, blocks_for(run_rows[r]), field, cols, &widened));
-        DBT_TRY(sync(st));
+        if (!widened) DBT_TRY(collect_columns(c, out[k]->p, blocks_for(run_rows[r]), field, cols, &widened));
+        DBT_CUDA(cudaEventRecord(c.packed[k], st));
+        DBT_CUDA(cudaStreamWaitEvent(st2, c.packed[k], 0));
+        DBT_TRY(download(c, out[k]->p, (char *)runs + r * C * DBT_BLOCK_BYTES, blocks_for(run_rows[r]) * DBT_BLOCK_BYTES, st2));
+        DBT_CUDA(cudaEventRecord(c.landed[k], st2));
     }
+    DBT_TRY(sync(st2));
+    DBT_TRY(sync(st));
     if (widened) { // some run has strings without a NUL in 32 bytes: collect every run's columns again at 120 bytes
+        g_stats[OS_WIDENED] = 1;
         DBT_TRY(cols.layout(c.cols, nmax, field, kStrWords));
         DBT_TRY(c.ws.ensure(dbt_dev_ws_bytes_kw(op, C, 0, field, kStrWords)));
         for (uint64_t r = 0; r < R; ++r) {
             const uint64_t nb = blocks_for(run_rows[r]);
-            DBT_TRY(upload(c, (const char *)runs + r * C * DBT_BLOCK_BYTES, c.in_r.p, nb * DBT_BLOCK_BYTES));
+            DBT_TRY(upload(c, (const char *)runs + r * C * DBT_BLOCK_BYTES, in[0]->p, nb * DBT_BLOCK_BYTES));
             bool again = false;
-            DBT_TRY(collect_columns(c, c.in_r.p, nb, field, cols, &again));
+            DBT_TRY(collect_columns(c, in[0]->p, nb, field, cols, &again));
         }
     }
     const uint64_t n = cols.n;
@@ -326,7 +348,9 @@ int ooc_sort(HostCtx &c, const void *h_in, uint64_t nblocks, int field, void *h_
     std::vector<uint32_t> h_lo(R), h_hi(R), h_base(R);
     const size_t smem = (3 * R + 2) * 4;
     uint64_t want = C * kRpb; // rows per output chunk; shrinks when a dedup chunk's slices would not fit the staging
-    for (uint64_t q0 = 0; q0 < m;) {
+    uint64_t chunk_no = 0;
+    for (uint64_t q0 = 0; q0 < m; ++chunk_no) {
+        const int k = (int)(chunk_no & 1);
         uint64_t q1 = std::min<uint64_t>(m, q0 + want);
         uint64_t staged = 0;
         for (;;) {
@@ -351,13 +375,16 @@ int ooc_sort(HostCtx &c, const void *h_in, uint64_t nblocks, int field, void *h_
             }
             want = std::max<uint64_t>(kRpb, (q1 - q0) / 2 / kRpb * kRpb);
             q1 = q0 + want; // (q1 < m here, so the chunk stays a whole number of blocks)
+            ++g_stats[OS_SHRINKS];
         }
+        ++g_stats[OS_CHUNKS];
+        g_stats[OS_STAGED] += staged;
         uint64_t cursor = 0;
         for (uint64_t r = 0; r < R; ++r) {
             h_base[r] = 0;
             if (h_lo[r] > h_hi[r]) continue;
             const uint64_t b0 = h_lo[r] / kRpb, nb = h_hi[r] / kRpb - b0 + 1;
-            DBT_TRY(upload(c, (const char *)runs + (r * C + b0) * DBT_BLOCK_BYTES, (char *)c.in_r.p + cursor * DBT_BLOCK_BYTES,
+            DBT_TRY(upload(c, (const char *)runs + (r * C + b0) * DBT_BLOCK_BYTES, (char *)in[k]->p + cursor * DBT_BLOCK_BYTES,
                            nb * DBT_BLOCK_BYTES));
             h_base[r] = (uint32_t)(cursor * kRpb - b0 * kRpb); // modulo 2^32; the sum with the row-in-run is in range
             cursor += nb;
@@ -367,12 +394,17 @@ int ooc_sort(HostCtx &c, const void *h_in, uint64_t nblocks, int field, void *h_
         slice_map_kernel<<<grid, 256, (2 * R + 1) * 4, st>>>(L, q0, q1, d_off, (uint32_t)R, d_base, d_idx);
         count_launch();
         DBT_KERNEL_CHECK();
-        DBT_TRY(gather_records(c.in_r.p, d_idx, nullptr, q1 - q0, c.out0.p, st, 0, (uint32_t)(q0 / kRpb)));
-        DBT_TRY(download(c, c.out0.p, (char *)h_out + (q0 / kRpb) * DBT_BLOCK_BYTES, blocks_for(q1 - q0) * DBT_BLOCK_BYTES));
-        DBT_TRY(sync(st)); // h_base / staging are reused by the next chunk
+        if (chunk_no >= 2) DBT_CUDA(cudaStreamWaitEvent(st, c.landed[k], 0)); // out[k]: chunk_no-2 must be home first
+        DBT_TRY(gather_records(in[k]->p, d_idx, nullptr, q1 - q0, out[k]->p, st, 0, (uint32_t)(q0 / kRpb)));
+        DBT_CUDA(cudaEventRecord(c.packed[k], st));
+        DBT_CUDA(cudaStreamWaitEvent(st2, c.packed[k], 0));
+        DBT_TRY(download(c, out[k]->p, (char *)h_out + (q0 / kRpb) * DBT_BLOCK_BYTES, blocks_for(q1 - q0) * DBT_BLOCK_BYTES, st2));
+        DBT_CUDA(cudaEventRecord(c.landed[k], st2));
         q0 = q1;
         if (want < C * kRpb) want = std::min<uint64_t>(C * kRpb, want * 2);
     }
+    DBT_TRY(sync(st2));
+    DBT_TRY(sync(st));
     return 0;
 }
 
@@ -386,32 +418,40 @@ int ooc_hashjoin(HostCtx &c, const void *h_in_r, uint64_t nbr, const void *h_in_
     }
     DBT_TRY(c.in_r.ensure(C * DBT_BLOCK_BYTES));
     DBT_TRY(c.in_s.ensure((C + 1) * DBT_BLOCK_BYTES)); // block 0: rows carried from the previous chunk
-    DBT_TRY(c.out0.ensure((C + 1) * DBT_BLOCK_BYTES));
+    Buf *out[2] = {&c.out0, &c.out1}; // chunk k's matches go home on st2 while chunk k+1 comes in on st
+    for (int k = 0; k < 2; ++k) DBT_TRY(out[k]->ensure((C + 1) * DBT_BLOCK_BYTES));
+    cudaStream_t st2 = c.st2;
     char *stage = (char *)c.in_s.p;
     Columns cols;
     uint32_t kw = 8;
+    memset(g_stats, 0, sizeof g_stats);
     uint64_t total_out = 0; // rows matched so far (keeps counting past the capacity so the caller learns the size)
     for (int attempt = 0; attempt < 2; ++attempt) {
         // ---- R: key columns, chunk by chunk ------------------------------------------------------------
         DBT_TRY(cols.layout(c.cols, nbr * kRpb, field, kw));
         DBT_TRY(c.ws.ensure(dbt_dev_ws_bytes_kw(DBT_OP_HASHJOIN, nbr, C, field, kw))); // R's table / bitmap + one S chunk's columns
         bool widened = false;
+        g_stats[OS_RUNS] = g_stats[OS_SCHUNKS] = 0;
         for (uint64_t b = 0; b < nbr && !widened; b += C) {
             const uint64_t nb = std::min<uint64_t>(C, nbr - b);
+            ++g_stats[OS_RUNS];
             DBT_TRY(upload(c, (const char *)h_in_r + b * DBT_BLOCK_BYTES, c.in_r.p, nb * DBT_BLOCK_BYTES));
             DBT_TRY(collect_columns(c, c.in_r.p, nb, field, cols, &widened));
         }
         if (widened) {
             kw = kStrWords;
+            g_stats[OS_WIDENED] = 1;
             continue;
         }
         KeyCols rk = cols.keycols(field);
         // ---- S: stream, probe, append ------------------------------------------------------------------
         uint64_t out_block = 0; // full blocks already in h_out
         uint32_t carry = 0;     // rows waiting in staging block 0
+        uint64_t emitted_chunks = 0;
         total_out = 0;
         for (uint64_t b = 0; b < nbs && !widened; b += C) {
             const uint64_t nb = std::min<uint64_t>(C, nbs - b);
+            ++g_stats[OS_SCHUNKS];
             DBT_TRY(upload(c, (const char *)h_in_s + b * DBT_BLOCK_BYTES, stage + DBT_BLOCK_BYTES, nb * DBT_BLOCK_BYTES));
             Arena ws(c.ws.p, c.ws.cap);
             Prepared ps;
@@ -444,24 +484,32 @@ int ooc_hashjoin(HostCtx &c, const void *h_in_r, uint64_t nbr, const void *h_in_
             if (total_out > cap_rows) continue; // over capacity: keep counting only
             uint32_t *rows = (uint32_t *)c.out2.p, *slots = rows + rows_cap + kRpb;
             const uint64_t emit = carry + total;
-            DBT_TRY(c.out0.ensure((blocks_for(emit) + 1) * DBT_BLOCK_BYTES));
+            const int k = (int)(emitted_chunks & 1);
+            if (emitted_chunks >= 2) DBT_TRY(sync_event(c.landed[k])); // out[k] may be regrown below: it must be idle
+            DBT_TRY(out[k]->ensure((blocks_for(emit) + 1) * DBT_BLOCK_BYTES));
             if (emit) {
                 const int grid = (int)std::min<uint64_t>((emit + 255) / 256, 148 * 8);
                 carry_slots_kernel<<<grid, 256, 0, st>>>(rows, ps.row_slot, carry, total, slots);
                 count_launch();
                 DBT_KERNEL_CHECK();
-                DBT_TRY(gather_records(stage, slots, nullptr, emit, c.out0.p, st, 0, (uint32_t)out_block));
+                DBT_TRY(gather_records(stage, slots, nullptr, emit, out[k]->p, st, 0, (uint32_t)out_block));
             }
             const uint64_t full = emit / kRpb;
-            DBT_TRY(download(c, c.out0.p, (char *)h_out + out_block * DBT_BLOCK_BYTES, full * DBT_BLOCK_BYTES));
             carry = (uint32_t)(emit - full * kRpb);
             if (carry) // the partly filled last block waits in staging block 0 for the next chunk's rows
-                DBT_CUDA(cudaMemcpyAsync(stage, (char *)c.out0.p + full * DBT_BLOCK_BYTES, DBT_BLOCK_BYTES, cudaMemcpyDeviceToDevice, st));
+                DBT_CUDA(cudaMemcpyAsync(stage, (char *)out[k]->p + full * DBT_BLOCK_BYTES, DBT_BLOCK_BYTES, cudaMemcpyDeviceToDevice, st));
+            DBT_CUDA(cudaEventRecord(c.packed[k], st));
+            DBT_CUDA(cudaStreamWaitEvent(st2, c.packed[k], 0));
+            DBT_TRY(download(c, out[k]->p, (char *)h_out + out_block * DBT_BLOCK_BYTES, full * DBT_BLOCK_BYTES, st2));
+            DBT_CUDA(cudaEventRecord(c.landed[k], st2));
             out_block += full;
-            DBT_TRY(sync(st));
+            ++emitted_chunks;
+            DBT_TRY(sync(st)); // the row lists (out2) and the workspace are reused by the next chunk
         }
+        DBT_TRY(sync(st2));
         if (widened) {
             kw = kStrWords;
+            g_stats[OS_WIDENED] = 1;
             continue;
         }
         if (carry && total_out <= cap_rows) {
@@ -479,6 +527,12 @@ int ooc_hashjoin(HostCtx &c, const void *h_in_r, uint64_t nbr, const void *h_in_
 }
 
 } // namespace dbt
+
+extern "C" int dbt_host_ooc_stats(uint64_t out[6]) {
+    if (!out) return DBT_ERR_ARG;
+    for (int i = 0; i < 6; ++i) out[i] = dbt::g_stats[i];
+    return 0;
+}
 
 extern "C" int dbt_host_set_chunk_blocks(uint64_t blocks) {
     dbt::g_chunk_override = blocks;

@@ -39,11 +39,12 @@ static bool is_device_accessible_host(const void *p) {
 }
 
 // host image -> device (direct when the caller's memory is pinned, else through pinned staging)
-int upload(HostCtx &c, const void *h, void *d, size_t bytes) {
-    StageScope sc(ST_H2D, c.st);
+int upload(HostCtx &c, const void *h, void *d, size_t bytes, cudaStream_t on) {
+    cudaStream_t st = on ? on : c.st;
+    StageScope sc(ST_H2D, st);
     if (!bytes) return 0;
     if (is_device_accessible_host(h)) {
-        DBT_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c.st));
+        DBT_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st));
         return 0;
     }
     const size_t chunk = kChunkBlocks * DBT_BLOCK_BYTES;
@@ -54,16 +55,17 @@ int upload(HostCtx &c, const void *h, void *d, size_t bytes) {
         size_t len = std::min(chunk, bytes - off);
         DBT_CUDA(cudaEventSynchronize(c.ev[k])); // previous copy out of this staging buffer is done
         memcpy(c.stage[k].p, (const char *)h + off, len);
-        DBT_CUDA(cudaMemcpyAsync((char *)d + off, c.stage[k].p, len, cudaMemcpyHostToDevice, c.st));
-        DBT_CUDA(cudaEventRecord(c.ev[k], c.st));
+        DBT_CUDA(cudaMemcpyAsync((char *)d + off, c.stage[k].p, len, cudaMemcpyHostToDevice, st));
+        DBT_CUDA(cudaEventRecord(c.ev[k], st));
     }
     return 0;
 }
-int download(HostCtx &c, const void *d, void *h, size_t bytes) {
-    StageScope sc(ST_D2H, c.st);
+int download(HostCtx &c, const void *d, void *h, size_t bytes, cudaStream_t on) {
+    cudaStream_t st = on ? on : c.st;
+    StageScope sc(ST_D2H, st);
     if (!bytes) return 0;
     if (is_device_accessible_host(h)) {
-        DBT_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c.st)); // completes at the job's wait
+        DBT_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st)); // completes at the job's wait
         return 0;
     }
     const size_t chunk = kChunkBlocks * DBT_BLOCK_BYTES;
@@ -73,12 +75,10 @@ int download(HostCtx &c, const void *d, void *h, size_t bytes) {
     int k = 0;
     for (size_t off = 0; off < bytes; off += chunk, k ^= 1) {
         size_t len = std::min(chunk, bytes - off);
-        if (nlen[k]) { // drain the previous use of this staging buffer
-            DBT_CUDA(cudaEventSynchronize(c.ev[k]));
-            memcpy((char *)h + noff[k], c.stage[k].p, nlen[k]);
-        }
-        DBT_CUDA(cudaMemcpyAsync(c.stage[k].p, (const char *)d + off, len, cudaMemcpyDeviceToHost, c.st));
-        DBT_CUDA(cudaEventRecord(c.ev[k], c.st));
+        DBT_CUDA(cudaEventSynchronize(c.ev[k])); // the previous use of this staging buffer (either direction) is over
+        if (nlen[k]) memcpy((char *)h + noff[k], c.stage[k].p, nlen[k]);
+        DBT_CUDA(cudaMemcpyAsync(c.stage[k].p, (const char *)d + off, len, cudaMemcpyDeviceToHost, st));
+        DBT_CUDA(cudaEventRecord(c.ev[k], st));
         noff[k] = off;
         nlen[k] = len;
     }

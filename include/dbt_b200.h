@@ -239,6 +239,9 @@ int dbt_host_trim(void);
  * tests use this to drive the path with small images; env DBT_OOC_CHUNK_BLOCKS does the same), 0 restores the
  * automatic choice from the device's memory size.  Limits: < 2^30 rows per sort, MergeJoin is in-core only. */
 int dbt_host_set_chunk_blocks(uint64_t blocks);
+/* what the last out-of-core call did: {runs (R chunks for a join), output chunks, chunk shrinks, key-width
+ * restarts (120-byte strings found late), blocks staged for the gathers, S chunks} */
+int dbt_host_ooc_stats(uint64_t out[6]);
 
 /* pinned host memory helpers for callers that want zero-staging copies */
 int dbt_host_alloc(void **p, size_t bytes);

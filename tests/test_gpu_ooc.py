@@ -27,6 +27,12 @@ def chunked(dbt):
     L.dbt_host_trim()
 
 
+def ooc_stats(dbt):
+    st = (C.c_uint64 * 6)()
+    dbt.check(dbt.lib().dbt_host_ooc_stats(st))
+    return dict(zip(("runs", "chunks", "shrinks", "widened", "staged", "s_chunks"), [int(x) for x in st]))
+
+
 def host_sort(dbt, orc, blocks, field):
     out = orc.new_blocks(len(blocks))
     n = C.c_uint64()
@@ -60,9 +66,15 @@ def test_out_of_core_sort_and_dedup_match_the_oracle(dbt, orc, chunked, field):
     got, n = host_sort(dbt, orc, f1, field)
     want = orc.sort(f1, field)
     assert n == 30000 and H.same_image(got, want), H.first_diff(got, want)
+    st = ooc_stats(dbt)
+    assert st["runs"] == 5 and st["chunks"] == 5 and st["shrinks"] == 0 and 300 <= st["staged"] <= 300 + 2 * 5 * 5
     got, n, u = host_dedup(dbt, orc, f1, field)
     want = orc.dedup(f1, field)
     assert (n, u) == (30000, orc.count_rows(want)) and H.same_image(got, want), H.first_diff(got, want)
+    st = ooc_stats(dbt)
+    assert st["runs"] == 5
+    if field == "1":  # 5000 distinct nums spread over all five runs: one chunk's slices overflow the staging
+        assert st["shrinks"] > 0 and st["chunks"] > 1
 
 
 def test_out_of_core_with_ragged_blocks_few_keys_and_tiny_chunks(dbt, orc, chunked):
@@ -107,6 +119,7 @@ def test_out_of_core_long_strings_appear_in_a_late_run(dbt, orc, chunked):
         got, n = host_sort(dbt, orc, f1, field)
         want = orc.sort(f1, field)
         assert H.same_image(got, want), (field, H.first_diff(got, want))
+        assert ooc_stats(dbt)["widened"] == 1
         got, n, u = host_dedup(dbt, orc, f1, field)
         assert H.same_image(got, orc.dedup(f1, field)), field
     # hash join: long strings only in a late S chunk => both sides restart at 120 bytes
@@ -115,6 +128,7 @@ def test_out_of_core_long_strings_appear_in_a_late_run(dbt, orc, chunked):
     rc, got, n = host_hashjoin(dbt, orc, f1, f2, "2")
     want = orc.hashjoin(f1, f2, "2")
     assert rc == 0 and n == orc.count_rows(want) and H.same_image(got, want)
+    assert ooc_stats(dbt)["widened"] == 1
 
 
 @pytest.mark.parametrize("field", FIELDS)
@@ -126,6 +140,8 @@ def test_out_of_core_hashjoin_streams_s_in_chunks(dbt, orc, chunked, field):
     rc, got, n = host_hashjoin(dbt, orc, f1, f2, field)
     want = orc.hashjoin(f1, f2, field)
     assert rc == 0 and n == orc.count_rows(want) and H.same_image(got, want), H.first_diff(got, want)
+    st = ooc_stats(dbt)
+    assert st["runs"] == 4 and st["s_chunks"] == 4
 
 
 def test_out_of_core_hashjoin_field3_multiplicity_and_capacity(dbt, orc, chunked):
