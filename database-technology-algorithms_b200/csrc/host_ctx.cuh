@@ -36,6 +36,7 @@ struct Buf {
 struct HostCtx {
     Buf in_r, in_s, out0, out1, out2, ws;
     Buf cols, runs; // out-of-core: resident key columns (device), sorted runs (pinned host)
+    Buf side_r, side_s, side_o; // out-of-core merge join: dedup(R), dedup(S), result when the caller passes no buffer (host)
     Buf stage[2];
     cudaStream_t st = nullptr;
     cudaStream_t st2 = nullptr;            // out-of-core: results go home on this stream while the next chunk comes in
@@ -86,6 +87,8 @@ int ooc_sort(HostCtx &c, const void *h_in, uint64_t nblocks, int field, void *h_
              uint64_t *nrows, uint64_t *nunique);
 int ooc_hashjoin(HostCtx &c, const void *h_in_r, uint64_t nbr, const void *h_in_s, uint64_t nbs, int field, void *h_out,
                  uint64_t out_capacity_blocks, uint64_t chunk_blocks, uint64_t *nres);
+int ooc_mergejoin(HostCtx &c, const void *h_in_r, uint64_t nbr, const void *h_in_s, uint64_t nbs, int field, void *h_out_ur,
+                  void *h_out_us, void *h_out, uint64_t chunk_blocks, uint64_t res[4]);
 
 } // namespace dbt
 

@@ -223,6 +223,14 @@ static int sync(cudaStream_t st) {
     DBT_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
+// on every exit path (errors included) nothing may still be copying into the caller's buffers
+struct DrainOnExit {
+    cudaStream_t a, b;
+    ~DrainOnExit() {
+        cudaStreamSynchronize(a);
+        cudaStreamSynchronize(b);
+    }
+};
 static int sync_event(cudaEvent_t e) {
     DBT_CUDA(cudaEventSynchronize(e));
     return 0;
@@ -255,6 +263,7 @@ int ooc_sort(HostCtx &c, const void *h_in, uint64_t nblocks, int field, void *h_
         return DBT_ERR_UNSUPPORTED;
     }
     cudaStream_t st = c.st;
+    DrainOnExit drain{c.st, c.st2};
     memset(g_stats, 0, sizeof g_stats);
     g_stats[OS_RUNS] = R;
     const int op = dedup ? DBT_OP_DEDUP : DBT_OP_SORT;
@@ -411,6 +420,7 @@ int ooc_sort(HostCtx &c, const void *h_in, uint64_t nblocks, int field, void *h_
 int ooc_hashjoin(HostCtx &c, const void *h_in_r, uint64_t nbr, const void *h_in_s, uint64_t nbs, int field, void *h_out,
                  uint64_t out_capacity_blocks, uint64_t C, uint64_t *nres) {
     cudaStream_t st = c.st;
+    DrainOnExit drain{c.st, c.st2};
     const uint64_t cap_rows = out_capacity_blocks * kRpb;
     if (nbr * kRpb >= (1ull << 32) || C * kRpb >= (1ull << 31)) {
         set_error("out-of-core hash join: R must have fewer than 2^32 rows");
@@ -523,6 +533,131 @@ int ooc_hashjoin(HostCtx &c, const void *h_in_r, uint64_t nbr, const void *h_in_
         set_error("hashjoin: output capacity too small (nres returned)");
         return DBT_ERR_WORKSPACE;
     }
+    return 0;
+}
+
+// ---- merge join out of core = dedup(R), dedup(S) (each out of core when it has to be), then a streamed semi-join
+// of dedup(R) against the keys of dedup(S).  dedup(R) is in ascending key order and holds the min-recid row of every
+// key, so the rows that survive are exactly the reference's intersection output (DatabaseProject.cpp:414-460, emit
+// R's record), in the same order; building on dedup(S) keeps field '3' at one emission per key.
+static int host_dedup_any(HostCtx &c, const void *h_in, uint64_t nb, int field, void *h_out, uint64_t C, uint64_t *u) {
+    uint64_t n = 0;
+    if (nb > C) return ooc_sort(c, h_in, nb, field, h_out, true, C, &n, u);
+    const size_t bytes = (size_t)nb * DBT_BLOCK_BYTES;
+    DBT_TRY(c.in_r.ensure(bytes));
+    DBT_TRY(c.out0.ensure(bytes));
+    DBT_TRY(upload(c, h_in, c.in_r.p, bytes));
+    DBT_TRY(with_workspace(c, DBT_OP_DEDUP, nb, 0, field, [&](void *ws, size_t wb) {
+        return dbt_dev_dedup(c.in_r.p, nb, field, c.out0.p, ws, wb, c.st, &n, u);
+    }));
+    DBT_TRY(download(c, c.out0.p, h_out, blocks_for(*u) * DBT_BLOCK_BYTES));
+    return sync(c.st);
+}
+
+// host-side key order of two records (DatabaseProject.cpp:44-92), for the walk's read counter only
+static const unsigned char *host_row(const void *img, uint64_t i) {
+    return (const unsigned char *)img + (i / kRpb) * DBT_BLOCK_BYTES + 8 + (i % kRpb) * DBT_RECORD_BYTES;
+}
+static int host_key_cmp(const unsigned char *a, const unsigned char *b, int field) {
+    auto u32 = [](const unsigned char *p) {
+        uint32_t v;
+        memcpy(&v, p, 4);
+        return v;
+    };
+    auto cmp_str = [](const unsigned char *x, const unsigned char *y) {
+        for (int i = 0; i < 120; ++i) {
+            if (x[i] != y[i]) return x[i] < y[i] ? -1 : 1;
+            if (!x[i]) return 0;
+        }
+        return 0;
+    };
+    if (field == '0' || field == '1' || field == '3') {
+        const uint32_t x = u32(a + (field == '0' ? 0 : 4)), y = u32(b + (field == '0' ? 0 : 4));
+        if (x != y) return x < y ? -1 : 1;
+        if (field != '3') return 0;
+    }
+    return cmp_str(a + 8, b + 8);
+}
+// block reads after the first two of the reference's two-pointer walk over two sorted unique images
+// (the closed form of kernels_join.cu: walk_reads_kernel, evaluated on the host images)
+static uint64_t host_walk_reads(const void *ur, uint64_t nr, const void *us, uint64_t ns, int field) {
+    if (!nr || !ns) return 0;
+    auto lower_bound = [&](const void *img, uint64_t n, const unsigned char *key) {
+        uint64_t lo = 0, hi = n;
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) / 2;
+            if (host_key_cmp(host_row(img, mid), key, field) < 0) lo = mid + 1;
+            else hi = mid;
+        }
+        return lo;
+    };
+    const unsigned char *lr = host_row(ur, nr - 1), *ls = host_row(us, ns - 1);
+    if (host_key_cmp(lr, ls, field) <= 0) { // R runs out first (or both together)
+        const uint64_t lb = lower_bound(us, ns, lr);
+        return (nr + kRpb - 1) / kRpb + lb / kRpb;
+    }
+    const uint64_t lb = lower_bound(ur, nr, ls);
+    const bool match = lb < nr && host_key_cmp(ls, host_row(ur, lb), field) == 0;
+    return (lb + (match ? 1 : 0)) / kRpb + (ns + kRpb - 1) / kRpb;
+}
+
+static int host_scratch(Buf &b, size_t bytes, void **p) { // pinned if the host can spare it, pageable otherwise
+    if (b.cap >= bytes && b.p) {
+        *p = b.p;
+        return 0;
+    }
+    b.release();
+    void *q = nullptr;
+    if (cudaHostAlloc(&q, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess) {
+        b.pinned = true;
+    } else {
+        cudaGetLastError();
+        q = malloc(bytes ? bytes : 1);
+        if (!q) {
+            set_error("out-of-core: no host memory for a side image");
+            return DBT_ERR_WORKSPACE;
+        }
+        b.pinned = false;
+        b.malloced = true;
+    }
+    b.p = q;
+    b.cap = bytes;
+    *p = q;
+    return 0;
+}
+
+int ooc_mergejoin(HostCtx &c, const void *h_in_r, uint64_t nbr, const void *h_in_s, uint64_t nbs, int field, void *h_out_ur,
+                  void *h_out_us, void *h_out, uint64_t C, uint64_t res[4]) {
+    void *ur = h_out_ur, *us = h_out_us;
+    if (!ur) DBT_TRY(host_scratch(c.side_r, (size_t)nbr * DBT_BLOCK_BYTES, &ur));
+    if (!us) DBT_TRY(host_scratch(c.side_s, (size_t)nbs * DBT_BLOCK_BYTES, &us));
+    uint64_t nur = 0, nus = 0, nres = 0;
+    DBT_TRY(host_dedup_any(c, h_in_r, nbr, field, ur, C, &nur));
+    DBT_TRY(host_dedup_any(c, h_in_s, nbs, field, us, C, &nus));
+    const uint64_t bur = blocks_for(nur), bus = blocks_for(nus);
+    void *out = h_out;
+    if (!out) DBT_TRY(host_scratch(c.side_o, (size_t)std::min(bur, bus) * DBT_BLOCK_BYTES, &out));
+    if (nur && nus) {
+        // semi-join: probe side = dedup(R) (its rows are emitted, in its order), build side = the keys of dedup(S)
+        if (std::max(bur, bus) > C) {
+            DBT_TRY(ooc_hashjoin(c, us, bus, ur, bur, field, out, std::min(bur, bus), C, &nres));
+        } else {
+            DBT_TRY(c.in_r.ensure(bus * DBT_BLOCK_BYTES));
+            DBT_TRY(c.in_s.ensure(bur * DBT_BLOCK_BYTES));
+            DBT_TRY(c.out0.ensure(std::min(bur, bus) * DBT_BLOCK_BYTES));
+            DBT_TRY(upload(c, us, c.in_r.p, bus * DBT_BLOCK_BYTES));
+            DBT_TRY(upload(c, ur, c.in_s.p, bur * DBT_BLOCK_BYTES));
+            DBT_TRY(with_workspace(c, DBT_OP_HASHJOIN, bus, bur, field, [&](void *ws, size_t wb) {
+                return dbt_dev_hashjoin(c.in_r.p, bus, c.in_s.p, bur, field, c.out0.p, std::min(bur, bus), ws, wb, c.st, &nres);
+            }));
+            DBT_TRY(download(c, c.out0.p, out, blocks_for(nres) * DBT_BLOCK_BYTES));
+            DBT_TRY(sync(c.st));
+        }
+    }
+    res[0] = nres;
+    res[1] = nur;
+    res[2] = nus;
+    res[3] = host_walk_reads(ur, nur, us, nus, field);
     return 0;
 }
 

@@ -175,10 +175,11 @@ static int mergejoin_begin(int slot, const void *h_in_r, uint64_t nbr, const voi
     HostCtx *cp;
     DBT_TRY(slot_begin(slot, device, &cp));
     HostCtx &c = *cp;
-    if (ooc_chunk_blocks(DBT_OP_MERGEJOIN, nbr, nbs, field)) {
-        set_error("MergeJoin of images larger than the device is not implemented: deduplicate both sides out of core "
-                  "(dbt_host_dedup) and join the results");
-        return DBT_ERR_UNSUPPORTED;
+    if (const uint64_t chunk = ooc_chunk_blocks(DBT_OP_MERGEJOIN, nbr, nbs, field)) { // two dedups + a streamed semi-join
+        uint64_t r[4] = {0, 0, 0, 0};
+        DBT_TRY(ooc_mergejoin(c, h_in_r, nbr, h_in_s, nbs, field, h_out_ur, h_out_us, h_out, chunk, r));
+        g_jobs[slot] = Job{true, {r[0], r[1], r[2], r[3]}};
+        return 0;
     }
     size_t br = (size_t)nbr * DBT_BLOCK_BYTES, bs = (size_t)nbs * DBT_BLOCK_BYTES;
     DBT_TRY(c.in_r.ensure(br));
@@ -229,6 +230,12 @@ static int hashjoin_begin(int slot, const void *h_in_r, uint64_t nbr, const void
     return 0;
 }
 
+// a failed begin leaves nothing in flight that still reads or writes the caller's buffers
+static int drained(int slot, int rc) {
+    if (rc && slot >= 0 && slot < DBT_HOST_SLOTS && slot_ctx(slot).st) cudaStreamSynchronize(slot_ctx(slot).st);
+    return rc;
+}
+
 static int job_wait(int slot, uint64_t *result4) {
     if (slot < 0 || slot >= DBT_HOST_SLOTS) {
         set_error("bad job slot");
@@ -248,18 +255,18 @@ static int job_wait(int slot, uint64_t *result4) {
 } // namespace dbt
 
 extern "C" int dbt_host_mergesort_begin(int slot, const void *h_in, uint64_t nblocks, int field, void *h_out, int device) {
-    return sort_begin(slot, h_in, nblocks, field, h_out, device);
+    return drained(slot, sort_begin(slot, h_in, nblocks, field, h_out, device));
 }
 extern "C" int dbt_host_dedup_begin(int slot, const void *h_in, uint64_t nblocks, int field, void *h_out, int device) {
-    return dedup_begin(slot, h_in, nblocks, field, h_out, device);
+    return drained(slot, dedup_begin(slot, h_in, nblocks, field, h_out, device));
 }
 extern "C" int dbt_host_mergejoin_begin(int slot, const void *h_in_r, uint64_t nbr, const void *h_in_s, uint64_t nbs,
                                         int field, void *h_out_ur, void *h_out_us, void *h_out, int device) {
-    return mergejoin_begin(slot, h_in_r, nbr, h_in_s, nbs, field, h_out_ur, h_out_us, h_out, device);
+    return drained(slot, mergejoin_begin(slot, h_in_r, nbr, h_in_s, nbs, field, h_out_ur, h_out_us, h_out, device));
 }
 extern "C" int dbt_host_hashjoin_begin(int slot, const void *h_in_r, uint64_t nbr, const void *h_in_s, uint64_t nbs,
                                        int field, void *h_out, uint64_t out_capacity_blocks, int device) {
-    return hashjoin_begin(slot, h_in_r, nbr, h_in_s, nbs, field, h_out, out_capacity_blocks, device, nullptr);
+    return drained(slot, hashjoin_begin(slot, h_in_r, nbr, h_in_s, nbs, field, h_out, out_capacity_blocks, device, nullptr));
 }
 extern "C" int dbt_host_job_wait(int slot, uint64_t *result4) { return job_wait(slot, result4); }
 extern "C" int dbt_host_job_slots(void) { return DBT_HOST_SLOTS; }
@@ -275,7 +282,7 @@ extern "C" int dbt_host_trim(void) {
         if (c.device < 0) continue;
         DBT_CUDA(cudaSetDevice(c.device));
         DBT_CUDA(cudaStreamSynchronize(c.st));
-        Buf *bufs[] = {&c.in_r, &c.in_s, &c.out0, &c.out1, &c.out2, &c.ws, &c.stage[0], &c.stage[1], &c.cols, &c.runs};
+        Buf *bufs[] = {&c.in_r, &c.in_s, &c.out0, &c.out1, &c.out2, &c.ws, &c.stage[0], &c.stage[1], &c.cols, &c.runs, &c.side_r, &c.side_s, &c.side_o};
         for (Buf *b : bufs) b->release();
     }
     return 0;
@@ -283,7 +290,7 @@ extern "C" int dbt_host_trim(void) {
 
 extern "C" int dbt_host_mergesort(const void *h_in, uint64_t nblocks, int field, void *h_out, int device,
                                   uint64_t *nrows) {
-    DBT_TRY(sort_begin(0, h_in, nblocks, field, h_out, device));
+    DBT_TRY(drained(0, sort_begin(0, h_in, nblocks, field, h_out, device)));
     uint64_t r[4];
     DBT_TRY(job_wait(0, r));
     if (nrows) *nrows = r[0];
@@ -292,7 +299,7 @@ extern "C" int dbt_host_mergesort(const void *h_in, uint64_t nblocks, int field,
 
 extern "C" int dbt_host_dedup(const void *h_in, uint64_t nblocks, int field, void *h_out, int device, uint64_t *nrows,
                               uint64_t *nunique) {
-    DBT_TRY(dedup_begin(0, h_in, nblocks, field, h_out, device));
+    DBT_TRY(drained(0, dedup_begin(0, h_in, nblocks, field, h_out, device)));
     uint64_t r[4];
     DBT_TRY(job_wait(0, r));
     if (nrows) *nrows = r[0];
@@ -302,7 +309,7 @@ extern "C" int dbt_host_dedup(const void *h_in, uint64_t nblocks, int field, voi
 
 extern "C" int dbt_host_mergejoin(const void *h_in_r, uint64_t nbr, const void *h_in_s, uint64_t nbs, int field,
                                   void *h_out_ur, void *h_out_us, void *h_out, int device, uint64_t *res) {
-    DBT_TRY(mergejoin_begin(0, h_in_r, nbr, h_in_s, nbs, field, h_out_ur, h_out_us, h_out, device));
+    DBT_TRY(drained(0, mergejoin_begin(0, h_in_r, nbr, h_in_s, nbs, field, h_out_ur, h_out_us, h_out, device)));
     uint64_t r[4];
     DBT_TRY(job_wait(0, r));
     if (res) memcpy(res, r, sizeof r);
@@ -311,7 +318,7 @@ extern "C" int dbt_host_mergejoin(const void *h_in_r, uint64_t nbr, const void *
 
 extern "C" int dbt_host_hashjoin(const void *h_in_r, uint64_t nbr, const void *h_in_s, uint64_t nbs, int field,
                                  void *h_out, uint64_t out_capacity_blocks, int device, uint64_t *nres) {
-    DBT_TRY(hashjoin_begin(0, h_in_r, nbr, h_in_s, nbs, field, h_out, out_capacity_blocks, device, nres));
+    DBT_TRY(drained(0, hashjoin_begin(0, h_in_r, nbr, h_in_s, nbs, field, h_out, out_capacity_blocks, device, nres)));
     uint64_t r[4];
     DBT_TRY(job_wait(0, r));
     if (nres) *nres = r[0];
@@ -572,9 +579,26 @@ void MergeJoin(char *infile1, char *infile2, unsigned char field, block_t *, uns
     check_nmem_or_exit(nmem_blocks);
     check_field_or_exit(field);
     HostCtx &c = ctx();
-    if (ooc_chunk_blocks(DBT_OP_MERGEJOIN, file_blocks(infile1), file_blocks(infile2), field))
-        die("MergeJoin: the two files do not fit on the device together (out-of-core MergeJoin is not implemented; "
-            "EliminateDuplicates on each file works out of core)");
+    if (const uint64_t chunk = ooc_chunk_blocks(DBT_OP_MERGEJOIN, file_blocks(infile1), file_blocks(infile2), field)) {
+        // larger than the device: both dedups and the intersection run out of core through host memory (host_ooc.cu)
+        const uint64_t nbr = read_file(infile1, g_files.pin[0]);
+        const uint64_t nbs = read_file(infile2, g_files.pin[1]);
+        must(g_files.pin[2].ensure((size_t)nbr * DBT_BLOCK_BYTES), "pinned staging");
+        must(g_files.pin[3].ensure((size_t)nbs * DBT_BLOCK_BYTES), "pinned staging");
+        must(g_files.pin[4].ensure((size_t)std::min(nbr, nbs) * DBT_BLOCK_BYTES), "pinned staging");
+        uint64_t res[4] = {0, 0, 0, 0};
+        must(ooc_mergejoin(c, g_files.pin[0].p, nbr, g_files.pin[1].p, nbs, field, g_files.pin[2].p, g_files.pin[3].p,
+                           g_files.pin[4].p, chunk, res), "out-of-core merge join");
+        std::cout << "Eliminating Duplicates..." << std::endl << "Merge Sorting..." << std::endl
+                  << "Eliminating Duplicates..." << std::endl;
+        write_file("1outfile.bin", g_files.pin[2].p, blocks_for(res[1]) * DBT_BLOCK_BYTES);
+        write_file("2outfile.bin", g_files.pin[3].p, blocks_for(res[2]) * DBT_BLOCK_BYTES);
+        write_file(outfile, g_files.pin[4].p, blocks_for(res[0]) * DBT_BLOCK_BYTES);
+        stage_resolve();
+        *nres = clamp32(res[0]);
+        *nios = clamp32(dbt_mergejoin_nios(nbr, nbs, nmem_blocks, res));
+        return;
+    }
     const uint64_t nbr = load_file(infile1, g_files.pin[0], c.in_r);
     const uint64_t nbs = load_file(infile2, g_files.pin[1], c.in_s);
     must(c.out0.ensure((size_t)nbr * DBT_BLOCK_BYTES), "device output");

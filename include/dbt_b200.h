@@ -237,7 +237,8 @@ int dbt_host_trim(void);
  * sort/dedup = in-core sort of chunk-sized runs + one global sort of the resident key columns + chunked gather from
  * the runs; hash join = R's key columns resident, S streamed in chunks.  `blocks` (> 0) forces the chunk size (the
  * tests use this to drive the path with small images; env DBT_OOC_CHUNK_BLOCKS does the same), 0 restores the
- * automatic choice from the device's memory size.  Limits: < 2^30 rows per sort, MergeJoin is in-core only. */
+ * automatic choice from the device's memory size.  MergeJoin out of core = both dedups as above + a streamed
+ * semi-join of dedup(R) against the keys of dedup(S).  Limit: < 2^30 rows per out-of-core sort. */
 int dbt_host_set_chunk_blocks(uint64_t blocks);
 /* what the last out-of-core call did: {runs (R chunks for a join), output chunks, chunk shrinks, key-width
  * restarts (120-byte strings found late), blocks staged for the gathers, S chunks} */

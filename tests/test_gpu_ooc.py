@@ -164,6 +164,25 @@ def test_out_of_core_hashjoin_field3_multiplicity_and_capacity(dbt, orc, chunked
     assert rc == 0 and n == nres and H.same_image(got, want)
 
 
+@pytest.mark.parametrize("field", FIELDS)
+def test_out_of_core_mergejoin_is_two_dedups_and_a_streamed_semijoin(dbt, orc, chunked, field):
+    L = dbt.lib()
+    f1, f2 = orc.gen_ref(9, 150)
+    want, wur, wus, info = orc.mergejoin(f1, f2, field)
+    for r, s, chunk in ((f1, f2, 40), (f1[:30], f2, 40), (f1, f2[:25], 40)):  # both sides chunked / only one of them
+        want, wur, wus, info = orc.mergejoin(r, s, field)
+        chunked(chunk)
+        res = (C.c_uint64 * 4)()
+        o1, o2, o3 = orc.new_blocks(len(r)), orc.new_blocks(len(s)), orc.new_blocks(min(len(r), len(s)))
+        dbt.check(L.dbt_host_mergejoin(r.ctypes.data, len(r), s.ctypes.data, len(s), ord(field), o1.ctypes.data, o2.ctypes.data,
+                                       o3.ctypes.data, 0, res))
+        assert [int(x) for x in res] == [info["nres"], info["nunique_R"], info["nunique_S"], info["later_reads"]], (field, len(r), len(s))
+        assert H.same_image(o3[: len(want)], want) and H.same_image(o1[: len(wur)], wur) and H.same_image(o2[: len(wus)], wus)
+        # the side images are optional
+        dbt.check(L.dbt_host_mergejoin(r.ctypes.data, len(r), s.ctypes.data, len(s), ord(field), None, None, o3.ctypes.data, 0, res))
+        assert res[0] == info["nres"] and H.same_image(o3[: len(want)], want)
+
+
 def test_file_entry_points_switch_to_out_of_core(dbt, orc, chunked, tmp_path, monkeypatch):
     monkeypatch.chdir(tmp_path)
     f1, f2 = orc.gen_ref(42, 300)
@@ -181,6 +200,11 @@ def test_file_entry_points_switch_to_out_of_core(dbt, orc, chunked, tmp_path, mo
     want = orc.hashjoin(f1, f2, "1")
     assert n == orc.count_rows(want) and nios == orc.hashjoin_nios(300, 300, 64, n)
     assert H.same_image(read_blocks(orc, "outhash.bin"), want)
+    n, nios = call_join(dbt, "MergeJoin", "file.bin", "file2.bin", "2", 100, "outmerge.bin")
+    want, ur, us, info = orc.mergejoin(f1, f2, "2")
+    assert n == info["nres"] and nios == orc.mergejoin_nios(300, 300, 100, info)
+    assert H.same_image(read_blocks(orc, "outmerge.bin"), want)
+    assert H.same_image(read_blocks(orc, "1outfile.bin"), ur) and H.same_image(read_blocks(orc, "2outfile.bin"), us)
 
 
 def test_out_of_core_jobs_and_in_core_jobs_share_the_slots(dbt, orc, chunked):
