@@ -222,3 +222,41 @@ def test_out_of_core_jobs_and_in_core_jobs_share_the_slots(dbt, orc, chunked):
     for slot, o in ((1, out), (2, out2)):
         dbt.check(L.dbt_host_job_wait(slot, r))
         assert r[1] == orc.count_rows(want) and H.same_image(o[: len(want)], want)
+
+
+_OOC_CASES = []
+_rr = np.random.default_rng(777)
+for _i in range(10):
+    _OOC_CASES.append({"seed": 5000 + _i, "recid": str(_rr.choice(["ascending", "shuffled", "duplicates"])),
+                       "strlen": str(_rr.choice(["short", "short", "boundary", "long"])), "ragged": bool(_rr.random() < 0.5),
+                       "nb": int(_rr.integers(60, 200)), "chunk": int(_rr.integers(32, 64))})
+
+
+@pytest.mark.parametrize("case", _OOC_CASES, ids=lambda c: f"s{c['seed']}-{c['recid'][:3]}-{c['strlen'][:2]}-{'rag' if c['ragged'] else 'dense'}-{c['nb']}b-c{c['chunk']}")
+def test_out_of_core_random_parity(dbt, orc, chunked, case):
+    """Random shapes (ragged headers, duplicate recids, strings around the 32-byte boundary, junk after the NUL)
+    through every out-of-core operator with a random forced chunk size."""
+    from test_gpu_random import random_file
+
+    L = dbt.lib()
+    rng = np.random.default_rng(case["seed"])
+    r = random_file(orc, rng, case["nb"], case)
+    s = random_file(orc, rng, int(rng.integers(40, 160)), case)
+    chunked(case["chunk"])
+    for field in FIELDS:
+        got, n = host_sort(dbt, orc, r, field)
+        want = orc.sort(r, field)
+        assert H.same_image(got, want), ("sort", field, H.first_diff(got, want))
+        got, n, u = host_dedup(dbt, orc, r, field)
+        want = orc.dedup(r, field)
+        assert H.same_image(got, want), ("dedup", field, H.first_diff(got, want))
+        want = orc.hashjoin(r, s, field)
+        rc, got, n = host_hashjoin(dbt, orc, r, s, field, cap_blocks=max(H.nb(orc.count_rows(want)), 1))
+        assert rc == 0 and H.same_image(got, want), ("hashjoin", field)
+        want, wur, wus, info = orc.mergejoin(r, s, field)
+        res = (C.c_uint64 * 4)()
+        o1, o2, o3 = orc.new_blocks(len(r)), orc.new_blocks(len(s)), orc.new_blocks(min(len(r), len(s)))
+        dbt.check(L.dbt_host_mergejoin(r.ctypes.data, len(r), s.ctypes.data, len(s), ord(field), o1.ctypes.data, o2.ctypes.data,
+                                       o3.ctypes.data, 0, res))
+        assert [int(x) for x in res] == [info["nres"], info["nunique_R"], info["nunique_S"], info["later_reads"]], ("mergejoin", field)
+        assert H.same_image(o3[: len(want)], want) and H.same_image(o1[: len(wur)], wur) and H.same_image(o2[: len(wus)], wus)
