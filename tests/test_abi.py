@@ -45,7 +45,7 @@ def test_contract_header_layout_compiles_and_matches(tmp_path):
 
 
 def test_counters_are_pure_host_arithmetic(dbt, orc):
-    for B, M in [(10000, 64), (10000, 101), (200, 8), (600, 3), (1, 3), (1000000, 64)]:
+    for B, M in [(10000, 64), (10000, 101), (200, 8), (600, 8), (600, 3), (300, 16), (1, 3), (1000000, 64)]:
         assert dbt.sort_counters(B, M) == orc.sort_counters(B, M)
     L = dbt.lib()
     assert L.dbt_dedup_nios(300, 64, 8698) == orc.dedup_nios(300, 64, 8698) == 707

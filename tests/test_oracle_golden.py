@@ -89,6 +89,12 @@ def test_counter_formulae_match_the_reference(orc, golden):
     assert orc.sort_counters(10000, 101) == {"nsorted_segs": 101, "npasses": 2, "nios": 20100}
     assert orc.sort_counters(1000000, 64) == {"nsorted_segs": 15879, "npasses": 4, "nios": 4000000}
     assert orc.sort_counters(10_000_000, 64) == {"nsorted_segs": 158772, "npasses": 4, "nios": 40000000}
+    # the probe results frozen in SURVEY.md 8(c): (blocks, nmem) -> (segments, passes)
+    for (B, M), (segs, passes) in {(200, 8): (30, 3), (600, 8): (89, 4), (600, 3): (402, 9), (300, 16): (22, 3),
+                                   (10000, 101): (101, 2)}.items():
+        c = orc.sort_counters(B, M)
+        assert (c["nsorted_segs"], c["npasses"]) == (segs, passes), (B, M, c)
+    assert orc.sort_counters(300, 16)["nios"] == 904
     for field in "0123":
         k = meta["counters"][f"hjoin_f{field}"]
         assert abs(orc.hashjoin_nios(meta["nblocks"], meta["nblocks"], 64, k["nres"]) - k["nios"]) <= 1
