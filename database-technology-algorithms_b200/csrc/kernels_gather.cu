@@ -33,7 +33,13 @@ struct ScanWs {
     uint32_t *ctr;   // zeroed
 };
 
-constexpr int kScanThreads = 512;
+#ifndef DBT_SCAN_THREADS
+#define DBT_SCAN_THREADS 512
+#endif
+#ifndef DBT_SCAN_MINB
+#define DBT_SCAN_MINB 2
+#endif
+constexpr int kScanThreads = DBT_SCAN_THREADS;
 constexpr int kScanItems = 16; // two groups of 8 consecutive rows per thread
 constexpr int kScanTile = kScanThreads * kScanItems;
 
@@ -44,7 +50,7 @@ constexpr int kScanTile = kScanThreads * kScanItems;
 //          A tile's outputs are first compacted in shared memory and then written coalesced; a tile that emits
 //          more than it holds (field-'3' multiplicities) writes directly.
 template <class CountFn, class EmitFn>
-__global__ void __launch_bounds__(kScanThreads, 2) // <= 64 registers: two 512-thread CTAs per SM (ncu: the compaction variant took 110)
+__global__ void __launch_bounds__(kScanThreads, DBT_SCAN_MINB) // <= 64 registers: two 512-thread CTAs per SM (ncu: the compaction variant took 110)
 scan_emit_kernel(uint64_t n, CountFn cnt, EmitFn emit, ScanWs ws, unsigned long long *total_out) {
     __shared__ uint64_t s_wsum[kScanThreads / 32];
     __shared__ uint64_t s_prefix;
