@@ -554,8 +554,8 @@ def extra_measurements(dbt, torch, dev, peak):
             ok = ok and bool((c[1:] >= c[:-1]).all().item())
         assert ok, "1B pair sort produced an unsorted result"
         out["pair_sort_1B_u32"] = {"records_per_s": n / (ms * 1e-3), "ms": ms,
-                                   "hbm_frac_of_measured_at_72B_per_record": 72.0 * n / (ms * 1e-3) / 1e9 / peak,
-                                   "note": "keys+values already in HBM; includes the OR/AND pre-scan (4 B), histogram (4 B) and 4 passes x 16 B"}
+                                   "hbm_frac_of_measured_at_68B_per_record": 68.0 * n / (ms * 1e-3) / 1e9 / peak,
+                                   "note": "keys+values already in HBM; one read of the keys for OR/AND + the four byte histograms (4 B) and 4 passes x 16 B = 68 B per pair (SURVEY.md 8d)"}
         del keys, k1, k2, v1, v2, ws
         torch.cuda.empty_cache()
     except Exception as e:  # noqa: BLE001

@@ -146,6 +146,48 @@ __global__ void __launch_bounds__(512) hist_kernel(const uint32_t *__restrict__ 
     }
 }
 
+// OR / AND of the keys and the histograms of their four bytes in ONE read (the pair-sort entry point: the digit
+// plan is only known after the OR/AND, but when it turns out byte-aligned -- every full-range sort -- the byte
+// histograms are exactly the planned digits' and the separate histogram read is skipped).  16-byte aligned keys.
+__global__ void __launch_bounds__(512) or_and_hist_kernel(const uint32_t *__restrict__ keys, uint64_t n,
+                                                          uint32_t *__restrict__ or_and /*2, initialised*/,
+                                                          uint32_t *__restrict__ ghist /*[4][256], zeroed*/) {
+    __shared__ uint32_t sh[4][kRadix];
+    for (int i = threadIdx.x; i < 4 * kRadix; i += blockDim.x) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    uint32_t o = 0, a = 0xFFFFFFFFu;
+    auto one = [&](uint32_t k) {
+        o |= k;
+        a &= k;
+        atomicAdd(&sh[0][k & 0xFF], 1u);
+        atomicAdd(&sh[1][(k >> 8) & 0xFF], 1u);
+        atomicAdd(&sh[2][(k >> 16) & 0xFF], 1u);
+        atomicAdd(&sh[3][k >> 24], 1u);
+    };
+    const uint64_t nvec = n / 4;
+    const uint4 *kv = reinterpret_cast<const uint4 *>(keys);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        const uint4 v = kv[i];
+        one(v.x);
+        one(v.y);
+        one(v.z);
+        one(v.w);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) one(keys[nvec * 4 + threadIdx.x]);
+    o = __reduce_or_sync(0xFFFFFFFFu, o);
+    a = __reduce_and_sync(0xFFFFFFFFu, a);
+    if ((threadIdx.x & 31) == 0) {
+        atomicOr(&or_and[0], o);
+        atomicAnd(&or_and[1], a);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * kRadix; i += blockDim.x) {
+        const uint32_t c = (&sh[0][0])[i];
+        if (c) atomicAdd(&ghist[i], c);
+    }
+}
+
 // in-place exclusive scan of each 256-bin histogram (one CTA per digit position)
 __global__ void __launch_bounds__(kRadix) hist_scan_kernel(uint32_t *ghist) {
     __shared__ uint32_t wsum[8];
@@ -816,7 +858,7 @@ int gather_word(const uint32_t *d_src, uint32_t stride, uint32_t word, const uin
 
 using namespace dbt;
 
-extern "C" size_t dbt_sort_pairs_ws_bytes(uint64_t n) { return sort_ws_bytes(n) + 256; }
+extern "C" size_t dbt_sort_pairs_ws_bytes(uint64_t n) { return sort_ws_bytes(n) + 256 + 4 * 256 * 4 + 512; } // + OR/AND words, byte histograms
 
 extern "C" int dbt_sort_pairs_u32(uint32_t *d_keys, uint32_t *d_keys_alt, uint32_t *d_vals, uint32_t *d_vals_alt,
                                   uint64_t n, int begin_bit, int end_bit, void *d_ws, size_t ws_bytes, void *stream,
@@ -828,14 +870,25 @@ extern "C" int dbt_sort_pairs_u32(uint32_t *d_keys, uint32_t *d_keys_alt, uint32
     cudaStream_t st = (cudaStream_t)stream;
     Arena ws(d_ws, ws_bytes);
     uint32_t *oa = ws.take<uint32_t>(64);
-    if (!oa) {
+    uint32_t *byte_hist = ws.take<uint32_t>(4 * kRadix);
+    if (!oa || !byte_hist) {
         set_error("dbt_sort_pairs_u32: workspace too small");
         return DBT_ERR_WORKSPACE;
     }
     uint32_t h[2] = {0, 0};
+    const bool fused = (((uintptr_t)d_keys) & 15) == 0; // one read for OR/AND and the byte histograms
     if (n) {
         StageScope sc(ST_MISC, st);
-        DBT_TRY(or_and_reduce(d_keys, n, oa, st));
+        if (fused) {
+            init_or_and_kernel<<<1, 1, 0, st>>>(oa);
+            DBT_CUDA(cudaMemsetAsync(byte_hist, 0, 4 * kRadix * 4, st));
+            const int grid = (int)std::min<uint64_t>((n / 4 + 511) / 512 + 1, 148 * 4);
+            or_and_hist_kernel<<<grid, 512, 0, st>>>(d_keys, n, oa, byte_hist);
+            count_launch(2);
+            DBT_KERNEL_CHECK();
+        } else {
+            DBT_TRY(or_and_reduce(d_keys, n, oa, st));
+        }
         DBT_CUDA(cudaMemcpyAsync(h, oa, 8, cudaMemcpyDeviceToHost, st));
         DBT_CUDA(cudaStreamSynchronize(st));
     }
@@ -843,7 +896,7 @@ extern "C" int dbt_sort_pairs_u32(uint32_t *d_keys, uint32_t *d_keys_alt, uint32
                                                  : (uint32_t)((((uint64_t)1 << (end_bit - begin_bit)) - 1) << begin_bit);
     uint32_t varying = (h[0] ^ h[1]) & range;
     uint32_t *k = d_keys, *ka = d_keys_alt, *v = d_vals, *va = d_vals_alt;
-    DBT_TRY(sort_pairs_masked(k, ka, v, va, n, varying, false, ws, st));
+    DBT_TRY(sort_pairs_masked(k, ka, v, va, n, varying, false, ws, st, (n && fused) ? byte_hist : nullptr));
     DBT_CUDA(cudaStreamSynchronize(st));
     stage_resolve();
     if (result_in_alt) *result_in_alt = (k == d_keys_alt) ? 1 : 0;
