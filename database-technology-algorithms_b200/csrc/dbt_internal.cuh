@@ -161,7 +161,16 @@ int prepare(const void *d_img, uint64_t nblocks, int field, Arena &ws, cudaStrea
             uint32_t force_kw = 0);
 // rows ordered by (key(field), recid), remaining ties in file order: the row permutation and, for one-word keys,
 // the sorted key column
-int sort_rows_by_key(KeyCols &k, int field, Arena &ws, cudaStream_t st, uint32_t **perm_out, uint32_t **sorted_w0_out);
+// compact != nullptr (single-relation callers only): a str / num+str key with at most 64 varying bits is sorted as the
+// concatenation of those bits; *compact then describes that key (n != 0; w0 = its most significant word, str = the
+// second word with kw = 1 when it needs two) and equal compact keys mean equal keys, so the caller's unique scan can
+// run on it -- with the returned sorted column (field '1' semantics) when it is one word, through the view
+// (field '3' semantics) when it is two.
+int sort_rows_by_key(KeyCols &k, int field, Arena &ws, cudaStream_t st, uint32_t **perm_out, uint32_t **sorted_w0_out,
+                     KeyCols *compact = nullptr);
+// first row of every group of equal keys in sorted order, using the compact key when sort_rows_by_key made one
+int unique_sorted(const KeyCols &k, const KeyCols &compact, int field, const uint32_t *d_perm, const uint32_t *d_sorted_w0,
+                  uint64_t n, uint32_t *d_uperm, uint64_t *d_count, Arena &ws, cudaStream_t st);
 
 // joins (kernels_join.cu)
 size_t hash_table_slots(uint64_t nr);

@@ -70,12 +70,75 @@ int prepare(const void *d_img, uint64_t nblocks, int field, Arena &ws, cudaStrea
     return 0;
 }
 
+// ---- order-preserving key compaction --------------------------------------------------------------
+// Bits that are constant over the whole relation cannot decide a comparison, so a multi-word key (str, num+str)
+// is equivalent, for ordering and for equality WITHIN the relation, to the concatenation of its varying bits,
+// most significant first.  Reference-like strings (5 letters) carry 31 varying bits in their 32 key bytes: one
+// u32 instead of a multi-word LSD with a random word gather per extra word.  Used when at most 64 bits vary.
+struct CompactPlan {
+    uint32_t nruns;
+    uint8_t word[64];  // 255 = w0, else the index of the str word
+    uint8_t shift[64]; // lowest bit of the run inside its word
+    uint8_t width[64]; // 1..32
+    uint8_t out[64];   // lowest bit of the run inside the 64-bit compact key
+};
+__global__ void __launch_bounds__(256)
+compact_keys_kernel(const uint32_t *__restrict__ w0, const uint32_t *__restrict__ str, uint32_t kw, uint64_t n, CompactPlan p,
+                    uint32_t *__restrict__ lo, uint32_t *__restrict__ hi) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        unsigned long long key = 0;
+        for (uint32_t r = 0; r < p.nruns; ++r) {
+            const uint32_t w = (p.word[r] == 255) ? w0[i] : str[i * kw + p.word[r]];
+            const uint32_t m = (p.width[r] >= 32) ? 0xFFFFFFFFu : ((1u << p.width[r]) - 1u);
+            key |= (unsigned long long)((w >> p.shift[r]) & m) << p.out[r];
+        }
+        lo[i] = (uint32_t)key;
+        if (hi) hi[i] = (uint32_t)(key >> 32);
+    }
+}
+// Plan the runs for field '2' (str words) or '3' (w0 then str words); returns the number of varying bits (0 = do not compact).
+static int plan_compaction(const KeyCols &k, int field, CompactPlan *p) {
+    memset(p, 0, sizeof *p);
+    struct Src {
+        uint8_t word;
+        uint32_t mask;
+    };
+    std::vector<Src> srcs; // most significant first
+    if (field == '3' && k.w0) srcs.push_back({255, k.vary_w0});
+    for (uint32_t j = 0; j < k.kw && j < 30; ++j) srcs.push_back({(uint8_t)j, k.vary_str[j]});
+    int total = 0;
+    for (const Src &s : srcs) total += __builtin_popcount(s.mask);
+    if (total == 0 || total > 64) return 0;
+    int out = total;
+    for (const Src &s : srcs) {
+        uint32_t m = s.mask;
+        while (m) { // runs of consecutive varying bits, from the top
+            const int hi = 31 - __builtin_clz(m);
+            int lo = hi;
+            while (lo > 0 && ((m >> (lo - 1)) & 1u)) --lo;
+            const int width = hi - lo + 1;
+            if (p->nruns >= 64) return 0;
+            out -= width;
+            p->word[p->nruns] = s.word;
+            p->shift[p->nruns] = (uint8_t)lo;
+            p->width[p->nruns] = (uint8_t)width;
+            p->out[p->nruns] = (uint8_t)out;
+            ++p->nruns;
+            m &= (lo == 0) ? 0u : ((1u << lo) - 1u);
+        }
+    }
+    return total;
+}
+
 // Order the rows by (key(field), recid); ties beyond that keep file order (LSD passes are stable).
 // Returns the row permutation and, for 1-word keys, the sorted key column.
-int sort_rows_by_key(KeyCols &k, int field, Arena &ws, cudaStream_t st, uint32_t **perm_out, uint32_t **sorted_w0_out) {
+int sort_rows_by_key(KeyCols &k, int field, Arena &ws, cudaStream_t st, uint32_t **perm_out, uint32_t **sorted_w0_out,
+                     KeyCols *compact) {
     const uint64_t n = k.n;
     *perm_out = nullptr;
     *sorted_w0_out = nullptr;
+    if (compact) memset(compact, 0, sizeof *compact);
     if (n == 0) return 0;
     struct Word {
         const uint32_t *src;
@@ -83,18 +146,47 @@ int sort_rows_by_key(KeyCols &k, int field, Arena &ws, cudaStream_t st, uint32_t
     };
     std::vector<Word> words; // least significant first
     if (field != '0' && k.recid_unsorted && k.vary_recid) words.push_back({k.recid, 1, 0, k.vary_recid});
-    if (field >= '2')
+    // single-relation callers (sort, dedup): a multi-word key whose varying bits fit 64 bits is sorted as those bits
+    uint32_t *ck_lo = nullptr, *ck_hi = nullptr;
+    int cbits = 0;
+    if (compact && field >= '2' && getenv("DBT_NO_KEY_COMPACTION") == nullptr) {
+        CompactPlan plan;
+        cbits = plan_compaction(k, field, &plan);
+        if (cbits) {
+            ck_lo = ws.take<uint32_t>(n);
+            ck_hi = cbits > 32 ? ws.take<uint32_t>(n) : nullptr;
+            if (!ck_lo || (cbits > 32 && !ck_hi)) {
+                set_error("sort: workspace too small");
+                return DBT_ERR_WORKSPACE;
+            }
+            StageScope sc(ST_WORD_GATHER, st);
+            const int grid = (int)std::min<uint64_t>((n + 255) / 256, 148 * 16);
+            compact_keys_kernel<<<grid, 256, 0, st>>>(field == '3' ? k.w0 : nullptr, k.str, k.kw, n, plan, ck_lo, ck_hi);
+            count_launch();
+            DBT_KERNEL_CHECK();
+            const int lo_bits = std::min(cbits, 32);
+            words.push_back({ck_lo, 1, 0, lo_bits >= 32 ? 0xFFFFFFFFu : ((1u << lo_bits) - 1u)});
+            if (ck_hi) words.push_back({ck_hi, 1, 0, (cbits - 32 >= 32) ? 0xFFFFFFFFu : ((1u << (cbits - 32)) - 1u)});
+            // the view the caller's unique scan can use: equal compact keys <=> equal keys (within this relation)
+            compact->n = n;
+            compact->kw = 1;
+            compact->w0 = ck_hi ? ck_hi : ck_lo;
+            compact->str = ck_hi ? ck_lo : nullptr;
+        }
+    }
+    if (field >= '2' && !cbits)
         for (int j = (int)k.kw - 1; j >= 0; --j)
             if (k.vary_str[j]) words.push_back({k.str, k.kw, (uint32_t)j, k.vary_str[j]});
-    const bool w0_is_key = field != '2';
+    const bool w0_is_key = field != '2' && !cbits; // (field '3': num is inside the compact key)
     // field '0' with recids already ascending in file order: the file is sorted (stable) as it is
     const bool w0_sorted_already = (field == '0' && !k.recid_unsorted);
     if (w0_is_key && k.vary_w0 && !w0_sorted_already) words.push_back({k.w0, 1, 0, k.vary_w0});
 
     uint32_t *ka = nullptr, *kb = ws.take<uint32_t>(n), *va = ws.take<uint32_t>(n), *vb = ws.take<uint32_t>(n);
-    const bool single_col = (words.size() == 1 && words[0].src == k.w0); // sort the column in place (clobbers it)
+    // a single one-word key: sort the column in place (clobbers it)
+    const bool single_col = (words.size() == 1 && (words[0].src == k.w0 || words[0].src == ck_lo));
     if (!single_col) ka = ws.take<uint32_t>(n);
-    else ka = k.w0;
+    else ka = const_cast<uint32_t *>(words[0].src);
     if (!ka || !kb || !va || !vb) {
         set_error("sort: workspace too small");
         return DBT_ERR_WORKSPACE;
@@ -115,8 +207,19 @@ int sort_rows_by_key(KeyCols &k, int field, Arena &ws, cudaStream_t st, uint32_t
     if (field == '0' || field == '1') {
         if (!words.empty() && words.back().src == k.w0) *sorted_w0_out = kk;
         else *sorted_w0_out = k.w0; // constant column, or already ascending: the column is its own sorted copy
+    } else if (cbits && !ck_hi) {
+        *sorted_w0_out = kk; // the sorted one-word compact key (the last word sorted)
     }
     return 0;
+}
+
+int unique_sorted(const KeyCols &k, const KeyCols &compact, int field, const uint32_t *d_perm, const uint32_t *d_sorted_w0,
+                  uint64_t n, uint32_t *d_uperm, uint64_t *d_count, Arena &ws, cudaStream_t st) {
+    if (compact.n && !compact.str) // one-word compact key: its sorted column is at hand
+        return unique_rows(compact, '1', d_perm, d_sorted_w0, n, d_uperm, nullptr, d_count, ws, st);
+    if (compact.n) // two words: compare (hi, lo) through the row list
+        return unique_rows(compact, '3', d_perm, nullptr, n, d_uperm, nullptr, d_count, ws, st);
+    return unique_rows(k, field, d_perm, d_sorted_w0, n, d_uperm, nullptr, d_count, ws, st);
 }
 
 static int read_u64(const uint64_t *d, uint64_t *h, int count, cudaStream_t st) {
@@ -139,7 +242,7 @@ static size_t rel_bytes(uint64_t nb, int field, uint32_t kw, bool sorted) {
     b += pad256(4 * n);                              // ragged slot list
     b += 512 + pad256(4 * n);                        // stats + recid
     if (field != '2') b += pad256(4 * n);            // w0
-    if (field >= '2') b += pad256(4 * n * 8) + (kw > 8 ? pad256(4 * n * kw) : 0);
+    if (field >= '2') b += pad256(4 * n * 8) + (kw > 8 ? pad256(4 * n * kw) : 0) + (sorted ? 2 * pad256(4 * n) : 0); // + compact key words
     if (sorted) b += 4 * pad256(4 * n) + sort_ws_bytes(n) + 4096; // ping/pong keys+rows, look-back state
     return b;
 }
@@ -413,7 +516,8 @@ extern "C" int dbt_dev_mergesort(const void *d_in, uint64_t nblocks, int field, 
     Prepared p;
     DBT_TRY(prepare(d_in, nblocks, field, ws, st, &p));
     uint32_t *perm, *sorted;
-    DBT_TRY(sort_rows_by_key(p.keys, field, ws, st, &perm, &sorted));
+    KeyCols compact;
+    DBT_TRY(sort_rows_by_key(p.keys, field, ws, st, &perm, &sorted, &compact));
     DBT_TRY(gather_records(d_in, perm, p.row_slot, p.info.nrows, d_out, st));
     if (nrows) *nrows = p.info.nrows;
     return finish(st);
@@ -432,14 +536,15 @@ extern "C" int dbt_dev_dedup(const void *d_in, uint64_t nblocks, int field, void
     uint64_t u = 0;
     if (n) {
         uint32_t *perm, *sorted;
-        DBT_TRY(sort_rows_by_key(p.keys, field, ws, st, &perm, &sorted));
+        KeyCols compact;
+        DBT_TRY(sort_rows_by_key(p.keys, field, ws, st, &perm, &sorted, &compact));
         uint32_t *uperm = ws.take<uint32_t>(n);
         uint64_t *d_cnt = ws.take<uint64_t>(8);
         if (!uperm || !d_cnt) {
             set_error("dedup: workspace too small");
             return DBT_ERR_WORKSPACE;
         }
-        DBT_TRY(unique_rows(p.keys, field, perm, sorted, n, uperm, nullptr, d_cnt, ws, st));
+        DBT_TRY(unique_sorted(p.keys, compact, field, perm, sorted, n, uperm, d_cnt, ws, st));
         DBT_TRY(read_u64(d_cnt, &u, 1, st));
         DBT_TRY(gather_records(d_in, uperm, p.row_slot, u, d_out, st));
     }

@@ -318,3 +318,34 @@ def test_digit_plans_with_and_without_the_extraction_histogram(dbt, orc, shape):
         assert n == orc.count_rows(f1) and H.same_image(got, want), (shape, field, H.first_diff(got, want))
         got, n, u = H.dev_dedup(dbt, orc, f1, field)
         assert H.same_image(got, orc.dedup(f1, field)), (shape, field)
+
+
+@pytest.mark.parametrize("shape", ["one_word", "two_words", "too_wide"])
+def test_multiword_keys_sorted_through_their_varying_bits(dbt, orc, shape):
+    """str / num+str keys whose varying bits fit 32 or 64 bits are sorted (and deduplicated) as the concatenation of
+    those bits; wider keys take the word-by-word LSD.  All three must give the oracle's image."""
+    f1 = orc.gen_ref(23, 80, two=False, num_mod=7)
+    rows = f1["entries"].reshape(-1).copy()
+    n = len(rows)
+    rng = np.random.default_rng(5)
+    s = np.zeros((n, 120), dtype=np.uint8)
+    if shape == "one_word":        # 5 letters from 'a'..'d' + one "Hola"-like outlier: ~3 bits x 5 bytes
+        s[:, :5] = rng.integers(ord("a"), ord("e"), size=(n, 5), dtype=np.uint8)
+    elif shape == "two_words":     # 9 letters a..z: ~5 bits x 9 bytes = 45 bits (+ 3 of num for field '3')
+        s[:, :9] = rng.integers(ord("a"), ord("z") + 1, size=(n, 9), dtype=np.uint8)
+    else:                          # 20 letters: > 64 varying bits
+        s[:, :20] = rng.integers(ord("a"), ord("z") + 1, size=(n, 20), dtype=np.uint8)
+    s[::50, 2:] = 0                # some shorter strings: the NUL takes part in the order
+    s[1::97] = s[0]                # exact duplicates of one key
+    rows["str"] = s.view("V120").reshape(-1)
+    rows = rows[rng.permutation(n)]   # recids not in file order: the recid word is sorted below the compact key
+    f1["entries"][:] = rows.reshape(f1["entries"].shape)
+    f1["nreserved"][3] = 41
+    f1["entries"]["valid"][3, 41:] = 0
+    for field in ("2", "3"):
+        got, cnt = H.dev_sort(dbt, orc, f1, field)
+        want = orc.sort(f1, field)
+        assert cnt == orc.count_rows(f1) and H.same_image(got, want), (shape, field, H.first_diff(got, want))
+        got, cnt, u = H.dev_dedup(dbt, orc, f1, field)
+        want = orc.dedup(f1, field)
+        assert u == orc.count_rows(want) and H.same_image(got, want), (shape, field, H.first_diff(got, want))
