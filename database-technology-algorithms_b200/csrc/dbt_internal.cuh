@@ -105,6 +105,8 @@ struct KeyCols {
     const uint32_t *w0_byte_hist; // [4][256] histogram of w0's bytes made during extraction (or nullptr)
     // the raw OR / AND words behind the vary_* masks (out-of-core: combined over all runs before the global sort)
     uint32_t or_w0, and_w0, or_recid, and_recid, or_str[30], and_str[30];
+    // compact-key views made by sort_rows_by_key only: the key words in sorted order (two-word keys: both columns)
+    const uint32_t *sorted_hi, *sorted_lo;
 };
 
 // ---- launchers implemented in the .cu files --------------------------------------------------
@@ -140,6 +142,12 @@ int iota_u32(uint32_t *d, uint64_t n, cudaStream_t st);
 // unique / compaction / gather (kernels_gather.cu)
 int unique_rows(const KeyCols &k, int field, const uint32_t *d_perm, const uint32_t *d_sorted_w0, uint64_t n,
                 uint32_t *d_uperm, uint32_t *d_ukeys, uint64_t *d_count /*device u64*/, Arena &ws, cudaStream_t st);
+// two-word keys whose two columns are at hand in sorted order: first position of every group of equal (hi, lo);
+// d_upos (optional) receives the sorted position of every unique row
+int unique_rows_sorted2(const uint32_t *d_hi, const uint32_t *d_lo, const uint32_t *d_perm, uint64_t n, uint32_t *d_uperm,
+                        uint32_t *d_upos, uint64_t *d_count, Arena &ws, cudaStream_t st);
+// out[i] = {hi[pos[i]], lo[pos[i]]}
+int take_pairs(const uint32_t *d_hi, const uint32_t *d_lo, const uint32_t *d_pos, uint64_t n, uint32_t *d_out, cudaStream_t st);
 // out = values[i] (or i when values == nullptr) repeated counts[i] times, ascending i; *d_total = sum(counts)
 int compact_select(const uint32_t *d_counts, const uint32_t *d_values, uint64_t n, uint32_t *d_out, uint64_t out_cap,
                    uint64_t *d_total, Arena &ws, cudaStream_t st);
@@ -179,7 +187,9 @@ int hash_join_counts(const KeyCols &r, const KeyCols &s, int field, uint32_t *d_
 // sorted unique row lists of R and S -> per-R-unique-row 0/1 match flags, and the reference walk's read count
 int intersect_sorted(const KeyCols &r, const uint32_t *d_ur, const uint32_t *d_urkeys, uint64_t nur, const KeyCols &s,
                      const uint32_t *d_us, const uint32_t *d_uskeys, uint64_t nus, int field, uint32_t *d_flags,
-                     uint64_t *d_later_reads, Arena &ws, cudaStream_t st);
+                     uint64_t *d_later_reads, Arena &ws, cudaStream_t st, bool keys_are_contiguous = false);
+// keys_are_contiguous: multi-word keys only -- d_urkeys / d_uskeys already hold the sorted unique keys, all words of a
+// key side by side (w0 first), so the merge path reads them directly instead of collecting them through the row lists
 
 int match_ranges(const KeyCols &r, const uint32_t *d_rperm, const uint32_t *d_rsorted_w0, const KeyCols &s, int field,
                  uint32_t *d_first, uint32_t *d_count, cudaStream_t st);

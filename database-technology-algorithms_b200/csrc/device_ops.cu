@@ -209,6 +209,17 @@ int sort_rows_by_key(KeyCols &k, int field, Arena &ws, cudaStream_t st, uint32_t
         else *sorted_w0_out = k.w0; // constant column, or already ascending: the column is its own sorted copy
     } else if (cbits && !ck_hi) {
         *sorted_w0_out = kk; // the sorted one-word compact key (the last word sorted)
+        compact->sorted_lo = kk;
+    } else if (cbits) { // two words: hi is the last word sorted; bring lo into the same order (one gather)
+        uint32_t *slo = ws.take<uint32_t>(n);
+        if (!slo) {
+            set_error("sort: workspace too small");
+            return DBT_ERR_WORKSPACE;
+        }
+        StageScope sc(ST_WORD_GATHER, st);
+        DBT_TRY(gather_word(ck_lo, 1, 0, vv, slo, n, st));
+        compact->sorted_hi = kk;
+        compact->sorted_lo = slo;
     }
     return 0;
 }
@@ -217,8 +228,8 @@ int unique_sorted(const KeyCols &k, const KeyCols &compact, int field, const uin
                   uint64_t n, uint32_t *d_uperm, uint64_t *d_count, Arena &ws, cudaStream_t st) {
     if (compact.n && !compact.str) // one-word compact key: its sorted column is at hand
         return unique_rows(compact, '1', d_perm, d_sorted_w0, n, d_uperm, nullptr, d_count, ws, st);
-    if (compact.n) // two words: compare (hi, lo) through the row list
-        return unique_rows(compact, '3', d_perm, nullptr, n, d_uperm, nullptr, d_count, ws, st);
+    if (compact.n) // two words: both columns are at hand in sorted order
+        return unique_rows_sorted2(compact.sorted_hi, compact.sorted_lo, d_perm, n, d_uperm, nullptr, d_count, ws, st);
     return unique_rows(k, field, d_perm, d_sorted_w0, n, d_uperm, nullptr, d_count, ws, st);
 }
 
@@ -242,7 +253,7 @@ static size_t rel_bytes(uint64_t nb, int field, uint32_t kw, bool sorted) {
     b += pad256(4 * n);                              // ragged slot list
     b += 512 + pad256(4 * n);                        // stats + recid
     if (field != '2') b += pad256(4 * n);            // w0
-    if (field >= '2') b += pad256(4 * n * 8) + (kw > 8 ? pad256(4 * n * kw) : 0) + (sorted ? 2 * pad256(4 * n) : 0); // + compact key words
+    if (field >= '2') b += pad256(4 * n * 8) + (kw > 8 ? pad256(4 * n * kw) : 0) + (sorted ? 6 * pad256(4 * n) : 0); // + compact key words, lo in sorted order, positions, (hi, lo) pairs
     if (sorted) b += 4 * pad256(4 * n) + sort_ws_bytes(n) + 4096; // ping/pong keys+rows, look-back state
     return b;
 }
@@ -553,26 +564,33 @@ extern "C" int dbt_dev_dedup(const void *d_in, uint64_t nblocks, int field, void
     return finish(st);
 }
 
-// sort + unique of one relation; leaves the unique row list (and unique key column for 1-word keys)
-static int dedup_rel(const void *d_in, uint64_t nblocks, int field, Arena &ws, cudaStream_t st, Prepared *p,
-                     uint32_t **urows, uint32_t **ukeys, uint64_t *nu, uint32_t force_kw = 0) {
-    DBT_TRY(prepare(d_in, nblocks, field, ws, st, p, force_kw));
+// sort + unique of one prepared relation; leaves the unique row list (and the unique key column for one-word keys).
+// compact_ok: the caller has given both join sides the same (joint) vary masks, so both compact their keys with the
+// same plan and `view` (n != 0) describes keys that are comparable across the two relations.
+static int dedup_prepared(Prepared *p, int field, Arena &ws, cudaStream_t st, bool compact_ok, uint32_t **urows,
+                          uint32_t **ukeys, uint64_t *nu, KeyCols *view) {
     const uint64_t n = p->info.nrows;
     *urows = *ukeys = nullptr;
     *nu = 0;
+    memset(view, 0, sizeof *view);
     if (!n) return 0;
     uint32_t *perm, *sorted;
-    DBT_TRY(sort_rows_by_key(p->keys, field, ws, st, &perm, &sorted));
+    DBT_TRY(sort_rows_by_key(p->keys, field, ws, st, &perm, &sorted, compact_ok ? view : nullptr));
     *urows = ws.take<uint32_t>(n);
-    const bool one = (field == '0' || field == '1');
-    *ukeys = one ? ws.take<uint32_t>(n) : nullptr;
+    const bool one = (field == '0' || field == '1') || (view->n && !view->str);
+    const bool two = view->n && view->str; // two-word compact key: unique keys come out as contiguous (hi, lo) pairs
+    *ukeys = one ? ws.take<uint32_t>(n) : (two ? ws.take<uint32_t>(2 * n) : nullptr);
+    uint32_t *upos = two ? ws.take<uint32_t>(n) : nullptr;
     uint64_t *d_cnt = ws.take<uint64_t>(8);
-    if (!*urows || (one && !*ukeys) || !d_cnt) {
+    if (!*urows || ((one || two) && !*ukeys) || (two && !upos) || !d_cnt) {
         set_error("mergejoin: workspace too small");
         return DBT_ERR_WORKSPACE;
     }
-    DBT_TRY(unique_rows(p->keys, field, perm, sorted, n, *urows, *ukeys, d_cnt, ws, st));
+    if (two) DBT_TRY(unique_rows_sorted2(view->sorted_hi, view->sorted_lo, perm, n, *urows, upos, d_cnt, ws, st));
+    else if (view->n) DBT_TRY(unique_rows(*view, '1', perm, sorted, n, *urows, *ukeys, d_cnt, ws, st));
+    else DBT_TRY(unique_rows(p->keys, field, perm, sorted, n, *urows, *ukeys, d_cnt, ws, st));
     DBT_TRY(read_u64(d_cnt, nu, 1, st));
+    if (two) DBT_TRY(take_pairs(view->sorted_hi, view->sorted_lo, upos, *nu, *ukeys, st));
     return 0;
 }
 
@@ -587,12 +605,34 @@ extern "C" int dbt_dev_mergejoin(const void *d_in_r, uint64_t nbr, const void *d
     Prepared pr, ps;
     uint32_t *ur, *urk, *us, *usk;
     uint64_t nur, nus;
-    DBT_TRY(dedup_rel(d_in_r, nbr, field, ws, st, &pr, &ur, &urk, &nur));
-    DBT_TRY(dedup_rel(d_in_s, nbs, field, ws, st, &ps, &us, &usk, &nus));
-    if (field >= '2' && pr.keys.kw != ps.keys.kw && nur && nus) { // mixed key widths: redo the narrow side at full width
-        if (pr.keys.kw < ps.keys.kw) DBT_TRY(dedup_rel(d_in_r, nbr, field, ws, st, &pr, &ur, &urk, &nur, ps.keys.kw));
-        else DBT_TRY(dedup_rel(d_in_s, nbs, field, ws, st, &ps, &us, &usk, &nus, pr.keys.kw));
+    DBT_TRY(prepare(d_in_r, nbr, field, ws, st, &pr));
+    DBT_TRY(prepare(d_in_s, nbs, field, ws, st, &ps));
+    if (field >= '2' && pr.keys.kw != ps.keys.kw && pr.info.nrows && ps.info.nrows) {
+        // only one side has strings of 32+ bytes: widen the other side's keys to the full 120 bytes as well
+        if (pr.keys.kw < ps.keys.kw) DBT_TRY(prepare(d_in_r, nbr, field, ws, st, &pr, ps.keys.kw));
+        else DBT_TRY(prepare(d_in_s, nbs, field, ws, st, &ps, pr.keys.kw));
     }
+    // Key compaction across the two relations: with the vary masks of their UNION, both sides drop the same constant
+    // bits, so the compact keys keep the joint order and compare across R and S.
+    bool joint = false;
+    if (field >= '2' && pr.info.nrows && ps.info.nrows) {
+        KeyCols j = pr.keys;
+        j.vary_w0 = (pr.keys.or_w0 | ps.keys.or_w0) ^ (pr.keys.and_w0 & ps.keys.and_w0);
+        for (uint32_t w = 0; w < 30; ++w)
+            j.vary_str[w] = (w < j.kw) ? ((pr.keys.or_str[w] | ps.keys.or_str[w]) ^ (pr.keys.and_str[w] & ps.keys.and_str[w])) : 0u;
+        CompactPlan plan;
+        if (plan_compaction(j, field, &plan)) {
+            joint = true;
+            for (KeyCols *k : {&pr.keys, &ps.keys}) {
+                k->vary_w0 = j.vary_w0;
+                for (uint32_t w = 0; w < 30; ++w) k->vary_str[w] = j.vary_str[w];
+            }
+        }
+    }
+    KeyCols vr, vs;
+    DBT_TRY(dedup_prepared(&pr, field, ws, st, joint, &ur, &urk, &nur, &vr));
+    DBT_TRY(dedup_prepared(&ps, field, ws, st, joint, &us, &usk, &nus, &vs));
+    const bool cj = vr.n && vs.n; // both sides made compact keys (same plan)
     // the side files "1outfile.bin" / "2outfile.bin" (DatabaseProject.cpp:385-394)
     if (d_out_ur) DBT_TRY(gather_records(d_in_r, ur, pr.row_slot, nur, d_out_ur, st));
     if (d_out_us) DBT_TRY(gather_records(d_in_s, us, ps.row_slot, nus, d_out_us, st));
@@ -605,7 +645,8 @@ extern "C" int dbt_dev_mergejoin(const void *d_in_r, uint64_t nbr, const void *d
             set_error("mergejoin: workspace too small");
             return DBT_ERR_WORKSPACE;
         }
-        DBT_TRY(intersect_sorted(pr.keys, ur, urk, nur, ps.keys, us, usk, nus, field, flags, d_res + 1, ws, st));
+        DBT_TRY(intersect_sorted(cj ? vr : pr.keys, ur, urk, nur, cj ? vs : ps.keys, us, usk, nus,
+                                 cj ? (vr.str ? '3' : '1') : field, flags, d_res + 1, ws, st, cj && vr.str));
         DBT_TRY(compact_select(flags, ur, nur, mrows, nur, d_res, ws, st));
         uint64_t h[2];
         DBT_TRY(read_u64(d_res, h, 2, st));

@@ -322,7 +322,7 @@ int ooc_sort(HostCtx &c, const void *h_in, uint64_t nblocks, int field, void *h_
     // ---- phase 2: global order of the resident columns ----------------------------------------------
     std::vector<uint32_t> h_off(R + 1, 0);
     for (uint64_t r = 0; r < R; ++r) h_off[r + 1] = h_off[r] + (uint32_t)run_rows[r];
-    const size_t ws2 = 9 * pad256(4 * n) + sort_ws_bytes(n) + pad256(8 * (n / 2048 + 2)) + pad256(4 * C * kRpb) + (4 << 20);
+    const size_t ws2 = 10 * pad256(4 * n) + sort_ws_bytes(n) + pad256(8 * (n / 2048 + 2)) + pad256(4 * C * kRpb) + (4 << 20);
     DBT_TRY(c.ws.ensure(ws2));
     Arena ws(c.ws.p, c.ws.cap);
     uint32_t *d_off = ws.take<uint32_t>(R + 1), *d_lo = ws.take<uint32_t>(R), *d_hi = ws.take<uint32_t>(R),

@@ -304,6 +304,60 @@ struct EmitPerm { // out1 = the row (payload); out2 = its key from the sorted co
     __device__ uint32_t v2(uint64_t i, uint32_t) const { return sorted[i]; }
 };
 
+struct UniqueCountSorted2 { // two-word keys, both columns in sorted order; payload = the row (perm[i])
+    const uint32_t *hi, *lo, *perm;
+    __device__ void load(uint64_t i0, uint64_t n, uint32_t c[8], uint32_t pay[8]) const {
+        uint32_t h[8], l[8];
+        load8(hi, i0, n, h);
+        load8(lo, i0, n, l);
+        load8(perm, i0, n, pay);
+        uint32_t ph = (i0 > 0 && i0 < n) ? hi[i0 - 1] : 0u, pl = (i0 > 0 && i0 < n) ? lo[i0 - 1] : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            c[k] = (i0 + k < n) ? ((i0 + k == 0 || h[k] != ph || l[k] != pl) ? 1u : 0u) : 0u;
+            ph = h[k];
+            pl = l[k];
+        }
+    }
+};
+template <bool TWO>
+struct EmitPermPos { // out1 = the row (payload); out2 = its sorted position (optional)
+    static constexpr bool kTwo = TWO;
+    static constexpr bool kIndexed = false;
+    static constexpr bool kCustom = false;
+    uint32_t *out1;
+    uint32_t *out2;
+    uint64_t cap;
+    __device__ void at(uint64_t, uint64_t) const {}
+    __device__ void expand(uint64_t, uint64_t, uint32_t, uint32_t) const {}
+    __device__ uint32_t v1(uint64_t, uint32_t row) const { return row; }
+    __device__ uint32_t v2(uint64_t i, uint32_t) const { return (uint32_t)i; }
+};
+int unique_rows_sorted2(const uint32_t *d_hi, const uint32_t *d_lo, const uint32_t *d_perm, uint64_t n, uint32_t *d_uperm,
+                        uint32_t *d_upos, uint64_t *d_count, Arena &ws, cudaStream_t st) {
+    StageScope sc(ST_UNIQUE, st);
+    if (d_upos) return run_scan_emit(n, UniqueCountSorted2{d_hi, d_lo, d_perm}, EmitPermPos<true>{d_uperm, d_upos, n}, d_count, ws, st);
+    return run_scan_emit(n, UniqueCountSorted2{d_hi, d_lo, d_perm}, EmitPermPos<false>{d_uperm, nullptr, n}, d_count, ws, st);
+}
+__global__ void __launch_bounds__(256)
+take_pairs_kernel(const uint32_t *__restrict__ hi, const uint32_t *__restrict__ lo, const uint32_t *__restrict__ pos, uint64_t n,
+                  uint2 *__restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t q = pos[i];
+        out[i] = make_uint2(hi[q], lo[q]);
+    }
+}
+int take_pairs(const uint32_t *d_hi, const uint32_t *d_lo, const uint32_t *d_pos, uint64_t n, uint32_t *d_out, cudaStream_t st) {
+    if (!n) return 0;
+    StageScope sc(ST_UNIQUE, st);
+    const int grid = (int)std::min<uint64_t>((n + 255) / 256, 148 * 16);
+    take_pairs_kernel<<<grid, 256, 0, st>>>(d_hi, d_lo, d_pos, n, (uint2 *)d_out);
+    count_launch();
+    DBT_KERNEL_CHECK();
+    return 0;
+}
+
 int unique_rows(const KeyCols &k, int field, const uint32_t *d_perm, const uint32_t *d_sorted_w0, uint64_t n,
                 uint32_t *d_uperm, uint32_t *d_ukeys, uint64_t *d_count, Arena &ws, cudaStream_t st) {
     StageScope sc(ST_UNIQUE, st);

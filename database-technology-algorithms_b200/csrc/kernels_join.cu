@@ -530,7 +530,7 @@ int match_ranges(const KeyCols &r, const uint32_t *d_rperm, const uint32_t *d_rs
 
 int intersect_sorted(const KeyCols &r, const uint32_t *d_ur, const uint32_t *d_urkeys, uint64_t nur, const KeyCols &s,
                      const uint32_t *d_us, const uint32_t *d_uskeys, uint64_t nus, int field, uint32_t *d_flags,
-                     uint64_t *d_later_reads, Arena &ws, cudaStream_t st) {
+                     uint64_t *d_later_reads, Arena &ws, cudaStream_t st, bool keys_are_contiguous) {
     StageScope sc(ST_INTERSECT, st);
     const bool one = (field == '0' || field == '1');
     SortedList a{one ? d_urkeys : nullptr, d_ur, KeyView{field == '2' ? nullptr : r.w0, r.str, r.kw}, nur};
@@ -542,7 +542,7 @@ int intersect_sorted(const KeyCols &r, const uint32_t *d_ur, const uint32_t *d_u
         const uint32_t *A = d_urkeys, *B = d_uskeys;
         size_t m0 = ws.mark();
         bool ok = true;
-        if (!one) { // multi-word keys: make the two sorted key lists contiguous first (one random 32-byte read per key)
+        if (!one && !keys_are_contiguous) { // multi-word keys: make the two sorted key lists contiguous first (one random 32-byte read per key)
             uint32_t *ca = ws.take<uint32_t>(nur * kwt), *cb = ws.take<uint32_t>(nus * kwt);
             if (!ca || !cb) ok = false;
             else {
