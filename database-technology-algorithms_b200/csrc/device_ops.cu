@@ -131,6 +131,24 @@ static int plan_compaction(const KeyCols &k, int field, CompactPlan *p) {
     return total;
 }
 
+// vary masks of the union of two relations (join sides), and the compaction plan they give (0 = do not compact)
+static int joint_compaction(const KeyCols &a, const KeyCols &b, int field, CompactPlan *plan, KeyCols *masks) {
+    *masks = a;
+    masks->vary_w0 = (a.or_w0 | b.or_w0) ^ (a.and_w0 & b.and_w0);
+    for (uint32_t w = 0; w < 30; ++w)
+        masks->vary_str[w] = (w < a.kw) ? ((a.or_str[w] | b.or_str[w]) ^ (a.and_str[w] & b.and_str[w])) : 0u;
+    if (getenv("DBT_NO_KEY_COMPACTION") != nullptr) return 0;
+    return plan_compaction(*masks, field, plan);
+}
+static int launch_compaction(const KeyCols &k, int field, const CompactPlan &plan, uint32_t *lo, uint32_t *hi, cudaStream_t st) {
+    StageScope sc(ST_WORD_GATHER, st);
+    const int grid = (int)std::min<uint64_t>((k.n + 255) / 256, 148 * 16);
+    compact_keys_kernel<<<grid, 256, 0, st>>>(field == '3' ? k.w0 : nullptr, k.str, k.kw, k.n, plan, lo, hi);
+    count_launch();
+    DBT_KERNEL_CHECK();
+    return 0;
+}
+
 // Order the rows by (key(field), recid); ties beyond that keep file order (LSD passes are stable).
 // Returns the row permutation and, for 1-word keys, the sorted key column.
 int sort_rows_by_key(KeyCols &k, int field, Arena &ws, cudaStream_t st, uint32_t **perm_out, uint32_t **sorted_w0_out,
@@ -159,11 +177,7 @@ int sort_rows_by_key(KeyCols &k, int field, Arena &ws, cudaStream_t st, uint32_t
                 set_error("sort: workspace too small");
                 return DBT_ERR_WORKSPACE;
             }
-            StageScope sc(ST_WORD_GATHER, st);
-            const int grid = (int)std::min<uint64_t>((n + 255) / 256, 148 * 16);
-            compact_keys_kernel<<<grid, 256, 0, st>>>(field == '3' ? k.w0 : nullptr, k.str, k.kw, n, plan, ck_lo, ck_hi);
-            count_launch();
-            DBT_KERNEL_CHECK();
+            DBT_TRY(launch_compaction(k, field, plan, ck_lo, ck_hi, st));
             const int lo_bits = std::min(cbits, 32);
             words.push_back({ck_lo, 1, 0, lo_bits >= 32 ? 0xFFFFFFFFu : ((1u << lo_bits) - 1u)});
             if (ck_hi) words.push_back({ck_hi, 1, 0, (cbits - 32 >= 32) ? 0xFFFFFFFFu : ((1u << (cbits - 32)) - 1u)});
@@ -278,7 +292,7 @@ extern "C" size_t dbt_dev_ws_bytes_kw(int op, uint64_t nbr, uint64_t nbs, int fi
     case DBT_OP_HASHJOIN:
         b += rel_bytes(nbr, field, kw, false) + rel_bytes(nbs, field, kw, false) + 2 * pad256(4 * hash_table_slots(nr)) +
              2 * pad256(4 * ns) + scan + 4096;
-        if (field == '0' || field == '1') b += (1ull << 29) + 4096; // room for the full-range key bitmap (512 MB)
+        if (field != '3') b += (1ull << 29) + 4096 + pad256(4 * nr) + pad256(4 * ns); // the full-range key bitmap (512 MB); compact str keys
         break;
     default: return 0;
     }
@@ -616,12 +630,9 @@ extern "C" int dbt_dev_mergejoin(const void *d_in_r, uint64_t nbr, const void *d
     // bits, so the compact keys keep the joint order and compare across R and S.
     bool joint = false;
     if (field >= '2' && pr.info.nrows && ps.info.nrows) {
-        KeyCols j = pr.keys;
-        j.vary_w0 = (pr.keys.or_w0 | ps.keys.or_w0) ^ (pr.keys.and_w0 & ps.keys.and_w0);
-        for (uint32_t w = 0; w < 30; ++w)
-            j.vary_str[w] = (w < j.kw) ? ((pr.keys.or_str[w] | ps.keys.or_str[w]) ^ (pr.keys.and_str[w] & ps.keys.and_str[w])) : 0u;
+        KeyCols j;
         CompactPlan plan;
-        if (plan_compaction(j, field, &plan)) {
+        if (joint_compaction(pr.keys, ps.keys, field, &plan, &j)) {
             joint = true;
             for (KeyCols *k : {&pr.keys, &ps.keys}) {
                 k->vary_w0 = j.vary_w0;
@@ -772,7 +783,26 @@ extern "C" int dbt_dev_hashjoin(const void *d_in_r, uint64_t nbr, const void *d_
             return DBT_ERR_WORKSPACE;
         }
         uint64_t rows_cap = std::max<uint64_t>(std::min<uint64_t>(cap, (field == '3') ? cap : ns), 1);
-        DBT_TRY(hash_join_counts(pr.keys, ps.keys, field, counts, ws, st));
+        // str keys whose varying bits (over R and S together) fit one word are joined as that word: the set-semantics
+        // u32 paths (direct-address bitmap, sliced bitmap, u32 table) replace the 32-byte-key hash table
+        KeyCols rk = pr.keys, sk = ps.keys;
+        int jf = field;
+        if (field == '2') {
+            KeyCols j;
+            CompactPlan plan;
+            const int bits = joint_compaction(pr.keys, ps.keys, field, &plan, &j);
+            if (bits && bits <= 32) {
+                uint32_t *lo_r = ws.take<uint32_t>(pr.info.nrows), *lo_s = ws.take<uint32_t>(ns);
+                if (lo_r && lo_s) {
+                    DBT_TRY(launch_compaction(pr.keys, field, plan, lo_r, nullptr, st));
+                    DBT_TRY(launch_compaction(ps.keys, field, plan, lo_s, nullptr, st));
+                    rk.w0 = lo_r;
+                    sk.w0 = lo_s;
+                    jf = '1';
+                }
+            }
+        }
+        DBT_TRY(hash_join_counts(rk, sk, jf, counts, ws, st));
         DBT_TRY(compact_select(counts, nullptr, ns, rows, rows_cap, d_total, ws, st));
         uint64_t total = 0;
         DBT_TRY(read_u64(d_total, &total, 1, st));
