@@ -224,17 +224,23 @@ int sort_rows_by_key(KeyCols &k, int field, Arena &ws, cudaStream_t st, uint32_t
     } else if (cbits && !ck_hi) {
         *sorted_w0_out = kk; // the sorted one-word compact key (the last word sorted)
         compact->sorted_lo = kk;
-    } else if (cbits) { // two words: hi is the last word sorted; bring lo into the same order (one gather)
-        uint32_t *slo = ws.take<uint32_t>(n);
-        if (!slo) {
-            set_error("sort: workspace too small");
-            return DBT_ERR_WORKSPACE;
-        }
-        StageScope sc(ST_WORD_GATHER, st);
-        DBT_TRY(gather_word(ck_lo, 1, 0, vv, slo, n, st));
+    } else if (cbits) { // two words: hi is the last word sorted; lo follows on demand (sorted_low_word)
         compact->sorted_hi = kk;
-        compact->sorted_lo = slo;
     }
+    return 0;
+}
+
+// two-word compact keys: bring the low word into sorted order (one gather through the permutation) for the scans
+static int sorted_low_word(KeyCols &view, const uint32_t *d_perm, Arena &ws, cudaStream_t st) {
+    if (!view.n || !view.str || view.sorted_lo) return 0;
+    uint32_t *slo = ws.take<uint32_t>(view.n);
+    if (!slo) {
+        set_error("sort: workspace too small");
+        return DBT_ERR_WORKSPACE;
+    }
+    StageScope sc(ST_WORD_GATHER, st);
+    DBT_TRY(gather_word(view.str, 1, 0, d_perm, slo, view.n, st));
+    view.sorted_lo = slo;
     return 0;
 }
 
@@ -242,8 +248,11 @@ int unique_sorted(const KeyCols &k, const KeyCols &compact, int field, const uin
                   uint64_t n, uint32_t *d_uperm, uint64_t *d_count, Arena &ws, cudaStream_t st) {
     if (compact.n && !compact.str) // one-word compact key: its sorted column is at hand
         return unique_rows(compact, '1', d_perm, d_sorted_w0, n, d_uperm, nullptr, d_count, ws, st);
-    if (compact.n) // two words: both columns are at hand in sorted order
-        return unique_rows_sorted2(compact.sorted_hi, compact.sorted_lo, d_perm, n, d_uperm, nullptr, d_count, ws, st);
+    if (compact.n) { // two words: both columns in sorted order
+        KeyCols v = compact;
+        DBT_TRY(sorted_low_word(v, d_perm, ws, st));
+        return unique_rows_sorted2(v.sorted_hi, v.sorted_lo, d_perm, n, d_uperm, nullptr, d_count, ws, st);
+    }
     return unique_rows(k, field, d_perm, d_sorted_w0, n, d_uperm, nullptr, d_count, ws, st);
 }
 
@@ -600,7 +609,10 @@ static int dedup_prepared(Prepared *p, int field, Arena &ws, cudaStream_t st, bo
         set_error("mergejoin: workspace too small");
         return DBT_ERR_WORKSPACE;
     }
-    if (two) DBT_TRY(unique_rows_sorted2(view->sorted_hi, view->sorted_lo, perm, n, *urows, upos, d_cnt, ws, st));
+    if (two) {
+        DBT_TRY(sorted_low_word(*view, perm, ws, st));
+        DBT_TRY(unique_rows_sorted2(view->sorted_hi, view->sorted_lo, perm, n, *urows, upos, d_cnt, ws, st));
+    }
     else if (view->n) DBT_TRY(unique_rows(*view, '1', perm, sorted, n, *urows, *ukeys, d_cnt, ws, st));
     else DBT_TRY(unique_rows(p->keys, field, perm, sorted, n, *urows, *ukeys, d_cnt, ws, st));
     DBT_TRY(read_u64(d_cnt, nu, 1, st));

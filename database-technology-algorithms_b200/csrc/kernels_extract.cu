@@ -269,6 +269,12 @@ extract_stream_kernel(const uint32_t *__restrict__ img, uint64_t nblocks, uint64
     }
     __syncthreads();
     uint32_t o_w0 = 0, a_w0 = 0xFFFFFFFFu, o_id = 0, a_id = 0xFFFFFFFFu, unsorted = 0, overflow = 0;
+    uint32_t o_s[HAS_STR ? 8 : 1], a_s[HAS_STR ? 8 : 1]; // kw == 8: per-thread OR/AND of the key words
+#pragma unroll
+    for (int j = 0; j < (HAS_STR ? 8 : 1); ++j) {
+        o_s[j] = 0;
+        a_s[j] = 0xFFFFFFFFu;
+    }
     for (uint64_t k = 0; k < my_blocks; ++k) {
         if (tid == 0 && k + kExStages - 1 < my_blocks) issue(k + kExStages - 1);
         const int sidx = (int)(k % kExStages);
@@ -310,7 +316,25 @@ extract_stream_kernel(const uint32_t *__restrict__ img, uint64_t nblocks, uint64
             }
             unsorted |= recid < prev;
         }
-        if (HAS_STR) { // whole warps take part: the per-word OR/AND go through warp reductions
+        if (HAS_STR && kw == 8) {
+            // the common width: the row's eight key words are built in registers and leave as two 16-byte stores (a warp
+            // writes 1 KB contiguous in two instructions instead of eight strided 4-byte stores); OR/AND stay in
+            // registers until the CTA has seen all of its blocks
+            if (live) {
+                bool ended = false;
+                uint32_t w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    w[j] = norm_word(rec[kStrWord + j], ended);
+                    o_s[j] |= w[j];
+                    a_s[j] &= w[j];
+                }
+                uint4 *dst = reinterpret_cast<uint4 *>(out_str + row * 8);
+                dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                overflow |= !ended;
+            }
+        } else if (HAS_STR) { // whole warps take part: the per-word OR/AND go through warp reductions
             bool ended = false;
             uint32_t *dst = out_str + row * kw;
             for (uint32_t j = 0; j < kw; ++j) {
@@ -336,6 +360,17 @@ extract_stream_kernel(const uint32_t *__restrict__ img, uint64_t nblocks, uint64
     a_id = __reduce_and_sync(0xFFFFFFFFu, a_id);
     unsorted = __reduce_or_sync(0xFFFFFFFFu, unsorted);
     overflow = __reduce_or_sync(0xFFFFFFFFu, overflow);
+    if (HAS_STR && kw == 8) {
+#pragma unroll
+        for (int j = 0; j < (HAS_STR ? 8 : 1); ++j) {
+            const uint32_t so = __reduce_or_sync(0xFFFFFFFFu, o_s[j]);
+            const uint32_t sa = __reduce_and_sync(0xFFFFFFFFu, a_s[j]);
+            if (lane == 0) {
+                atomicOr(&s_or[2 + j], so);
+                atomicAnd(&s_and[2 + j], sa);
+            }
+        }
+    }
     if (lane == 0) {
         atomicOr(&s_or[0], o_w0);
         atomicAnd(&s_and[0], a_w0);
