@@ -7,7 +7,7 @@ plumbing for device memory and streams.  There is no CPU fallback: if the shared
 missing, or no CUDA device is visible, every operator raises.
 
 Import with ``importlib.import_module("database-technology-algorithms_b200")`` (the directory
-name carries a hyphen) or through the ``dbt_b200`` alias module at the repo root.
+name carries a hyphen).
 """
 from __future__ import annotations
 

@@ -182,6 +182,12 @@ int unique_sorted(const KeyCols &k, const KeyCols &compact, int field, const uin
 
 // joins (kernels_join.cu)
 size_t hash_table_slots(uint64_t nr);
+int build_key_bitmap(const uint32_t *d_keys, uint64_t n, Arena &ws, cudaStream_t st, uint32_t **bm, uint32_t *base,
+                     uint32_t *span);
+// one streaming pass over the S image (kernels_semijoin.cu): matching records go straight to the packed output image;
+// d_total: 16 bytes on the device {u64 matches, u32 look-back error flag}
+int semijoin_stream(const void *d_s_img, uint64_t nblocks_s, int field, const uint32_t *d_bitmap, uint32_t base, uint32_t span,
+                    void *d_out, uint64_t cap_rows, uint64_t *d_total, Arena &ws, cudaStream_t st);
 int hash_join_counts(const KeyCols &r, const KeyCols &s, int field, uint32_t *d_counts /*[s.n]*/, Arena &ws,
                      cudaStream_t st);
 // sorted unique row lists of R and S -> per-R-unique-row 0/1 match flags, and the reference walk's read count

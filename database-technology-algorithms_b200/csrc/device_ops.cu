@@ -32,7 +32,7 @@ int prepare(const void *d_img, uint64_t nblocks, int field, Arena &ws, cudaStrea
     k.str = has_str ? ws.take<uint32_t>(n * k.kw) : nullptr;
     if (!d_stats || !k.recid || (has_w0 && !k.w0) || (has_str && !k.str)) {
         set_error("prepare: workspace too small");
-        return DBT_ERR_WORKSPACE;
+        return (has_str && k.kw > 8) ? DBT_ERR_NEED_WIDE_KEYS : DBT_ERR_WORKSPACE;
     }
     ExtractStats h;
     uint32_t *d_byte_hist = has_w0 && !has_str ? ws.take<uint32_t>(4 * 256) : nullptr;
@@ -48,7 +48,7 @@ int prepare(const void *d_img, uint64_t nblocks, int field, Arena &ws, cudaStrea
         k.str = ws.take<uint32_t>(n * k.kw);
         if (!k.str) {
             set_error("prepare: workspace too small for 120-byte string keys (size it with dbt_dev_ws_bytes_kw(..., 30))");
-            return DBT_ERR_WORKSPACE;
+            return DBT_ERR_NEED_WIDE_KEYS;
         }
         DBT_TRY(extract_keys(d_img, nblocks, n, out->row_slot, out->info.blk_nres, out->info.blk_row_off, field, k.kw, k.w0, k.str,
                          k.recid, d_stats, st));
@@ -256,6 +256,28 @@ int unique_sorted(const KeyCols &k, const KeyCols &compact, int field, const uin
     return unique_rows(k, field, d_perm, d_sorted_w0, n, d_uperm, nullptr, d_count, ws, st);
 }
 
+// Both sides of a join: prepare R and S; when only one side has strings of 32+ bytes, the other side's keys are
+// widened to the full 120 bytes as well -- its first (8-word) columns are released before it is prepared again.
+static int prepare_pair(const void *d_r, uint64_t nbr, const void *d_s, uint64_t nbs, int field, Arena &ws, cudaStream_t st,
+                        Prepared *pr, Prepared *ps) {
+    const size_t m0 = ws.mark();
+    DBT_TRY(prepare(d_r, nbr, field, ws, st, pr));
+    const size_t m1 = ws.mark();
+    DBT_TRY(prepare(d_s, nbs, field, ws, st, ps));
+    if (field >= '2' && pr->keys.kw != ps->keys.kw && pr->info.nrows && ps->info.nrows) {
+        const uint32_t kw = std::max(pr->keys.kw, ps->keys.kw);
+        if (ps->keys.kw < kw) { // S is the narrow side: it was prepared last, redo it in place
+            ws.release(m1);
+            DBT_TRY(prepare(d_s, nbs, field, ws, st, ps, kw));
+        } else { // R is the narrow side: redo both, wide from the start
+            ws.release(m0);
+            DBT_TRY(prepare(d_r, nbr, field, ws, st, pr, kw));
+            DBT_TRY(prepare(d_s, nbs, field, ws, st, ps, kw));
+        }
+    }
+    return 0;
+}
+
 static int read_u64(const uint64_t *d, uint64_t *h, int count, cudaStream_t st) {
     DBT_CUDA(cudaMemcpyAsync(h, d, 8 * count, cudaMemcpyDeviceToHost, st));
     DBT_CUDA(cudaStreamSynchronize(st));
@@ -306,6 +328,11 @@ extern "C" size_t dbt_dev_ws_bytes_kw(int op, uint64_t nbr, uint64_t nbs, int fi
     default: return 0;
     }
     return b + b / 16;
+}
+extern "C" size_t dbt_dev_hashjoin_ws_bytes(uint64_t nbr, uint64_t nbs, int field, uint32_t kw, uint64_t out_capacity_blocks) {
+    size_t b = dbt_dev_ws_bytes_kw(DBT_OP_HASHJOIN, nbr, nbs, field, kw);
+    if (field == '3' && out_capacity_blocks > nbs) b += pad256(4 * (out_capacity_blocks - nbs) * kRpb) + 4096; // the emitted-row list
+    return b;
 }
 extern "C" size_t dbt_dev_ws_bytes(int op, uint64_t nbr, uint64_t nbs, int field) {
     return dbt_dev_ws_bytes_kw(op, nbr, nbs, field, 8);
@@ -631,13 +658,7 @@ extern "C" int dbt_dev_mergejoin(const void *d_in_r, uint64_t nbr, const void *d
     Prepared pr, ps;
     uint32_t *ur, *urk, *us, *usk;
     uint64_t nur, nus;
-    DBT_TRY(prepare(d_in_r, nbr, field, ws, st, &pr));
-    DBT_TRY(prepare(d_in_s, nbs, field, ws, st, &ps));
-    if (field >= '2' && pr.keys.kw != ps.keys.kw && pr.info.nrows && ps.info.nrows) {
-        // only one side has strings of 32+ bytes: widen the other side's keys to the full 120 bytes as well
-        if (pr.keys.kw < ps.keys.kw) DBT_TRY(prepare(d_in_r, nbr, field, ws, st, &pr, ps.keys.kw));
-        else DBT_TRY(prepare(d_in_s, nbs, field, ws, st, &ps, pr.keys.kw));
-    }
+    DBT_TRY(prepare_pair(d_in_r, nbr, d_in_s, nbs, field, ws, st, &pr, &ps));
     // Key compaction across the two relations: with the vary masks of their UNION, both sides drop the same constant
     // bits, so the compact keys keep the joint order and compare across R and S.
     bool joint = false;
@@ -684,6 +705,37 @@ extern "C" int dbt_dev_mergejoin(const void *d_in_r, uint64_t nbr, const void *d
     return finish(st);
 }
 
+// Fields '0'/'1' with a key bitmap at hand: the fused streaming semi-join (one read of S, no extraction, no gather).
+// *done = false when the bitmap did not fit the workspace (the caller then runs the column-based path).
+static int fused_semijoin(const uint32_t *d_rkeys, uint64_t nr, const void *d_in_s, uint64_t nbs, int field, void *d_out,
+                          uint64_t cap_blocks, Arena &ws, cudaStream_t st, uint64_t *nres, bool *done) {
+    *done = false;
+    if (getenv("DBT_JOIN_FUSED") && atoi(getenv("DBT_JOIN_FUSED")) == 0) return 0;
+    if (!nr || !nbs || nbs >= (1ull << 32)) return 0;
+    const size_t m0 = ws.mark();
+    uint32_t *bm, base, span;
+    DBT_TRY(build_key_bitmap(d_rkeys, nr, ws, st, &bm, &base, &span));
+    uint64_t *d_total = ws.take<uint64_t>(8);
+    if (!bm || !d_total) {
+        ws.release(m0);
+        return 0;
+    }
+    DBT_TRY(semijoin_stream(d_in_s, nbs, field, bm, base, span, d_out, cap_blocks * kRpb, d_total, ws, st));
+    uint64_t h[2] = {0, 0};
+    DBT_TRY(read_u64(d_total, h, 2, st));
+    *done = true;
+    *nres = h[0];
+    if ((uint32_t)h[1]) {
+        set_error("semijoin: the look-back chain timed out (internal error)");
+        return DBT_ERR_CUDA;
+    }
+    if (h[0] > cap_blocks * kRpb) {
+        set_error("hashjoin: output capacity too small (nres returned)");
+        return DBT_ERR_WORKSPACE;
+    }
+    return 0;
+}
+
 extern "C" int dbt_dev_semijoin_keys(const uint32_t *d_rkeys, uint64_t nr, const void *d_in_s, uint64_t nbs, int field,
                                      void *d_out, uint64_t out_capacity_blocks, void *d_ws, size_t ws_bytes, void *stream,
                                      uint64_t *nres) {
@@ -692,9 +744,14 @@ extern "C" int dbt_dev_semijoin_keys(const uint32_t *d_rkeys, uint64_t nr, const
     DBT_CHECK_ALIGNED(d_rkeys, d_in_s, d_out, d_ws);
     cudaStream_t st = (cudaStream_t)stream;
     Arena ws(d_ws, ws_bytes);
+    *nres = 0;
+    {
+        bool done = false;
+        DBT_TRY(fused_semijoin(d_rkeys, nr, d_in_s, nbs, field, d_out, out_capacity_blocks, ws, st, nres, &done));
+        if (done) return finish(st);
+    }
     Prepared ps;
     DBT_TRY(prepare(d_in_s, nbs, field, ws, st, &ps));
-    *nres = 0;
     const uint64_t ns = ps.info.nrows;
     if (ns && nr) {
         KeyCols rk;
@@ -734,12 +791,7 @@ extern "C" int dbt_dev_innerjoin_pairs(const void *d_in_r, uint64_t nbr, const v
     cudaStream_t st = (cudaStream_t)stream;
     Arena ws(d_ws, ws_bytes);
     Prepared pr, ps;
-    DBT_TRY(prepare(d_in_r, nbr, field, ws, st, &pr));
-    DBT_TRY(prepare(d_in_s, nbs, field, ws, st, &ps));
-    if (field >= '2' && pr.keys.kw != ps.keys.kw && pr.info.nrows && ps.info.nrows) {
-        if (pr.keys.kw < ps.keys.kw) DBT_TRY(prepare(d_in_r, nbr, field, ws, st, &pr, ps.keys.kw));
-        else DBT_TRY(prepare(d_in_s, nbs, field, ws, st, &ps, pr.keys.kw));
-    }
+    DBT_TRY(prepare_pair(d_in_r, nbr, d_in_s, nbs, field, ws, st, &pr, &ps));
     *npairs = 0;
     const uint64_t nr = pr.info.nrows, ns = ps.info.nrows;
     if (nr && ns) {
@@ -776,14 +828,16 @@ extern "C" int dbt_dev_hashjoin(const void *d_in_r, uint64_t nbr, const void *d_
     cudaStream_t st = (cudaStream_t)stream;
     Arena ws(d_ws, ws_bytes);
     Prepared pr, ps;
-    DBT_TRY(prepare(d_in_r, nbr, field, ws, st, &pr));
-    DBT_TRY(prepare(d_in_s, nbs, field, ws, st, &ps));
-    if (field >= '2' && pr.keys.kw != ps.keys.kw && pr.info.nrows && ps.info.nrows) {
-        // only one side has strings of 32+ bytes: widen the other side's keys to the full 120 bytes as well
-        if (pr.keys.kw < ps.keys.kw) DBT_TRY(prepare(d_in_r, nbr, field, ws, st, &pr, ps.keys.kw));
-        else DBT_TRY(prepare(d_in_s, nbs, field, ws, st, &ps, pr.keys.kw));
-    }
     *nres = 0;
+    if (field == '0' || field == '1') { // u32 keys: R's key column -> bitmap, then one streaming pass over S
+        const size_t m0 = ws.mark();
+        DBT_TRY(prepare(d_in_r, nbr, field, ws, st, &pr));
+        bool done = false;
+        DBT_TRY(fused_semijoin(pr.keys.w0, pr.info.nrows, d_in_s, nbs, field, d_out, out_capacity_blocks, ws, st, nres, &done));
+        if (done || !pr.info.nrows) return finish(st);
+        ws.release(m0);
+    }
+    DBT_TRY(prepare_pair(d_in_r, nbr, d_in_s, nbs, field, ws, st, &pr, &ps));
     const uint64_t ns = ps.info.nrows;
     if (ns && pr.info.nrows) {
         uint32_t *counts = ws.take<uint32_t>(ns);

@@ -43,6 +43,9 @@ struct HostCtx {
     cudaEvent_t ev[2] = {nullptr, nullptr};
     cudaEvent_t packed[2] = {nullptr, nullptr}, landed[2] = {nullptr, nullptr}; // out-of-core double buffering
     int device = -1;
+    size_t cached_device_bytes() const { // device memory this context already holds and would reuse for the next job
+        return in_r.cap + in_s.cap + out0.cap + out1.cap + out2.cap + ws.cap + cols.cap;
+    }
     int init(int dev) {
         int n = 0;
         cudaError_t e = cudaGetDeviceCount(&n);
@@ -82,7 +85,8 @@ int download(HostCtx &c, const void *d, void *h, size_t bytes, cudaStream_t on =
 inline size_t blocks_for(uint64_t rows) { return (size_t)((rows + kRpb - 1) / kRpb); }
 
 // out-of-core forms (host_ooc.cu).  chunk_blocks: the largest image that is processed in one piece.
-uint64_t ooc_chunk_blocks(int op, uint64_t nbr, uint64_t nbs, int field); // 0 = the job fits, run it in-core
+// 0 = the job fits (in the device's FREE memory plus what the context already caches), run it in-core
+uint64_t ooc_chunk_blocks(int op, uint64_t nbr, uint64_t nbs, int field, size_t cached_bytes = 0);
 int ooc_sort(HostCtx &c, const void *h_in, uint64_t nblocks, int field, void *h_out, bool dedup, uint64_t chunk_blocks,
              uint64_t *nrows, uint64_t *nunique);
 int ooc_hashjoin(HostCtx &c, const void *h_in_r, uint64_t nbr, const void *h_in_s, uint64_t nbs, int field, void *h_out,
@@ -94,12 +98,14 @@ int ooc_mergejoin(HostCtx &c, const void *h_in_r, uint64_t nbr, const void *h_in
 
 extern "C" size_t dbt_dev_ws_bytes_kw(int op, uint64_t nbr, uint64_t nbs, int field, uint32_t kw);
 
-// run `call(ws_ptr, ws_bytes)`; when it reports 120-byte string keys are needed, retry once with a larger workspace
-template <class F> static int with_workspace(dbt::HostCtx &c, int op, uint64_t nbr, uint64_t nbs, int field, F call) {
-    DBT_TRY(c.ws.ensure(dbt_dev_ws_bytes_kw(op, nbr, nbs, field, 8)));
+// run `call(ws_ptr, ws_bytes)`; when it reports that 120-byte string keys are needed, retry once with a larger workspace.
+// extra_bytes: on top of the operator's bound (HashJoin field '3' with an output larger than S)
+template <class F> static int with_workspace(dbt::HostCtx &c, int op, uint64_t nbr, uint64_t nbs, int field, F call,
+                                             size_t extra_bytes = 0) {
+    DBT_TRY(c.ws.ensure(dbt_dev_ws_bytes_kw(op, nbr, nbs, field, 8) + extra_bytes));
     int rc = call(c.ws.p, c.ws.cap);
-    if (rc == DBT_ERR_WORKSPACE && field >= '2' && strstr(dbt_last_error(), "120-byte")) {
-        DBT_TRY(c.ws.ensure(dbt_dev_ws_bytes_kw(op, nbr, nbs, field, 30)));
+    if (rc == DBT_ERR_NEED_WIDE_KEYS) {
+        DBT_TRY(c.ws.ensure(dbt_dev_ws_bytes_kw(op, nbr, nbs, field, 30) + extra_bytes));
         rc = call(c.ws.p, c.ws.cap);
     }
     return rc;

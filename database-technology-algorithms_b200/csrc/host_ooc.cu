@@ -31,7 +31,7 @@ constexpr uint32_t kMaxRuns = 2048;
 static uint64_t g_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 enum { OS_RUNS, OS_CHUNKS, OS_SHRINKS, OS_WIDENED, OS_STAGED, OS_SCHUNKS };
 
-uint64_t ooc_chunk_blocks(int op, uint64_t nbr, uint64_t nbs, int field) {
+uint64_t ooc_chunk_blocks(int op, uint64_t nbr, uint64_t nbs, int field, size_t cached_bytes) {
     uint64_t c = g_chunk_override;
     if (!c)
         if (const char *e = getenv("DBT_OOC_CHUNK_BLOCKS")) c = strtoull(e, nullptr, 10);
@@ -47,8 +47,11 @@ uint64_t ooc_chunk_blocks(int op, uint64_t nbr, uint64_t nbs, int field) {
         if (op == DBT_OP_HASHJOIN) need += img * (double)(nbr + 2 * nbs);
         else if (op == DBT_OP_MERGEJOIN) need += img * (double)(2 * nbr + 2 * nbs + std::min(nbr, nbs));
         else need += 2.0 * img * (double)nbr;
-        if (need <= 0.85 * (double)total_b) return 0;
-        c = (uint64_t)(0.12 * (double)total_b / img); // staged chunk + packed chunk + the in-core sort of one run
+        // what this job can have: the memory that is free now plus what the context already holds and will reuse
+        // (another job slot or a host framework sharing the GPU shrinks it: chunk instead of failing in cudaMalloc)
+        const double avail = std::min((double)total_b, (double)free_b + (double)cached_bytes);
+        if (need <= 0.92 * avail) return 0;
+        c = (uint64_t)(0.13 * avail / img); // staged chunk + packed chunk + the in-core sort of one run
     }
     const uint64_t big = (op == DBT_OP_HASHJOIN || op == DBT_OP_MERGEJOIN) ? std::max(nbr, nbs) : nbr;
     return big > c ? c : 0;
@@ -440,7 +443,9 @@ int ooc_hashjoin(HostCtx &c, const void *h_in_r, uint64_t nbr, const void *h_in_
     for (int attempt = 0; attempt < 2; ++attempt) {
         // ---- R: key columns, chunk by chunk ------------------------------------------------------------
         DBT_TRY(cols.layout(c.cols, nbr * kRpb, field, kw));
-        DBT_TRY(c.ws.ensure(dbt_dev_ws_bytes_kw(DBT_OP_HASHJOIN, nbr, C, field, kw))); // R's table / bitmap + one S chunk's columns
+        // one S chunk's columns + R's table (or bitmap): R's own key columns live in c.cols, not in the workspace
+        DBT_TRY(c.ws.ensure(dbt_dev_ws_bytes_kw(DBT_OP_HASHJOIN, 0, C, field, kw) + 3 * pad256(4 * hash_table_slots(nbr * kRpb)) +
+                            dbt_dev_ws_bytes_kw(DBT_OP_SORT, std::min<uint64_t>(C, nbr), 0, field, kw)));
         bool widened = false;
         g_stats[OS_RUNS] = g_stats[OS_SCHUNKS] = 0;
         for (uint64_t b = 0; b < nbr && !widened; b += C) {

@@ -128,7 +128,7 @@ static int sort_begin(int slot, const void *h_in, uint64_t nblocks, int field, v
     HostCtx *cp;
     DBT_TRY(slot_begin(slot, device, &cp));
     HostCtx &c = *cp;
-    if (const uint64_t chunk = ooc_chunk_blocks(DBT_OP_SORT, nblocks, 0, field)) { // larger than the device: runs + merge
+    if (const uint64_t chunk = ooc_chunk_blocks(DBT_OP_SORT, nblocks, 0, field, c.cached_device_bytes())) { // larger than the device: runs + merge
         uint64_t n = 0, u = 0;
         DBT_TRY(ooc_sort(c, h_in, nblocks, field, h_out, false, chunk, &n, &u));
         g_jobs[slot] = Job{true, {n, 0, 0, 0}};
@@ -151,7 +151,7 @@ static int dedup_begin(int slot, const void *h_in, uint64_t nblocks, int field, 
     HostCtx *cp;
     DBT_TRY(slot_begin(slot, device, &cp));
     HostCtx &c = *cp;
-    if (const uint64_t chunk = ooc_chunk_blocks(DBT_OP_DEDUP, nblocks, 0, field)) {
+    if (const uint64_t chunk = ooc_chunk_blocks(DBT_OP_DEDUP, nblocks, 0, field, c.cached_device_bytes())) {
         uint64_t n = 0, u = 0;
         DBT_TRY(ooc_sort(c, h_in, nblocks, field, h_out, true, chunk, &n, &u));
         g_jobs[slot] = Job{true, {n, u, 0, 0}};
@@ -175,7 +175,7 @@ static int mergejoin_begin(int slot, const void *h_in_r, uint64_t nbr, const voi
     HostCtx *cp;
     DBT_TRY(slot_begin(slot, device, &cp));
     HostCtx &c = *cp;
-    if (const uint64_t chunk = ooc_chunk_blocks(DBT_OP_MERGEJOIN, nbr, nbs, field)) { // two dedups + a streamed semi-join
+    if (const uint64_t chunk = ooc_chunk_blocks(DBT_OP_MERGEJOIN, nbr, nbs, field, c.cached_device_bytes())) { // two dedups + a streamed semi-join
         uint64_t r[4] = {0, 0, 0, 0};
         DBT_TRY(ooc_mergejoin(c, h_in_r, nbr, h_in_s, nbs, field, h_out_ur, h_out_us, h_out, chunk, r));
         g_jobs[slot] = Job{true, {r[0], r[1], r[2], r[3]}};
@@ -205,7 +205,7 @@ static int hashjoin_begin(int slot, const void *h_in_r, uint64_t nbr, const void
     HostCtx *cp;
     DBT_TRY(slot_begin(slot, device, &cp));
     HostCtx &c = *cp;
-    if (const uint64_t chunk = ooc_chunk_blocks(DBT_OP_HASHJOIN, nbr, nbs, field)) { // R's keys resident, S streams
+    if (const uint64_t chunk = ooc_chunk_blocks(DBT_OP_HASHJOIN, nbr, nbs, field, c.cached_device_bytes())) { // R's keys resident, S streams
         uint64_t n = 0;
         int rc = ooc_hashjoin(c, h_in_r, nbr, h_in_s, nbs, field, h_out, out_capacity_blocks, chunk, &n);
         if (nres_on_error) *nres_on_error = n;
@@ -220,10 +220,11 @@ static int hashjoin_begin(int slot, const void *h_in_r, uint64_t nbr, const void
     DBT_TRY(upload(c, h_in_r, c.in_r.p, br));
     DBT_TRY(upload(c, h_in_s, c.in_s.p, bs));
     uint64_t n = 0;
+    const size_t extra = dbt_dev_hashjoin_ws_bytes(nbr, nbs, field, 8, out_capacity_blocks) - dbt_dev_ws_bytes_kw(DBT_OP_HASHJOIN, nbr, nbs, field, 8);
     int rc = with_workspace(c, DBT_OP_HASHJOIN, nbr, nbs, field, [&](void *ws, size_t wb) {
         return dbt_dev_hashjoin(c.in_r.p, nbr, c.in_s.p, nbs, field, c.out0.p, out_capacity_blocks, ws, wb, c.st, &n);
-    });
-    if (nres_on_error) *nres_on_error = n; // on DBT_ERR_CAPACITY this is the size the caller must provide
+    }, extra);
+    if (nres_on_error) *nres_on_error = n; // on DBT_ERR_WORKSPACE (output capacity) this is the size the caller must provide
     DBT_TRY(rc);
     DBT_TRY(download(c, c.out0.p, h_out, blocks_for(n) * DBT_BLOCK_BYTES));
     g_jobs[slot] = Job{true, {n, 0, 0, 0}};
@@ -489,8 +490,8 @@ void write_file(const char *path, const void *h, size_t bytes) {
     close(fd);
 }
 
-template <class F> int with_ws(int op, uint64_t nbr, uint64_t nbs, int field, F call) {
-    return with_workspace(ctx(), op, nbr, nbs, field, call);
+template <class F> int with_ws(int op, uint64_t nbr, uint64_t nbs, int field, F call, size_t extra = 0) {
+    return with_workspace(ctx(), op, nbr, nbs, field, call, extra);
 }
 
 struct SortOut {
@@ -501,7 +502,7 @@ struct SortOut {
 SortOut sort_file(const char *infile, unsigned char field, unsigned nmem, const char *outpath, bool dedup, uint64_t *nunique) {
     HostCtx &c = ctx();
     const int op_id = dedup ? DBT_OP_DEDUP : DBT_OP_SORT;
-    if (const uint64_t chunk = ooc_chunk_blocks(op_id, file_blocks(infile), 0, field)) {
+    if (const uint64_t chunk = ooc_chunk_blocks(op_id, file_blocks(infile), 0, field, c.cached_device_bytes())) {
         // larger than the device: the file is sorted out of core through host memory (runs + merge, host_ooc.cu)
         const uint64_t nblocks = read_file(infile, g_files.pin[0]);
         SortOut o{};
@@ -579,7 +580,7 @@ void MergeJoin(char *infile1, char *infile2, unsigned char field, block_t *, uns
     check_nmem_or_exit(nmem_blocks);
     check_field_or_exit(field);
     HostCtx &c = ctx();
-    if (const uint64_t chunk = ooc_chunk_blocks(DBT_OP_MERGEJOIN, file_blocks(infile1), file_blocks(infile2), field)) {
+    if (const uint64_t chunk = ooc_chunk_blocks(DBT_OP_MERGEJOIN, file_blocks(infile1), file_blocks(infile2), field, c.cached_device_bytes())) {
         // larger than the device: both dedups and the intersection run out of core through host memory (host_ooc.cu)
         const uint64_t nbr = read_file(infile1, g_files.pin[0]);
         const uint64_t nbs = read_file(infile2, g_files.pin[1]);
@@ -621,10 +622,20 @@ void MergeJoin(char *infile1, char *infile2, unsigned char field, block_t *, uns
 
 void HashJoin(char *infile1, char *infile2, unsigned char field, block_t *, unsigned int nmem_blocks, char *outfile,
               unsigned int *nres, unsigned int *nios) {
-    if (nmem_blocks < 2) die("HashJoin: nmem_blocks must be >= 2");
+    if (nmem_blocks == 0) die("HashJoin: nmem_blocks must be >= 1");
+    if (nmem_blocks == 1) {
+        // the reference reads nmem_blocks-1 = 0 blocks per fread, sees an empty first block and stops at once in both
+        // phases (DatabaseProject.cpp:521-525, 564-568): one counted read per phase, no result, an empty output file
+        int fd = open(outfile, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (fd < 0) die(std::string("cannot create output file '") + outfile + "'");
+        close(fd);
+        *nres = 0;
+        *nios = 2;
+        return;
+    }
     HostCtx &c = ctx();
     if (field >= '0' && field <= '3')
-        if (const uint64_t chunk = ooc_chunk_blocks(DBT_OP_HASHJOIN, file_blocks(infile1), file_blocks(infile2), field)) {
+        if (const uint64_t chunk = ooc_chunk_blocks(DBT_OP_HASHJOIN, file_blocks(infile1), file_blocks(infile2), field, c.cached_device_bytes())) {
             // larger than the device: R's keys stay resident, S streams through in chunks (host_ooc.cu)
             const uint64_t nbr = read_file(infile1, g_files.pin[0]);
             const uint64_t nbs = read_file(infile2, g_files.pin[1]);
@@ -650,9 +661,10 @@ void HashJoin(char *infile1, char *infile2, unsigned char field, block_t *, unsi
         uint64_t cap = nbs; // fields '0'..'2' emit each S row at most once
         must(c.out0.ensure((size_t)cap * DBT_BLOCK_BYTES), "device output");
         auto run = [&](uint64_t capb) {
+            const size_t extra = dbt_dev_hashjoin_ws_bytes(nbr, nbs, field, 8, capb) - dbt_dev_ws_bytes_kw(DBT_OP_HASHJOIN, nbr, nbs, field, 8);
             return with_ws(DBT_OP_HASHJOIN, nbr, nbs, field, [&](void *ws, size_t wb) {
                 return dbt_dev_hashjoin(c.in_r.p, nbr, c.in_s.p, nbs, field, c.out0.p, capb, ws, wb, c.st, &n);
-            });
+            }, extra);
         };
         int rc = run(cap);
         if (rc == DBT_ERR_WORKSPACE && n > cap * kRpb) { // field '3' with many R duplicates: retry with the exact size

@@ -229,6 +229,36 @@ bitmap_probe_slice_kernel(const uint32_t *__restrict__ k, uint64_t n, uint32_t b
     }
 }
 
+// Direct-address bitmap of a u32 key column over [min, max] (any span: up to 512 MB for the full 32-bit range), taken
+// from the workspace.  *bm == nullptr afterwards means the workspace had no room for it (the caller falls back).
+int build_key_bitmap(const uint32_t *d_keys, uint64_t n, Arena &ws, cudaStream_t st, uint32_t **bm, uint32_t *base, uint32_t *span) {
+    *bm = nullptr;
+    *base = *span = 0;
+    if (!n) return 0;
+    uint32_t *aux = ws.take<uint32_t>(64);
+    if (!aux) return 0;
+    uint32_t h_mm[2] = {0xFFFFFFFFu, 0};
+    StageScope sc(ST_HASH_BUILD, st);
+    DBT_CUDA(cudaMemcpyAsync(aux, h_mm, 8, cudaMemcpyHostToDevice, st));
+    const int g = (int)std::min<uint64_t>((n + 255) / 256, 148 * 8);
+    minmax_kernel<<<g, 256, 0, st>>>(d_keys, n, aux);
+    count_launch();
+    DBT_CUDA(cudaMemcpyAsync(h_mm, aux, 8, cudaMemcpyDeviceToHost, st));
+    DBT_CUDA(cudaStreamSynchronize(st));
+    const uint64_t words = ((uint64_t)h_mm[1] - h_mm[0]) / 32 + 1;
+    uint32_t *b = ws.take<uint32_t>(words);
+    if (!b) return 0;
+    DBT_CUDA(cudaMemsetAsync(b, 0, words * 4, st));
+    const int gb = (int)std::min<uint64_t>((n + 255) / 256 + 1, 148 * 16);
+    bitmap_build_kernel<<<gb, 256, 0, st>>>(d_keys, n, h_mm[0], b);
+    count_launch();
+    DBT_KERNEL_CHECK();
+    *bm = b;
+    *base = h_mm[0];
+    *span = h_mm[1] - h_mm[0];
+    return 0;
+}
+
 size_t hash_table_slots(uint64_t nr) {
     uint64_t want = nr * 2 + 64, cap = 1024;
     while (cap < want) cap <<= 1;

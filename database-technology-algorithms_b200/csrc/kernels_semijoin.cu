@@ -1,0 +1,270 @@
+// kernels_semijoin.cu -- HashJoin's probe phase as ONE streaming pass over the S image (fields '0' and '1').
+//
+// The reference's probe (DatabaseProject.cpp:561-640) is itself a single pass over S: read a chunk of blocks, look
+// every record's key up in the table built from R, append the matching records to the output block, write it when it
+// is full.  The first CUDA version split that into extraction (a full read of S for 8 bytes per row), a probe over
+// the key column, a compaction and a random gather of the matching records (a second, scattered read of S).  Here S is
+// read once, sequentially:
+//
+//   persistent CTAs take S blocks in file order (dynamic block ids) and keep the NEXT block in flight with
+//   cp.async.bulk (global -> shared, mbarrier completion) while they work on the current one out of shared memory;
+//   every live row tests its key against the direct-address bitmap of keys(R) (L2-resident for reference-like key
+//   ranges); the block's match count goes into a decoupled look-back chain (64-bit tile states, the whole CTA looks
+//   back 256 predecessors per round trip) that yields the output row of the block's first match;
+//   the matching 140-byte records are copied from shared memory straight to their final place in the packed output
+//   image (consecutive matches are contiguous there, so the 4-byte stores of a warp coalesce), with the CANON block
+//   headers written by whoever emits a block's first row.
+//
+// DRAM traffic: 140 B read per S row + 140 B written per match -- the algorithmic minimum for an operator that must
+// look at every S record and emit the matching ones (the split version moved ~141 + 8 + 8 + 4 + 267 s + 140 s).
+#include "dbt_internal.cuh"
+#include <algorithm>
+#include <cstdlib>
+
+namespace dbt {
+
+constexpr int kSjThreads = 128;
+constexpr int kSjStages = 2;
+constexpr uint64_t kSjAgg = 1ull << 62, kSjInc = 2ull << 62, kSjMask = (1ull << 62) - 1;
+
+__device__ __forceinline__ uint32_t sj_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t sj_ld(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sj_st(uint64_t *p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+struct SjSmem {
+    alignas(128) uint32_t stage[kSjStages][kBlockWords];
+    alignas(8) uint64_t mbar[kSjStages];
+    uint64_t lb_sum[8];
+    uint32_t lb_inc[8], lb_ok[8];
+    uint32_t next_tile[kSjStages];
+    uint32_t src[kRpb]; // entry index (inside the S block) of the k-th match
+    uint32_t dst[kRpb]; // word offset of the k-th match's output record, relative to the first one's
+    uint32_t wcnt[kSjThreads / 32];
+};
+
+// Exclusive prefix (output rows before this tile) by decoupled look-back; the whole CTA takes part: thread t examines
+// predecessors t and t + 128 of the current window, so one round trip to L2 covers 256 tiles.  Uniform result.
+__device__ __forceinline__ uint64_t sj_lookback(SjSmem &sm, uint64_t *state, uint32_t tile, uint32_t m, uint32_t *err) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tile == 0) {
+        if (tid == 0) sj_st(&state[0], kSjInc | (uint64_t)m);
+        return 0;
+    }
+    if (tid == 0) sj_st(&state[tile], kSjAgg | (uint64_t)m);
+    uint64_t excl = 0;
+    int64_t p = (int64_t)tile - 1;
+    uint32_t spins = 0;
+    while (true) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t idx = p - (int64_t)(h * kSjThreads + tid);
+            const uint64_t sv = (idx >= 0) ? sj_ld(&state[idx]) : kSjInc;
+            const uint32_t ready = __ballot_sync(0xFFFFFFFFu, (sv >> 62) != 0);
+            const uint32_t inc = __ballot_sync(0xFFFFFFFFu, (sv & kSjInc) != 0);
+            const int first_inc = inc ? (__ffs(inc) - 1) : 32;
+            const uint32_t need = (first_inc >= 31) ? 0xFFFFFFFFu : ((2u << first_inc) - 1u);
+            uint64_t v = (lane <= first_inc) ? (sv & kSjMask) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+            if (lane == 0) {
+                const int s = h * (kSjThreads / 32) + warp; // segments in order of growing distance
+                sm.lb_sum[s] = v;
+                sm.lb_inc[s] = first_inc < 32;
+                sm.lb_ok[s] = (ready & need) == need;
+            }
+        }
+        __syncthreads();
+        uint64_t acc = 0;
+        bool found = false, fail = false;
+        int s = 0;
+        for (; s < 8; ++s) {
+            if (!sm.lb_ok[s]) {
+                fail = true;
+                break;
+            }
+            acc += sm.lb_sum[s];
+            if (sm.lb_inc[s]) {
+                found = true;
+                break;
+            }
+        }
+        __syncthreads(); // the scratch is rewritten by the next round
+        excl += acc;
+        if (found) break;
+        if (fail) { // segments before s were complete and held no inclusive prefix: keep them, poll again from s
+            p -= 32 * s;
+            if (++spins > (1u << 24)) { // a predecessor never published: report instead of hanging the device
+                if (tid == 0) atomicExch(err, 1u);
+                break;
+            }
+            continue;
+        }
+        p -= 2 * kSjThreads;
+    }
+    if (tid == 0) sj_st(&state[tile], kSjInc | (excl + (uint64_t)m));
+    return excl;
+}
+
+template <int FIELD> // 0 = recid, 1 = num
+__global__ void __launch_bounds__(kSjThreads)
+semijoin_stream_kernel(const uint32_t *__restrict__ img, uint32_t nblocks, const uint32_t *__restrict__ bm, uint32_t base,
+                       uint32_t span, uint32_t *__restrict__ out, uint64_t cap_rows, uint64_t *state /*[nblocks] zeroed*/,
+                       uint32_t *ctr /*[0] tile counter, [1] error flag; zeroed*/, unsigned long long *total_out) {
+    __shared__ SjSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    auto issue = [&](uint32_t t, int stg) { // thread 0: bulk copy of S block t into stage stg
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sj_smem_u32(&sm.mbar[stg])),
+                     "r"((uint32_t)DBT_BLOCK_BYTES)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         sj_smem_u32(sm.stage[stg])),
+                     "l"(img + (uint64_t)t * kBlockWords), "r"((uint32_t)DBT_BLOCK_BYTES), "r"(sj_smem_u32(&sm.mbar[stg]))
+                     : "memory");
+    };
+    if (tid == 0) {
+        for (int i = 0; i < kSjStages; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sj_smem_u32(&sm.mbar[i])), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t t = atomicAdd(&ctr[0], 1u);
+        sm.next_tile[0] = t;
+        if (t < nblocks) issue(t, 0);
+    }
+    __syncthreads();
+    uint32_t tile = sm.next_tile[0];
+    int stg = 0;
+    uint32_t parity = 0;
+    while (tile < nblocks) {
+        if (tid == 0) { // claim the next block now: its copy runs while this one is processed
+            const uint32_t t = atomicAdd(&ctr[0], 1u);
+            sm.next_tile[stg ^ 1] = t;
+            if (t < nblocks) issue(t, stg ^ 1);
+        }
+        uint32_t ok = 0;
+        while (!ok)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok)
+                         : "r"(sj_smem_u32(&sm.mbar[stg])), "r"((parity >> stg) & 1u)
+                         : "memory");
+        parity ^= 1u << stg;
+        const uint32_t *blk = sm.stage[stg];
+        const uint32_t nres = min(blk[1], kRpb);
+        bool match = false;
+        if (tid < (int)nres) {
+            const uint32_t key = blk[kEntriesWord + tid * kRecWords + (FIELD == 0 ? 0 : 1)];
+            const uint32_t v = key - base;
+            match = (v <= span) && ((__ldg(bm + (v >> 5)) >> (v & 31)) & 1u);
+        }
+        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, match);
+        if (lane == 0) sm.wcnt[warp] = __popc(ballot);
+        __syncthreads();
+        uint32_t wpre = 0, m = 0;
+#pragma unroll
+        for (int w = 0; w < kSjThreads / 32; ++w) {
+            const uint32_t c = sm.wcnt[w];
+            if (w < warp) wpre += c;
+            m += c;
+        }
+        if (match) sm.src[wpre + __popc(ballot & lt)] = (uint32_t)tid;
+        const uint64_t excl = sj_lookback(sm, state, tile, m, &ctr[1]); // (contains CTA barriers: sm.src is visible after it)
+        const uint64_t off0 = slot_word(excl);
+        if (tid < (int)m) {
+            const uint64_t g = excl + (uint64_t)tid;
+            const uint64_t b = g / kRpb;
+            const uint32_t e = (uint32_t)(g - b * kRpb);
+            sm.dst[tid] = (uint32_t)(b * kBlockWords + kEntriesWord + (uint64_t)e * kRecWords - off0);
+            if (e == 0 && g < cap_rows) { // first row of an output block: its header (the last block's is fixed afterwards)
+                uint32_t *ob = out + b * kBlockWords;
+                ob[0] = (uint32_t)b;
+                ob[1] = kRpb;
+                ob[kTrailerWord] = 1;
+                ob[kTrailerWord + 1] = kRpb;
+            }
+        }
+        __syncthreads();
+        const uint32_t nwords = m * kRecWords;
+        for (uint32_t idx = tid; idx < nwords; idx += kSjThreads) {
+            const uint32_t rec = idx / kRecWords, w = idx - rec * kRecWords;
+            if (excl + rec < cap_rows) out[off0 + sm.dst[rec] + w] = blk[kEntriesWord + sm.src[rec] * kRecWords + w];
+        }
+        if (tid == 0 && tile + 1 == nblocks) *total_out = excl + m;
+        __syncthreads(); // everyone is done with this stage (and with src/dst) before they are reused
+        tile = sm.next_tile[stg ^ 1];
+        stg ^= 1;
+    }
+}
+
+// the partly filled last output block: true header, unused slots zero (CANON)
+__global__ void __launch_bounds__(256)
+semijoin_finish_kernel(uint32_t *__restrict__ out, const unsigned long long *__restrict__ total, uint64_t cap_rows) {
+    const uint64_t T = *total;
+    if (T == 0 || T > cap_rows) return;
+    const uint32_t cnt = (uint32_t)(T % kRpb);
+    if (cnt == 0) return;
+    uint32_t *blk = out + (T / kRpb) * kBlockWords;
+    if (threadIdx.x == 0) {
+        blk[0] = (uint32_t)(T / kRpb);
+        blk[1] = cnt;
+        blk[kTrailerWord] = 1;
+        blk[kTrailerWord + 1] = cnt;
+    }
+    for (uint32_t i = cnt * kRecWords + threadIdx.x; i < kRpb * kRecWords; i += blockDim.x) blk[kEntriesWord + i] = 0;
+}
+
+// S rows (file order) whose key bit is set in the bitmap over [base, base + span]; *d_total receives the match count
+// (rows beyond cap_rows are counted, not written).  d_err != 0 afterwards means the look-back chain broke.
+int semijoin_stream(const void *d_s_img, uint64_t nblocks_s, int field, const uint32_t *d_bitmap, uint32_t base, uint32_t span,
+                    void *d_out, uint64_t cap_rows, uint64_t *d_total, Arena &ws, cudaStream_t st) {
+    if (nblocks_s == 0) {
+        DBT_CUDA(cudaMemsetAsync(d_total, 0, 16, st));
+        return 0;
+    }
+    if (nblocks_s >= (1ull << 32)) {
+        set_error("semijoin: S must have fewer than 2^32 blocks");
+        return DBT_ERR_UNSUPPORTED;
+    }
+    StageScope sc(ST_HASH_PROBE, st);
+    const size_t m0 = ws.mark();
+    uint64_t *state = ws.take<uint64_t>(nblocks_s);
+    uint32_t *ctr = ws.take<uint32_t>(64);
+    if (!state || !ctr) {
+        set_error("semijoin: workspace too small");
+        return DBT_ERR_WORKSPACE;
+    }
+    DBT_CUDA(cudaMemsetAsync(state, 0, nblocks_s * 8, st));
+    DBT_CUDA(cudaMemsetAsync(ctr, 0, 8, st));
+    DBT_CUDA(cudaMemsetAsync(d_total, 0, 16, st));
+    static int per_sm[2] = {0, 0};
+    const int f = field == '0' ? 0 : 1;
+    if (!per_sm[f]) {
+        int occ = 0;
+        if (f == 0) DBT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, semijoin_stream_kernel<0>, kSjThreads, 0));
+        else DBT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, semijoin_stream_kernel<1>, kSjThreads, 0));
+        if (const char *e = getenv("DBT_SEMIJOIN_CTAS")) occ = std::min(occ, atoi(e));
+        per_sm[f] = std::max(occ, 1);
+    }
+    int nsm = 148;
+    const int grid = (int)std::min<uint64_t>(nblocks_s, (uint64_t)nsm * per_sm[f]);
+    if (f == 0)
+        semijoin_stream_kernel<0><<<grid, kSjThreads, 0, st>>>((const uint32_t *)d_s_img, (uint32_t)nblocks_s, d_bitmap, base, span,
+                                                               (uint32_t *)d_out, cap_rows, state, ctr, (unsigned long long *)d_total);
+    else
+        semijoin_stream_kernel<1><<<grid, kSjThreads, 0, st>>>((const uint32_t *)d_s_img, (uint32_t)nblocks_s, d_bitmap, base, span,
+                                                               (uint32_t *)d_out, cap_rows, state, ctr, (unsigned long long *)d_total);
+    semijoin_finish_kernel<<<1, 256, 0, st>>>((uint32_t *)d_out, (const unsigned long long *)d_total, cap_rows);
+    count_launch(2);
+    DBT_KERNEL_CHECK();
+    // the error flag travels with the total: [1] of the same 16-byte result area is set by the caller's read
+    DBT_CUDA(cudaMemcpyAsync(d_total + 1, ctr + 1, 4, cudaMemcpyDeviceToDevice, st));
+    ws.release(m0);
+    return 0;
+}
+
+} // namespace dbt

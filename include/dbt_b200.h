@@ -42,7 +42,10 @@ typedef enum dbt_status {
     DBT_ERR_CUDA = -2,      /* CUDA runtime error, incl. "no device" */
     DBT_ERR_WORKSPACE = -3, /* workspace / output capacity too small */
     DBT_ERR_IO = -4,        /* file open/read/write failure */
-    DBT_ERR_UNSUPPORTED = -5
+    DBT_ERR_UNSUPPORTED = -5,
+    DBT_ERR_NEED_WIDE_KEYS = -6, /* a string has no NUL in its first 32 bytes and the workspace was sized for 8-word
+                                    keys: call again with a workspace from dbt_dev_ws_bytes_kw(..., 30) */
+    DBT_ERR_TIMEOUT = -7    /* a multi-GPU rendezvous or peer signal did not arrive in time */
 } dbt_status;
 
 const char *dbt_last_error(void);
@@ -98,8 +101,13 @@ typedef enum dbt_op { DBT_OP_SORT = 0, DBT_OP_DEDUP = 1, DBT_OP_MERGEJOIN = 2, D
 size_t dbt_dev_ws_bytes(int op, uint64_t nblocks_r, uint64_t nblocks_s, int field);
 /* same, for string keys of `kw` 32-bit words: 8 (strings shorter than 32 bytes, the default) or 30
  * (full 120-byte keys; an operator that meets a longer string with the small workspace fails with
- * DBT_ERR_WORKSPACE and a message naming this function) */
+ * DBT_ERR_NEED_WIDE_KEYS) */
 size_t dbt_dev_ws_bytes_kw(int op, uint64_t nblocks_r, uint64_t nblocks_s, int field, uint32_t kw);
+/* HashJoin whose output may be larger than S (field '3': an S row is emitted once per matching R row,
+ * DatabaseProject.cpp:616-629): the workspace for an output capacity of out_capacity_blocks blocks.  The plain
+ * bound above covers capacities up to nblocks_s. */
+size_t dbt_dev_hashjoin_ws_bytes(uint64_t nblocks_r, uint64_t nblocks_s, int field, uint32_t kw,
+                                 uint64_t out_capacity_blocks);
 
 /* MergeSort (DatabaseProject.cpp:172-381): every live row once, ordered by (key(field), recid). */
 int dbt_dev_mergesort(const void *d_in, uint64_t nblocks, int field, void *d_out, void *d_ws, size_t ws_bytes,
@@ -253,7 +261,8 @@ int dbt_host_free(void *p);
  * the reference generator main.cpp:41-77: 100 live rows per block, recid = row index, 5-letter
  * strings, "Hola" at row 1 of every block).  kind: 0 = exactly U distinct num keys over n rows,
  * 1 = uniform over [0,U), 2 = heavy-head power law over [0,U), 3 = half of the rows copy (num, str) of a random
- * row of the partner relation (kind 1, seed ^ 0x5EED) so that composite-key joins match.  Same arithmetic as
+ * row of the partner relation (kind 1, seed ^ 0x5EED) so that composite-key joins match, 4 = exact Zipf(1.1):
+ * num = rho(rank), rank ~ Zipf(s = 1.1) over [1, U] by rejection-inversion, rho a bijection of [0, U).  Same arithmetic as
  * oracle/dbt_oracle.c orc_gen_syn so any sub-range can be reproduced on the CPU.
  * ---------------------------------------------------------------------------------------------- */
 int dbt_gen_syn(uint64_t seed, uint64_t n_total, uint64_t U, int kind, uint64_t row0, uint64_t nrows, uint32_t recid0,

@@ -9,8 +9,8 @@
  * reference's four operators, each function citing the reference lines it follows.  The
  * reference as shipped ("REF") loses/duplicates a few rows; REF
  * itself is available as oracle/_ref/ref_runner (built from the untouched reference sources by
- * oracle/Makefile) and the two are pinned against each other by tests/test_oracle_vs_ref.py and
- * the committed fixtures in tests/golden/.
+ * oracle/Makefile) and the two are pinned against each other by tests/test_oracle_golden.py (frozen
+ * fixtures in tests/golden/) and tests/test_gpu_entrypoints.py (REF run live).
  *
  * Parity status: PINNED against the reference binary's behaviour (the reference has no tests or
  * golden vectors of its own).
@@ -418,8 +418,62 @@ static uint32_t bij32(uint32_t x, uint32_t seed) {
     return x;
 }
 
+/* kind 4: exact Zipf(s = 1.1) ranks over [1, U] by rejection-inversion (Hoermann & Derflinger, "Rejection-inversion to
+ * generate variates from monotone discrete distributions", 1996): H(x) = (x^(1-s) - 1)/(1-s) is the integral of the
+ * hat x^-s, a uniform u in (H(U + 1/2), H(3/2) - 1] is mapped through H^-1 and rounded to the nearest rank k, which is
+ * accepted when it is within s_cut of x or when u >= H(k + 1/2) - k^-s.  SURVEY.md 8(d) cfg 4: "S.num = rho(rank),
+ * rank ~ Zipf(s=1.1) over [1,D], rho a seeded bijection".  log and exp are spelled out with IEEE +, *, / in a fixed
+ * order (this file is compiled with -ffp-contract=off) so that the device generator, which uses the same sequence of
+ * correctly rounded operations, produces the same bits. */
+static double zbits2d(uint64_t b) { double d; memcpy(&d, &b, 8); return d; }
+static uint64_t zd2bits(double d) { uint64_t b; memcpy(&b, &d, 8); return b; }
+static double zlog(double x) {
+    uint64_t b = zd2bits(x);
+    int e = (int)((b >> 52) & 0x7FF) - 1023;
+    double m = zbits2d((b & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull);
+    if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }
+    double f = (m + -1.0) / (m + 1.0), f2 = f * f;
+    double p = 1.0 / 23.0;
+    for (int k = 21; k >= 1; k -= 2) p = p * f2 + 1.0 / (double)k;
+    return (double)e * 0.6931471805599453 + (2.0 * f) * p;
+}
+static double zexp(double y) {
+    static const double inv_fact[13] = {1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0,
+                                        1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0,
+                                        0.5, 1.0, 1.0};
+    double kf = y * 1.4426950408889634;
+    long long k = (long long)(kf < 0 ? kf + -0.5 : kf + 0.5);
+    double t1 = (double)k * 0.693147180369123816490, t2 = (double)k * 1.90821492927058770002e-10;
+    double r = (y + -t1) + -t2;
+    double p = 1.0 / 6227020800.0;
+    for (int i = 0; i < 13; ++i) p = p * r + inv_fact[i];
+    return p * zbits2d((uint64_t)(k + 1023) << 52);
+}
+#define ORC_ZIPF_S 1.1
+static double zh(double x) { return zexp(-ORC_ZIPF_S * zlog(x)); }
+static double zH(double x) { return (zexp((1.0 - ORC_ZIPF_S) * zlog(x)) + -1.0) / (1.0 - ORC_ZIPF_S); }
+static double zHinv(double u) {
+    double t = 1.0 + (1.0 - ORC_ZIPF_S) * u;
+    if (t < 1e-300) t = 1e-300;
+    return zexp(zlog(t) / (1.0 - ORC_ZIPF_S));
+}
+uint64_t orc_zipf_rank(uint64_t seed, uint64_t U, uint64_t r) {
+    double h_x1 = zH(1.5) + -1.0, h_n = zH((double)U + 0.5), s_cut = 2.0 + -zHinv(zH(2.5) + -zh(2.0));
+    for (uint64_t it = 0;; ++it) {
+        uint64_t hsh = mix64(mix64(seed * 0x100000001B3ull + r) + it * 0xD6E8FEB86659FD93ull);
+        double u01 = (double)(hsh >> 11) * 1.1102230246251565e-16;
+        double u = h_n + u01 * (h_x1 + -h_n);
+        double x = zHinv(u);
+        long long k = (long long)(x + 0.5);
+        if (k < 1) k = 1;
+        if ((uint64_t)k > U) k = (long long)U;
+        if ((double)k + -x <= s_cut || u >= zH((double)k + 0.5) + -zh((double)k) || it >= 63) return (uint64_t)k;
+    }
+}
+
 uint32_t orc_syn_num(uint64_t seed, uint64_t n, uint64_t U, int kind, uint64_t r) {
     const uint64_t A = 2654435761ull, C = 40503ull; /* A is prime > any n we use => gcd(A,n)=1 unless n multiple of A */
+    if (kind == 4) return (uint32_t)(((orc_zipf_rank(seed, U, r) - 1) * A + C) % U);
     if (kind == 0) {
         uint64_t j = (uint64_t)(((unsigned __int128)r * A + C) % n);
         return bij32((uint32_t)(j % U), (uint32_t)seed);

@@ -13,6 +13,10 @@ What is frozen (inputs are regenerated from the seed by oracle/dbt_oracle.c orc_
     for a single-merge-phase configuration (npasses = 2: REF is lossless there);
   * sort3p_f1: the same for npasses = 3, where REF loses a few rows (D1/D2): recids REF did output;
   * hjoin_f<field>: recids REF's HashJoin emitted, in its output order (S file order);
+  * hjoinm_f3: HashJoin field '3' with REAL multiplicities: a small num modulus makes the "Hola" rows of R (row 1 of
+    every block, main.cpp:57-61) share (num, str) keys, so S's "Hola" rows are emitted once per matching R row
+    (DatabaseProject.cpp:616-629).  The seed is searched so that no S row's group of emissions crosses an output-block
+    boundary: only then does REF stay inside its output block (defect D10) and its result is usable;
   * counters: nsorted_segs / npasses / nios / nunique / nres as printed by REF.
 """
 import json
@@ -49,6 +53,26 @@ def main():
         info, out, _ = orc.run_ref("hjoin", field, 64, f1, f2)
         arrays[f"hjoin_f{field}"] = orc.rows_of(out, info["a"])["recid"].copy()
         meta["counters"][f"hjoin_f{field}"] = {"nres": info["a"], "nios": info["nios"], "nmem": 64}
+    # field '3' with multiplicities, on a seed where REF does not overflow its output block (D10)
+    MULT_NB, MULT_MOD = 60, 12
+    for seed in range(1, 2000):
+        m1, m2 = orc.gen_ref(seed, MULT_NB, num_mod=MULT_MOD)
+        ids = orc.rows_of(orc.hashjoin(m1, m2, "3"))["recid"]
+        if len(ids) < 150:
+            continue
+        cuts = np.flatnonzero(np.diff(ids)) + 1                      # group starts (one group per emitting S row)
+        starts = np.concatenate([[0], cuts]); ends = np.concatenate([cuts, [len(ids)]])
+        mult = ends - starts
+        straddle = ((starts // 100) != ((ends - 1) // 100)).any()
+        if mult.max() >= 3 and not straddle:
+            break
+    else:
+        raise SystemExit("no usable seed for the multiplicity fixture")
+    info, out, _ = orc.run_ref("hjoin", "3", 64, m1, m2)
+    assert info.get("exit", 1) == 0 and info["a"] == len(ids), (info, len(ids))
+    arrays["hjoinm_f3"] = orc.rows_of(out, info["a"])["recid"].copy()
+    meta["mult"] = {"seed": seed, "nblocks": MULT_NB, "num_mod": MULT_MOD, "nres": info["a"], "nios": info["nios"], "nmem": 64,
+                    "max_multiplicity": int(mult.max()), "emitting_s_rows": int(len(mult))}
     g1 = orc.gen_ref(SEED3, NBLOCKS3, two=False)
     info, out, _ = orc.run_ref("sort", "1", NMEM3, g1)
     refc = orc.canonicalise_ties(out[out["nreserved"] > 0], "1")

@@ -153,6 +153,11 @@ def test_product_reproduces_the_reference_fixtures(dbt, orc):
         got, n = H.dev_hashjoin(dbt, orc, f1, f2, field)
         assert n == meta["counters"][f"hjoin_f{field}"]["nres"]
         assert np.array_equal(orc.rows_of(got)["recid"], arr[f"hjoin_f{field}"]), field
+    # field '3' with real multiplicities (REF fixture on a seed where REF does not overflow its output block)
+    m = meta["mult"]
+    r, s = orc.gen_ref(m["seed"], m["nblocks"], num_mod=m["num_mod"])
+    got, n = H.dev_hashjoin(dbt, orc, r, s, "3")
+    assert n == m["nres"] and np.array_equal(orc.rows_of(got)["recid"], arr["hjoinm_f3"])
 
 
 def test_host_scope_operators_with_pageable_and_pinned_buffers(dbt, orc):
@@ -313,3 +318,46 @@ def test_driver_runs_the_reference_workflow(dbt, orc, tmp_path):
     c = orc.sort_counters(200, 100)
     assert os.path.exists(tmp_path / f"segment{c['nsorted_segs']}.bin")
     assert H.same_image(read_blocks(orc, tmp_path / "NOduplicates.bin"), orc.dedup(f1, "1"))
+
+
+def test_hashjoin_field3_output_many_times_larger_than_s(dbt, orc, tmp_path, monkeypatch):
+    """Field '3' emits an S row once per matching R row (DatabaseProject.cpp:616-629): with ~10 equal (num, str) rows per
+    key in R the output is ~10x S.  The entry point retries with the exact capacity, and the workspace must grow with it."""
+    monkeypatch.chdir(tmp_path)
+    nb = 10_000                                     # 1M rows per side
+    r = orc.gen_syn(5, nb * 100, 1000, 1)           # num uniform over 1000 values
+    s = orc.gen_syn(6, nb * 100, 1000, 1)
+    for img in (r, s):                              # one string everywhere: composite key == num, ~1000 rows per key in R ...
+        e = img["entries"]
+        e["str"] = np.zeros(120, np.uint8).view("V120")[0]
+    e = r["entries"].reshape(-1).copy()
+    e["num"][100_000:] += 5000                      # ... but only R's first 100,000 rows can match: ~100 R rows per key
+    r["entries"][:] = e.reshape(r["entries"].shape)
+    e = s["entries"].reshape(-1).copy()
+    e["num"][100_000:] += 9000                      # and only S's first 100,000 rows probe them: ~10M output rows = 10 x S
+    s["entries"][:] = e.reshape(s["entries"].shape)
+    r.tofile("r.bin")
+    s.tofile("s.bin")
+    n, nios = call_join(dbt, "HashJoin", "r.bin", "s.bin", "3", 64, "out.bin")
+    rn = orc.rows_of(r)["num"][:100_000]
+    sn = orc.rows_of(s)["num"][:100_000]
+    per_key = np.bincount(rn, minlength=1000)
+    want_n = int(per_key[sn].sum())
+    assert want_n > 9 * nb * 100 and n == want_n
+    out = read_blocks(orc, "out.bin")
+    assert orc.count_rows(out) == want_n
+    got_ids = orc.rows_of(out)["recid"]
+    want_ids = np.repeat(orc.rows_of(s)["recid"][:100_000], per_key[sn])
+    assert np.array_equal(got_ids, want_ids)        # S file order, each row repeated once per matching R row
+    assert nios == orc.hashjoin_nios(nb, nb, 64, n)
+
+
+def test_hashjoin_with_one_memory_block_mirrors_the_reference(dbt, orc, workdir):
+    """nmem_blocks == 1: the reference reads 0 blocks per fread and stops at once in both phases (DatabaseProject.cpp:521-525,
+    564-568): nres = 0, two counted reads, an empty output file."""
+    n, nios = call_join(dbt, "HashJoin", "file.bin", "file2.bin", "1", 1, "oh1.bin")
+    assert (n, nios) == (0, 2) and os.path.getsize("oh1.bin") == 0
+    if orc.ref_available():
+        f1, f2 = workdir
+        info, ref_out, _ = orc.run_ref("hjoin", "1", 1, f1, f2)
+        assert info["a"] == 0 and info["nios"] == 2

@@ -176,6 +176,9 @@ def test_hashjoin_wide_key_range_and_table_fallback(dbt, orc, monkeypatch):
         e["num"] = pool[rng.integers(0, len(pool), size=e["num"].shape)]
     want = orc.hashjoin(r, s, "1")
     assert 0 < orc.count_rows(want) < orc.count_rows(s)
+    got, n = H.dev_hashjoin(dbt, orc, r, s, "1")          # fused streaming semi-join over the full-range bitmap
+    assert H.same_image(got, want), H.first_diff(got, want)
+    monkeypatch.setenv("DBT_JOIN_FUSED", "0")              # the column-based paths behind it:
     got, n = H.dev_hashjoin(dbt, orc, r, s, "1")          # sliced bitmap
     assert H.same_image(got, want), H.first_diff(got, want)
     monkeypatch.setenv("DBT_JOIN_NO_SLICES", "1")          # -> hash table (span too wide for the single bitmap)
@@ -235,7 +238,7 @@ def test_device_generator_matches_the_cpu_restatement_for_every_kind(dbt, orc):
     import torch
 
     n, U = 30000, 9000
-    for kind, seed in ((0, 42), (1, 7), (2, 9), (3, 21 ^ 0x5EED)):
+    for kind, seed in ((0, 42), (1, 7), (2, 9), (3, 21 ^ 0x5EED), (4, 9)):  # 4 = Zipf(1.1): double arithmetic, same bits
         d = H.dev_alloc(n // 100 * H.BLOCK_BYTES)
         dbt.check(dbt.lib().dbt_gen_syn(seed, n, U, kind, 0, n, 0, d.data_ptr(), H.stream()))
         torch.cuda.synchronize()
@@ -349,3 +352,83 @@ def test_multiword_keys_sorted_through_their_varying_bits(dbt, orc, shape):
         got, cnt, u = H.dev_dedup(dbt, orc, f1, field)
         want = orc.dedup(f1, field)
         assert u == orc.count_rows(want) and H.same_image(got, want), (shape, field, H.first_diff(got, want))
+
+
+def test_zipf_generator_is_zipf_and_reproducible_on_any_subrange(dbt, orc):
+    """kind 4: rank ~ Zipf(s = 1.1) over [1, U] by rejection-inversion, key = bijection(rank).  The device generator and
+    the CPU restatement must agree bit for bit on any sub-range of a large relation, and the head must carry Zipf's mass."""
+    import torch
+
+    n_total, U = 50_000_000, 100_000_000
+    for row0, nrows in ((0, 20000), (31_415_900, 20000), (n_total - 20000, 20000)):
+        d = H.dev_alloc(nrows // 100 * H.BLOCK_BYTES)
+        dbt.check(dbt.lib().dbt_gen_syn(9, n_total, U, 4, row0, nrows, 0, d.data_ptr(), H.stream()))
+        torch.cuda.synchronize()
+        got = H.to_host(d, nrows // 100, orc)
+        want = orc.gen_syn(9, n_total, U, 4, row0, nrows)
+        assert H.same_image(got, want), (row0, H.first_diff(got, want))
+    # the most frequent key of a 1M-row sample is rank 1's, with P = 1 / H_{U,1.1} = 0.111 (U = 1e8)
+    nrows = 1_000_000
+    d = H.dev_alloc(nrows // 100 * H.BLOCK_BYTES)
+    dbt.check(dbt.lib().dbt_gen_syn(9, n_total, U, 4, 0, nrows, 0, d.data_ptr(), H.stream()))
+    img = d[: nrows // 100 * H.BLOCK_BYTES].view(torch.int32).view(-1, 3504)[:, 2:3502].reshape(-1, 35)
+    num = img[:, 1].to(torch.int64) & 0xFFFFFFFF
+    vals, counts = torch.unique(num, return_counts=True)
+    top = counts.max().item() / nrows
+    assert 0.105 < top < 0.118, top
+    assert int(vals[counts.argmax()]) == (0 * 2654435761 + 40503) % U  # rho(rank 1 - 1)
+
+
+def test_fused_semijoin_edge_cases(dbt, orc, monkeypatch):
+    """Fields '0'/'1' run HashJoin's probe as one streaming pass over S: ragged S blocks (the pass reads nreserved from
+    the block it streams), results that end exactly on a block boundary, empty results, capacity errors carrying the
+    needed size, and agreement with the column-based path."""
+    r, s = orc.gen_ref(77, 240, num_mod=4000)
+    rng = np.random.default_rng(3)
+    rag = s.copy()
+    rag["nreserved"] = rng.integers(0, 101, size=len(rag)).astype(np.uint32)
+    rag["nreserved"][::7] = 0
+    rag["nreserved"][5] = 100
+    for field in "01":
+        for src in (s, rag):
+            want = orc.hashjoin(r, src, field)
+            got, n = H.dev_hashjoin(dbt, orc, r, src, field)
+            assert n == orc.count_rows(want) and H.same_image(got, want), (field, H.first_diff(got, want))
+    # exactly k * 100 matches: no partial last block to fix up
+    want = orc.hashjoin(r, s, "1")
+    k = orc.count_rows(want)
+    ids = orc.rows_of(want)["recid"]
+    cut = ids[(k // 100) * 100 - 1]            # keep S rows up to the row that completes the last full block
+    srows = s["entries"].reshape(-1)
+    keep = srows["recid"] <= cut
+    s2 = orc.new_blocks(len(s))
+    s2[:] = s
+    e2 = s2["entries"].reshape(-1).copy()
+    e2["num"][~keep] = 0xFFFFFFF0             # rows past the cut no longer match anything in R
+    s2["entries"][:] = e2.reshape(s2["entries"].shape)
+    want2 = orc.hashjoin(r, s2, "1")
+    assert orc.count_rows(want2) == (k // 100) * 100
+    got, n = H.dev_hashjoin(dbt, orc, r, s2, "1")
+    assert n == orc.count_rows(want2) and H.same_image(got, want2), H.first_diff(got, want2)
+    # nothing matches
+    e2["num"][:] = 0xFFFFFFF0
+    s2["entries"][:] = e2.reshape(s2["entries"].shape)
+    got, n = H.dev_hashjoin(dbt, orc, r, s2, "1")
+    assert n == 0 and len(got) == 0
+    # capacity too small: loud, with the needed size; the exact capacity then works
+    import ctypes as C
+    d_r, d_s = H.to_dev(r), H.to_dev(s)
+    wsb = dbt.dev_ws_bytes(dbt.OP_HASHJOIN, len(r), len(s), "1")
+    ws = H.dev_alloc(wsb)
+    d_out = H.dev_alloc(H.nb(k) * H.BLOCK_BYTES)
+    nres = C.c_uint64()
+    rc = dbt.lib().dbt_dev_hashjoin(d_r.data_ptr(), len(r), d_s.data_ptr(), len(s), ord("1"), d_out.data_ptr(), 2, ws.data_ptr(), wsb,
+                                    H.stream(), C.byref(nres))
+    assert rc == -3 and nres.value == k
+    rc = dbt.lib().dbt_dev_hashjoin(d_r.data_ptr(), len(r), d_s.data_ptr(), len(s), ord("1"), d_out.data_ptr(), H.nb(k), ws.data_ptr(),
+                                    wsb, H.stream(), C.byref(nres))
+    assert rc == 0 and H.same_image(H.to_host(d_out, H.nb(k), orc), want)
+    # the column-based path gives the same image
+    monkeypatch.setenv("DBT_JOIN_FUSED", "0")
+    got, n = H.dev_hashjoin(dbt, orc, r, rag, "0")
+    assert H.same_image(got, orc.hashjoin(r, rag, "0"))

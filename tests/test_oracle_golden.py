@@ -68,6 +68,22 @@ def test_hashjoin_equals_reference(orc, golden, inputs, field):
     assert np.array_equal(got, arr[f"hjoin_f{field}"])
 
 
+def test_hashjoin_field3_multiplicities_equal_reference(orc, golden):
+    """Field '3' with real multiplicities (R's "Hola" rows share (num, str) keys): every S row is emitted once per
+    matching R row, in S file order (DatabaseProject.cpp:541-544, 616-629).  The fixture's seed keeps REF inside its
+    output block (defect D10), so REF's output is the truth here."""
+    meta, arr = golden
+    m = meta["mult"]
+    r, s = orc.gen_ref(m["seed"], m["nblocks"], num_mod=m["num_mod"])
+    got = orc.rows_of(orc.hashjoin(r, s, "3"))["recid"]
+    assert len(got) == m["nres"] and np.array_equal(got, arr["hjoinm_f3"])
+    _, counts = np.unique(got, return_counts=True)
+    assert counts.max() == m["max_multiplicity"] >= 3 and len(counts) == m["emitting_s_rows"]
+    assert abs(orc.hashjoin_nios(m["nblocks"], m["nblocks"], m["nmem"], m["nres"]) - m["nios"]) <= 1
+    # SURVEY 8c: the pair-producing extension must agree with REF's field-3 count
+    assert len(orc.innerjoin_pairs(r, s, "3")) == m["nres"]
+
+
 @pytest.mark.parametrize("field", "0123")
 def test_dedup_count_within_the_reference_defect_window(orc, golden, inputs, field):
     meta, _ = golden
