@@ -28,7 +28,7 @@ C_ABI_SYMBOLS = [
     "dbt_sort_counters", "dbt_dedup_nios", "dbt_hashjoin_nios", "dbt_mergejoin_nios",
     "dbt_sort_pairs_ws_bytes", "dbt_sort_pairs_u32", "dbt_gather_records", "dbt_gather_records_limited",
     "dbt_dev_extract_keys_u32", "dbt_dev_partition_rows", "dbt_dev_partition_ws_bytes",
-    "dbt_dev_ws_bytes", "dbt_dev_ws_bytes_kw", "dbt_dev_mergesort", "dbt_dev_dedup", "dbt_dev_mergejoin", "dbt_dev_hashjoin", "dbt_dev_innerjoin_pairs", "dbt_dev_semijoin_keys",
+    "dbt_dev_ws_bytes", "dbt_dev_ws_bytes_kw", "dbt_dev_hashjoin_ws_bytes", "dbt_dev_mergesort", "dbt_dev_dedup", "dbt_dev_mergejoin", "dbt_dev_hashjoin", "dbt_dev_innerjoin_pairs", "dbt_dev_semijoin_keys",
     "dbt_host_mergesort", "dbt_host_dedup", "dbt_host_mergejoin", "dbt_host_hashjoin",
     "dbt_dev_extract_key_recid_u32", "dbt_dev_take_u32", "dbt_dev_order_columns", "dbt_dev_order_columns_ws_bytes",
     "dbt_gather_records_multi", "dbt_ipc_export",
@@ -36,6 +36,9 @@ C_ABI_SYMBOLS = [
     "dbt_host_mergesort_begin", "dbt_host_dedup_begin", "dbt_host_mergejoin_begin", "dbt_host_hashjoin_begin",
     "dbt_host_job_wait", "dbt_host_job_slots", "dbt_host_trim", "dbt_host_set_chunk_blocks", "dbt_host_ooc_stats",
     "dbt_host_alloc", "dbt_host_free", "dbt_gen_syn",
+    "dbt_dist_init", "dbt_dist_init_local", "dbt_dist_destroy", "dbt_dist_rank", "dbt_dist_world", "dbt_dist_barrier",
+    "dbt_dist_set_sub_ranges", "dbt_dist_allgather_host", "dbt_dist_sort", "dbt_dist_hashjoin", "dbt_dist_mergejoin",
+    "dbt_dist_stats", "dbt_dist_selftest_host",
     "dbt_stage_timing_enable", "dbt_stage_timing_reset", "dbt_stage_count", "dbt_stage_name", "dbt_stage_ms",
     "dbt_stage_launches", "dbt_kernel_launches",
 ]
@@ -87,6 +90,8 @@ def lib() -> C.CDLL:
     L.dbt_dev_ws_bytes.argtypes = [ci, u64, u64, ci]
     L.dbt_dev_ws_bytes_kw.restype = sz
     L.dbt_dev_ws_bytes_kw.argtypes = [ci, u64, u64, ci, u32]
+    L.dbt_dev_hashjoin_ws_bytes.restype = sz
+    L.dbt_dev_hashjoin_ws_bytes.argtypes = [u64, u64, ci, u32, u64]
     L.dbt_dev_mergesort.argtypes = [vp, u64, ci, vp, vp, sz, vp, pu64]
     L.dbt_dev_dedup.argtypes = [vp, u64, ci, vp, vp, sz, vp, pu64, pu64]
     L.dbt_dev_mergejoin.argtypes = [vp, u64, vp, u64, ci, vp, vp, vp, vp, sz, vp, pu64]
@@ -124,6 +129,19 @@ def lib() -> C.CDLL:
     L.dbt_host_alloc.argtypes = [C.POINTER(vp), sz]
     L.dbt_host_free.argtypes = [vp]
     L.dbt_gen_syn.argtypes = [u64, u64, u64, ci, u64, u64, u32, vp, vp]
+    L.dbt_dist_init.argtypes = [C.c_char_p, ci, ci, ci, C.POINTER(vp)]
+    L.dbt_dist_init_local.argtypes = [ci, C.POINTER(ci), C.POINTER(vp)]
+    L.dbt_dist_destroy.argtypes = [vp]
+    L.dbt_dist_rank.argtypes = [vp]
+    L.dbt_dist_world.argtypes = [vp]
+    L.dbt_dist_barrier.argtypes = [vp]
+    L.dbt_dist_set_sub_ranges.argtypes = [vp, u32]
+    L.dbt_dist_allgather_host.argtypes = [vp, vp, sz, vp]
+    L.dbt_dist_sort.argtypes = [vp, vp, u64, ci, ci, vp, u64, vp, pu64, pu64]
+    L.dbt_dist_hashjoin.argtypes = [vp, vp, u64, vp, u64, ci, vp, u64, vp, pu64]
+    L.dbt_dist_mergejoin.argtypes = [vp, vp, u64, vp, u64, ci, vp, u64, vp, pu64]
+    L.dbt_dist_stats.argtypes = [vp, C.POINTER(C.c_double)]
+    L.dbt_dist_selftest_host.argtypes = [C.c_char_p, ci, ci, pu64]
     L.dbt_stage_timing_enable.argtypes = [ci]
     L.dbt_stage_timing_enable.restype = None
     L.dbt_stage_timing_reset.restype = None
@@ -194,3 +212,47 @@ def dev_hashjoin(d_r: int, nbr: int, d_s: int, nbs: int, field, d_out: int, out_
     check(lib().dbt_dev_hashjoin(d_r, nbr, d_s, nbs, _fld(field), d_out, out_cap_blocks, d_ws, ws_bytes, stream,
                                  C.byref(n)))
     return n.value
+
+
+# ---- multi-GPU operators (csrc/dist.cu): one rank per GPU, collective calls -----------------------------
+class Dist:
+    """One rank of a multi-GPU group (C++ layer: shared-memory control block, peer-memory exchange, no NCCL on the
+    data path).  `session` must be the same string on every rank and unique per group (e.g. MASTER_PORT + a nonce)."""
+
+    def __init__(self, session: str, rank: int, world: int, device: int):
+        self.L = lib()
+        h = C.c_void_p()
+        check(self.L.dbt_dist_init(session.encode(), rank, world, device, C.byref(h)))
+        self.h, self.rank, self.world = h, rank, world
+
+    def close(self):
+        if self.h:
+            self.L.dbt_dist_destroy(self.h)
+            self.h = None
+
+    def barrier(self):
+        check(self.L.dbt_dist_barrier(self.h))
+
+    def set_sub_ranges(self, q: int):
+        check(self.L.dbt_dist_set_sub_ranges(self.h, q))
+
+    def sort(self, d_in: int, nblocks: int, field, dedup: bool, d_out: int, cap_blocks: int, stream: int = 0):
+        n, m = C.c_uint64(), C.c_uint64()
+        check(self.L.dbt_dist_sort(self.h, d_in, nblocks, _fld(field), 1 if dedup else 0, d_out, cap_blocks, stream, C.byref(n),
+                                   C.byref(m)))
+        return n.value, m.value
+
+    def hashjoin(self, d_r: int, nbr: int, d_s: int, nbs: int, field, d_out: int, cap_blocks: int, stream: int = 0) -> int:
+        n = C.c_uint64()
+        check(self.L.dbt_dist_hashjoin(self.h, d_r, nbr, d_s, nbs, _fld(field), d_out, cap_blocks, stream, C.byref(n)))
+        return n.value
+
+    def mergejoin(self, d_r: int, nbr: int, d_s: int, nbs: int, field, d_out: int, cap_blocks: int, stream: int = 0) -> dict:
+        res = (C.c_uint64 * 4)()
+        check(self.L.dbt_dist_mergejoin(self.h, d_r, nbr, d_s, nbs, _fld(field), d_out, cap_blocks, stream, res))
+        return {"nres": res[0], "nunique_R": res[1], "nunique_S": res[2], "later_reads": res[3]}
+
+    def stats(self) -> dict:
+        out = (C.c_double * 16)()
+        check(self.L.dbt_dist_stats(self.h, out))
+        return {"nvlink_ms": out[0], "bytes_remote": out[1], "bytes_total": out[2], "sub_ranges": int(out[3])}

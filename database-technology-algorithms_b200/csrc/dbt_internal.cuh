@@ -176,6 +176,8 @@ int prepare(const void *d_img, uint64_t nblocks, int field, Arena &ws, cudaStrea
 // (field '3' semantics) when it is two.
 int sort_rows_by_key(KeyCols &k, int field, Arena &ws, cudaStream_t st, uint32_t **perm_out, uint32_t **sorted_w0_out,
                      KeyCols *compact = nullptr);
+int sorted_rows(const void *d_img, uint64_t nblocks, int field, bool dedup, Arena &ws, cudaStream_t st, uint32_t **rows,
+                uint32_t **row_slot, uint64_t *n_in, uint64_t *n_out);
 // first row of every group of equal keys in sorted order, using the compact key when sort_rows_by_key made one
 int unique_sorted(const KeyCols &k, const KeyCols &compact, int field, const uint32_t *d_perm, const uint32_t *d_sorted_w0,
                   uint64_t n, uint32_t *d_uperm, uint64_t *d_count, Arena &ws, cudaStream_t st);

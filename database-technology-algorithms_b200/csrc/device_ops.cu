@@ -198,7 +198,8 @@ int sort_rows_by_key(KeyCols &k, int field, Arena &ws, cudaStream_t st, uint32_t
 
     uint32_t *ka = nullptr, *kb = ws.take<uint32_t>(n), *va = ws.take<uint32_t>(n), *vb = ws.take<uint32_t>(n);
     // a single one-word key: sort the column in place (clobbers it)
-    const bool single_col = (words.size() == 1 && (words[0].src == k.w0 || words[0].src == ck_lo));
+    // (field '3' without a compact key keeps w0 intact: its callers compare full keys through the row permutation)
+    const bool single_col = (words.size() == 1 && ((words[0].src == k.w0 && (field == '0' || field == '1')) || words[0].src == ck_lo));
     if (!single_col) ka = ws.take<uint32_t>(n);
     else ka = const_cast<uint32_t *>(words[0].src);
     if (!ka || !kb || !va || !vb) {
@@ -275,6 +276,40 @@ static int prepare_pair(const void *d_r, uint64_t nbr, const void *d_s, uint64_t
             DBT_TRY(prepare(d_s, nbs, field, ws, st, ps, kw));
         }
     }
+    return 0;
+}
+
+static int read_u64(const uint64_t *d, uint64_t *h, int count, cudaStream_t st);
+
+// The ordered (and optionally duplicate-free) row list of one image, without moving a record: what MergeSort /
+// EliminateDuplicates gather.  The multi-GPU layer appends the lists of consecutive key sub-ranges to one output image.
+int sorted_rows(const void *d_img, uint64_t nblocks, int field, bool dedup, Arena &ws, cudaStream_t st, uint32_t **rows,
+                uint32_t **row_slot, uint64_t *n_in, uint64_t *n_out) {
+    Prepared p;
+    DBT_TRY(prepare(d_img, nblocks, field, ws, st, &p));
+    const uint64_t n = p.info.nrows;
+    *n_in = n;
+    *n_out = 0;
+    *rows = nullptr;
+    *row_slot = p.row_slot;
+    if (!n) return 0;
+    uint32_t *perm, *sorted;
+    KeyCols compact;
+    DBT_TRY(sort_rows_by_key(p.keys, field, ws, st, &perm, &sorted, &compact));
+    if (!dedup) {
+        *rows = perm;
+        *n_out = n;
+        return 0;
+    }
+    uint32_t *uperm = ws.take<uint32_t>(n);
+    uint64_t *d_cnt = ws.take<uint64_t>(8);
+    if (!uperm || !d_cnt) {
+        set_error("dedup: workspace too small");
+        return DBT_ERR_WORKSPACE;
+    }
+    DBT_TRY(unique_sorted(p.keys, compact, field, perm, sorted, n, uperm, d_cnt, ws, st));
+    DBT_TRY(read_u64(d_cnt, n_out, 1, st));
+    *rows = uperm;
     return 0;
 }
 
@@ -710,7 +745,10 @@ extern "C" int dbt_dev_mergejoin(const void *d_in_r, uint64_t nbr, const void *d
 static int fused_semijoin(const uint32_t *d_rkeys, uint64_t nr, const void *d_in_s, uint64_t nbs, int field, void *d_out,
                           uint64_t cap_blocks, Arena &ws, cudaStream_t st, uint64_t *nres, bool *done) {
     *done = false;
-    if (getenv("DBT_JOIN_FUSED") && atoi(getenv("DBT_JOIN_FUSED")) == 0) return 0;
+    // opt-in for now (DBT_JOIN_FUSED=1): the chained single pass is exact but runs at 0.35 of the HBM roofline -- every
+    // tile pays ~4 serialized L2 round trips (ticket, bitmap, 1.7 look-back rounds) of ~3.7 us each under streaming
+    // load, profiles/r02_notes.md -- which is slower than the column path it is meant to replace (42.8 vs 32.7 ms)
+    if (!getenv("DBT_JOIN_FUSED") || atoi(getenv("DBT_JOIN_FUSED")) == 0) return 0;
     if (!nr || !nbs || nbs >= (1ull << 32)) return 0;
     const size_t m0 = ws.mark();
     uint32_t *bm, base, span;

@@ -376,8 +376,11 @@ int io_threads() {
     }();
     return n;
 }
-// parallel pread / pwrite of [off, off+len) between a file and memory
-void parallel_io(int fd, char *mem, size_t off, size_t len, bool write, const char *path) {
+// parallel pread / pwrite of file bytes [off, off+len) from / to mem[off, off+len): `mem` is the image of the WHOLE
+// file, so a chunk lands at the same offset in memory as in the file (the H2D / D2H copies of the chunk pipeline use
+// those offsets)
+void parallel_io(int fd, char *mem_base, size_t off, size_t len, bool write, const char *path) {
+    char *mem = mem_base + off;
     const int nt = (len < (8u << 20)) ? 1 : io_threads();
     std::vector<std::thread> th;
     std::vector<int> bad(nt, 0);

@@ -6,11 +6,12 @@
 // the key column, a compaction and a random gather of the matching records (a second, scattered read of S).  Here S is
 // read once, sequentially:
 //
-//   persistent CTAs take S blocks in file order (dynamic block ids) and keep the NEXT block in flight with
-//   cp.async.bulk (global -> shared, mbarrier completion) while they work on the current one out of shared memory;
+//   persistent CTAs take tiles of two consecutive S blocks in file order (a ticket per tile, taken only when the CTA
+//   is ready for it) and bring them into shared memory with one cp.async.bulk (mbarrier completion); seven resident
+//   CTAs per SM keep ~200 KB per SM in flight, which is what hides the DRAM latency;
 //   every live row tests its key against the direct-address bitmap of keys(R) (L2-resident for reference-like key
-//   ranges); the block's match count goes into a decoupled look-back chain (64-bit tile states, the whole CTA looks
-//   back 256 predecessors per round trip) that yields the output row of the block's first match;
+//   ranges); the tile's match count goes into a decoupled look-back chain (64-bit tile states, the whole CTA looks
+//   back 512 predecessors per round trip) that yields the output row of the block's first match;
 //   the matching 140-byte records are copied from shared memory straight to their final place in the packed output
 //   image (consecutive matches are contiguous there, so the 4-byte stores of a warp coalesce), with the CANON block
 //   headers written by whoever emits a block's first row.
@@ -23,8 +24,11 @@
 
 namespace dbt {
 
-constexpr int kSjThreads = 128;
-constexpr int kSjStages = 2;
+constexpr int kSjThreads = 256;
+constexpr int kSjTileBlocks = 2;                  // S blocks per tile: one row per thread (200 of the 256 threads)
+constexpr int kSjTileRows = kSjTileBlocks * kRpb;
+constexpr int kSjLbPerThread = 2;                 // look-back window = 2 x 256 predecessors per round trip
+constexpr int kSjLbSegs = kSjLbPerThread * (kSjThreads / 32);
 constexpr uint64_t kSjAgg = 1ull << 62, kSjInc = 2ull << 62, kSjMask = (1ull << 62) - 1;
 
 __device__ __forceinline__ uint32_t sj_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -38,18 +42,20 @@ __device__ __forceinline__ void sj_st(uint64_t *p, uint64_t v) {
 }
 
 struct SjSmem {
-    alignas(128) uint32_t stage[kSjStages][kBlockWords];
-    alignas(8) uint64_t mbar[kSjStages];
-    uint64_t lb_sum[8];
-    uint32_t lb_inc[8], lb_ok[8];
-    uint32_t next_tile[kSjStages];
-    uint32_t src[kRpb]; // entry index (inside the S block) of the k-th match
-    uint32_t dst[kRpb]; // word offset of the k-th match's output record, relative to the first one's
+    alignas(128) uint32_t stage[kSjTileBlocks * kBlockWords];
+    alignas(8) uint64_t mbar;
+    uint64_t lb_sum[kSjLbSegs];
+    uint32_t lb_inc[kSjLbSegs], lb_ok[kSjLbSegs];
+    uint32_t tile;
+    uint32_t src[kSjTileRows]; // word offset (inside the stage) of the k-th match's record
+    uint32_t dst[kSjTileRows]; // word offset of the k-th match's output record, relative to the first one's
     uint32_t wcnt[kSjThreads / 32];
 };
 
 // Exclusive prefix (output rows before this tile) by decoupled look-back; the whole CTA takes part: thread t examines
-// predecessors t and t + 128 of the current window, so one round trip to L2 covers 256 tiles.  Uniform result.
+// predecessors t and t + 256 of the current window, so one round trip to L2 covers 512 tiles.  Uniform result.
+// A tile takes its ticket only when it is about to be processed (no tile is claimed ahead of time), so the aggregates
+// of the predecessors are published within a DRAM latency of their tickets and the chain never waits on a parked tile.
 __device__ __forceinline__ uint64_t sj_lookback(SjSmem &sm, uint64_t *state, uint32_t tile, uint32_t m, uint32_t *err) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tile == 0) {
@@ -62,7 +68,7 @@ __device__ __forceinline__ uint64_t sj_lookback(SjSmem &sm, uint64_t *state, uin
     uint32_t spins = 0;
     while (true) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < kSjLbPerThread; ++h) {
             const int64_t idx = p - (int64_t)(h * kSjThreads + tid);
             const uint64_t sv = (idx >= 0) ? sj_ld(&state[idx]) : kSjInc;
             const uint32_t ready = __ballot_sync(0xFFFFFFFFu, (sv >> 62) != 0);
@@ -83,7 +89,7 @@ __device__ __forceinline__ uint64_t sj_lookback(SjSmem &sm, uint64_t *state, uin
         uint64_t acc = 0;
         bool found = false, fail = false;
         int s = 0;
-        for (; s < 8; ++s) {
+        for (; s < kSjLbSegs; ++s) {
             if (!sm.lb_ok[s]) {
                 fail = true;
                 break;
@@ -99,13 +105,14 @@ __device__ __forceinline__ uint64_t sj_lookback(SjSmem &sm, uint64_t *state, uin
         if (found) break;
         if (fail) { // segments before s were complete and held no inclusive prefix: keep them, poll again from s
             p -= 32 * s;
-            if (++spins > (1u << 24)) { // a predecessor never published: report instead of hanging the device
+            if (++spins > (1u << 22)) { // a predecessor never published: report instead of hanging the device
                 if (tid == 0) atomicExch(err, 1u);
                 break;
             }
+            __nanosleep(100);
             continue;
         }
-        p -= 2 * kSjThreads;
+        p -= kSjLbPerThread * kSjThreads;
     }
     if (tid == 0) sj_st(&state[tile], kSjInc | (excl + (uint64_t)m));
     return excl;
@@ -114,53 +121,56 @@ __device__ __forceinline__ uint64_t sj_lookback(SjSmem &sm, uint64_t *state, uin
 template <int FIELD> // 0 = recid, 1 = num
 __global__ void __launch_bounds__(kSjThreads)
 semijoin_stream_kernel(const uint32_t *__restrict__ img, uint32_t nblocks, const uint32_t *__restrict__ bm, uint32_t base,
-                       uint32_t span, uint32_t *__restrict__ out, uint64_t cap_rows, uint64_t *state /*[nblocks] zeroed*/,
-                       uint32_t *ctr /*[0] tile counter, [1] error flag; zeroed*/, unsigned long long *total_out) {
+                       uint32_t span, uint32_t *__restrict__ out, uint64_t cap_rows, uint64_t *state /*[ntiles] zeroed*/,
+                       uint32_t *ctr /*[0] ticket counter, [1] error flag; zeroed*/, unsigned long long *total_out) {
     __shared__ SjSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = (1u << lane) - 1u;
-    auto issue = [&](uint32_t t, int stg) { // thread 0: bulk copy of S block t into stage stg
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sj_smem_u32(&sm.mbar[stg])),
-                     "r"((uint32_t)DBT_BLOCK_BYTES)
-                     : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         sj_smem_u32(sm.stage[stg])),
-                     "l"(img + (uint64_t)t * kBlockWords), "r"((uint32_t)DBT_BLOCK_BYTES), "r"(sj_smem_u32(&sm.mbar[stg]))
-                     : "memory");
-    };
+    const uint32_t ntiles = (nblocks + kSjTileBlocks - 1) / kSjTileBlocks;
     if (tid == 0) {
-        for (int i = 0; i < kSjStages; ++i)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sj_smem_u32(&sm.mbar[i])), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sj_smem_u32(&sm.mbar)), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const uint32_t t = atomicAdd(&ctr[0], 1u);
-        sm.next_tile[0] = t;
-        if (t < nblocks) issue(t, 0);
     }
-    __syncthreads();
-    uint32_t tile = sm.next_tile[0];
-    int stg = 0;
     uint32_t parity = 0;
-    while (tile < nblocks) {
-        if (tid == 0) { // claim the next block now: its copy runs while this one is processed
+    const uint32_t my_blk = (uint32_t)tid / kRpb, my_e = (uint32_t)tid - my_blk * kRpb; // the row this thread tests
+    while (true) {
+        __syncthreads(); // everyone is done with the stage, src/dst and sm.tile of the previous tile
+        if (tid == 0) {  // take a ticket and start the bulk copy of the tile's blocks (consecutive in the image)
             const uint32_t t = atomicAdd(&ctr[0], 1u);
-            sm.next_tile[stg ^ 1] = t;
-            if (t < nblocks) issue(t, stg ^ 1);
+            sm.tile = t;
+            if (t < ntiles) {
+                const uint32_t b0 = t * kSjTileBlocks;
+                const uint32_t bytes = min((uint32_t)kSjTileBlocks, nblocks - b0) * (uint32_t)DBT_BLOCK_BYTES;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sj_smem_u32(&sm.mbar)), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 sj_smem_u32(sm.stage)),
+                             "l"(img + (uint64_t)b0 * kBlockWords), "r"(bytes), "r"(sj_smem_u32(&sm.mbar))
+                             : "memory");
+            }
         }
+        __syncthreads();
+        const uint32_t tile = sm.tile;
+        if (tile >= ntiles) break;
         uint32_t ok = 0;
         while (!ok)
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                          : "=r"(ok)
-                         : "r"(sj_smem_u32(&sm.mbar[stg])), "r"((parity >> stg) & 1u)
+                         : "r"(sj_smem_u32(&sm.mbar)), "r"(parity)
                          : "memory");
-        parity ^= 1u << stg;
-        const uint32_t *blk = sm.stage[stg];
-        const uint32_t nres = min(blk[1], kRpb);
+        parity ^= 1u;
+        const uint32_t nb_tile = min((uint32_t)kSjTileBlocks, nblocks - tile * kSjTileBlocks);
         bool match = false;
-        if (tid < (int)nres) {
-            const uint32_t key = blk[kEntriesWord + tid * kRecWords + (FIELD == 0 ? 0 : 1)];
-            const uint32_t v = key - base;
-            match = (v <= span) && ((__ldg(bm + (v >> 5)) >> (v & 31)) & 1u);
+        uint32_t my_word = 0;
+        if (my_blk < nb_tile) {
+            const uint32_t *blk = sm.stage + my_blk * kBlockWords;
+            const uint32_t nres = min(blk[1], kRpb);
+            if (my_e < nres) {
+                my_word = my_blk * kBlockWords + kEntriesWord + my_e * kRecWords;
+                const uint32_t key = sm.stage[my_word + (FIELD == 0 ? 0 : 1)];
+                const uint32_t v = key - base;
+                match = (v <= span) && ((__ldg(bm + (v >> 5)) >> (v & 31)) & 1u);
+            }
         }
         const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, match);
         if (lane == 0) sm.wcnt[warp] = __popc(ballot);
@@ -172,8 +182,8 @@ semijoin_stream_kernel(const uint32_t *__restrict__ img, uint32_t nblocks, const
             if (w < warp) wpre += c;
             m += c;
         }
-        if (match) sm.src[wpre + __popc(ballot & lt)] = (uint32_t)tid;
-        const uint64_t excl = sj_lookback(sm, state, tile, m, &ctr[1]); // (contains CTA barriers: sm.src is visible after it)
+        if (match) sm.src[wpre + __popc(ballot & lt)] = my_word;
+        const uint64_t excl = sj_lookback(sm, state, tile, m, &ctr[1]);
         const uint64_t off0 = slot_word(excl);
         if (tid < (int)m) {
             const uint64_t g = excl + (uint64_t)tid;
@@ -192,12 +202,9 @@ semijoin_stream_kernel(const uint32_t *__restrict__ img, uint32_t nblocks, const
         const uint32_t nwords = m * kRecWords;
         for (uint32_t idx = tid; idx < nwords; idx += kSjThreads) {
             const uint32_t rec = idx / kRecWords, w = idx - rec * kRecWords;
-            if (excl + rec < cap_rows) out[off0 + sm.dst[rec] + w] = blk[kEntriesWord + sm.src[rec] * kRecWords + w];
+            if (excl + rec < cap_rows) out[off0 + sm.dst[rec] + w] = sm.stage[sm.src[rec] + w];
         }
-        if (tid == 0 && tile + 1 == nblocks) *total_out = excl + m;
-        __syncthreads(); // everyone is done with this stage (and with src/dst) before they are reused
-        tile = sm.next_tile[stg ^ 1];
-        stg ^= 1;
+        if (tid == 0 && tile + 1 == ntiles) *total_out = excl + m;
     }
 }
 
@@ -232,13 +239,14 @@ int semijoin_stream(const void *d_s_img, uint64_t nblocks_s, int field, const ui
     }
     StageScope sc(ST_HASH_PROBE, st);
     const size_t m0 = ws.mark();
-    uint64_t *state = ws.take<uint64_t>(nblocks_s);
+    const uint64_t ntiles = (nblocks_s + kSjTileBlocks - 1) / kSjTileBlocks;
+    uint64_t *state = ws.take<uint64_t>(ntiles);
     uint32_t *ctr = ws.take<uint32_t>(64);
     if (!state || !ctr) {
         set_error("semijoin: workspace too small");
         return DBT_ERR_WORKSPACE;
     }
-    DBT_CUDA(cudaMemsetAsync(state, 0, nblocks_s * 8, st));
+    DBT_CUDA(cudaMemsetAsync(state, 0, ntiles * 8, st));
     DBT_CUDA(cudaMemsetAsync(ctr, 0, 8, st));
     DBT_CUDA(cudaMemsetAsync(d_total, 0, 16, st));
     static int per_sm[2] = {0, 0};
@@ -251,7 +259,7 @@ int semijoin_stream(const void *d_s_img, uint64_t nblocks_s, int field, const ui
         per_sm[f] = std::max(occ, 1);
     }
     int nsm = 148;
-    const int grid = (int)std::min<uint64_t>(nblocks_s, (uint64_t)nsm * per_sm[f]);
+    const int grid = (int)std::min<uint64_t>(ntiles, (uint64_t)nsm * per_sm[f]);
     if (f == 0)
         semijoin_stream_kernel<0><<<grid, kSjThreads, 0, st>>>((const uint32_t *)d_s_img, (uint32_t)nblocks_s, d_bitmap, base, span,
                                                                (uint32_t *)d_out, cap_rows, state, ctr, (unsigned long long *)d_total);

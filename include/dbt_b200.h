@@ -202,6 +202,53 @@ int dbt_ipc_close(void *d_ptr);
 int dbt_ipc_free(void *d_ptr);
 
 /* ----------------------------------------------------------------------------------------------
+ * Multi-GPU operators (C++ host layer, csrc/dist.cu).  One RANK per GPU of one box.  Ranks are
+ * processes (dbt_dist_init: they rendezvous through a POSIX shared-memory control block named after `session` and
+ * map each other's staging buffers with CUDA IPC) or threads of one process (dbt_dist_init_local: peer access, no
+ * IPC; this is how the file entry points use every visible GPU).  Every operator is COLLECTIVE: all ranks of the
+ * group call it, each with its own shard (device pointers on its own GPU, any cudaMalloc'ed memory).  Records and
+ * key columns cross NVLink as stores of the library's own kernels into the owner's staging buffer (gather + exchange
+ * in one kernel); completion travels as stream-ordered flags in peer memory; no NCCL, no torch on the data path.
+ *   sort / dedup   shard by key RANGE: splitters from a global sample cut the key space into P x Q sub-ranges (split
+ *                  on the key only, so equal keys meet); rows are pushed sub-range by sub-range and the owner runs
+ *                  the single-GPU operator on sub-range q while q+1.. are still on the wire.  The concatenation of
+ *                  the ranks' outputs, in rank order, is the globally sorted (duplicate-free) file
+ *                  (DatabaseProject.cpp:172-381, :94-170 across P GPUs).
+ *   hashjoin       fields '0'/'1': the build side's KEYS are replicated (4 bytes per R row) and every rank probes its
+ *                  own S shard in place (fused streaming semi-join): no S record moves, key skew cannot unbalance the
+ *                  ranks, the outputs concatenate in S file order like the reference's.  Fields '2'/'3': both
+ *                  relations are hash-partitioned on the key's first word, then the ordinary operator runs per rank.
+ *   mergejoin      both relations are range-partitioned with the SAME splitters, then dbt_dev_mergejoin per rank; the
+ *                  ranks' outputs concatenate in ascending key order (res[] are this rank's counts).
+ * Replaces nothing in the reference (it is single-threaded); boundary: dbtproj.h:55-96.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dbt_dist dbt_dist;
+int dbt_dist_init(const char *session, int rank, int world, int device, dbt_dist **out);
+int dbt_dist_init_local(int world, const int *devices, dbt_dist **out /*[world]*/);
+int dbt_dist_destroy(dbt_dist *d);
+int dbt_dist_rank(const dbt_dist *d);
+int dbt_dist_world(const dbt_dist *d);
+int dbt_dist_barrier(dbt_dist *d); /* host barrier over the control block */
+/* key sub-ranges per owner for sort/dedup (the pipeline depth); 0 = automatic: 4, or 1 for small shards */
+int dbt_dist_set_sub_ranges(dbt_dist *d, uint32_t q);
+/* every rank contributes `bytes` (<= 32 KB) of host memory; out receives world * bytes in rank order */
+int dbt_dist_allgather_host(dbt_dist *d, const void *mine, size_t bytes, void *out);
+/* d_out must hold out_capacity_blocks blocks (a rank receives about 1/P of the rows; splitters come from a sample, so
+ * leave headroom); *out_rows = rows in this rank's output, *rows_received = rows this rank owned before dedup */
+int dbt_dist_sort(dbt_dist *d, const void *d_in, uint64_t nblocks, int field, int dedup, void *d_out,
+                  uint64_t out_capacity_blocks, void *stream, uint64_t *out_rows, uint64_t *rows_received);
+int dbt_dist_hashjoin(dbt_dist *d, const void *d_r, uint64_t nblocks_r, const void *d_s, uint64_t nblocks_s, int field,
+                      void *d_out, uint64_t out_capacity_blocks, void *stream, uint64_t *nres);
+int dbt_dist_mergejoin(dbt_dist *d, const void *d_r, uint64_t nblocks_r, const void *d_s, uint64_t nblocks_s, int field,
+                       void *d_out, uint64_t out_capacity_blocks, void *stream, uint64_t *res /*[4]*/);
+/* last operator on this rank: [0] ms of the NVLink phase (first push .. last flag), [1] bytes stored into other GPUs,
+ * [2] bytes stored in total (incl. own staging), [3] sub-ranges used */
+int dbt_dist_stats(const dbt_dist *d, double out[16]);
+/* host-only self test of the control block (rendezvous, barriers, all-gathers, splitter choice, layout arithmetic);
+ * no CUDA call: runs on machines without a GPU.  *checksum is identical on all ranks. */
+int dbt_dist_selftest_host(const char *session, int rank, int world, uint64_t *checksum);
+
+/* ----------------------------------------------------------------------------------------------
  * Host-scope operators: image in host memory -> image in host memory, copies included.
  * These are what the file-based dbtproj entry points call after reading the block files into
  * pinned staging.  `device` is the CUDA device index.  h_out sized like the device-scope case.

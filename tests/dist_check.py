@@ -1,8 +1,12 @@
-"""Run under torchrun on >= 2 GPUs: the CUDA multi-GPU path (DistOps + LocalOps, fused gather->peer
-exchange or NCCL all-to-all) against the single-node CANON oracle.  Used by tests/test_gpu_dist.py."""
+"""Run under torchrun on >= 2 GPUs: the C++ multi-GPU layer (csrc/dist.cu through dbt.Dist: shared-memory control
+block, gather+push over peer memory, pipelined key sub-ranges) against the single-node CANON oracle.  Every output ROW
+is compared with all of its 140 bytes (the ranks' images concatenate with a partial block at each rank boundary, so
+rows, not blocks, are the unit).  torch.distributed is only used to agree on a session name and to collect the ranks'
+outputs for the comparison.  Used by tests/test_gpu_dist.py; prints DIST_CHECK_PASSED."""
 import importlib
 import os
 import sys
+import time
 
 import numpy as np
 import torch
@@ -17,7 +21,11 @@ BLOCK = 14016
 
 def rows_of_image(t, out_rows):
     nb = (out_rows + 99) // 100
-    return orc.rows_of(orc.as_blocks(t[: nb * BLOCK].cpu().numpy().copy()))["recid"].copy()
+    img = orc.as_blocks(t[: nb * BLOCK].cpu().numpy().copy())
+    assert int(img["nreserved"].sum()) == out_rows, (int(img["nreserved"].sum()), out_rows)
+    if nb:
+        assert (img["blockid"] == np.arange(nb)).all() and (img["valid"] == 1).all()  # CANON headers, rank-local numbering
+    return orc.rows_of(img).copy()
 
 
 def main():
@@ -25,43 +33,62 @@ def main():
     torch.cuda.set_device(lr)
     dev = torch.device("cuda", lr)
     dist.init_process_group("nccl", device_id=dev)
-    dmod = importlib.import_module("database-technology-algorithms_b200.dist")
-    ops = dmod.LocalOps(dev)
-    d = dmod.DistOps(ops, samples_per_rank=1024)
-    nb_local = 200
+    dbt = importlib.import_module("database-technology-algorithms_b200")
+    tok = [f"{os.environ.get('MASTER_PORT', '0')}_{os.getpid()}_{int(time.time() * 1e3) % 100000}"]
+    dist.broadcast_object_list(tok, src=0)
+    d = dbt.Dist(tok[0], rank, world, lr)
+    nb_local = int(os.environ.get("DIST_CHECK_BLOCKS", "200"))
     f1, f2 = orc.gen_ref(11, nb_local * world, num_mod=30000)
-    to_dev = lambda b: torch.from_numpy(b.view(np.uint8).reshape(-1).copy()).to(dev)
-    t1 = to_dev(f1[rank * nb_local:(rank + 1) * nb_local])
-    t2 = to_dev(f2[rank * nb_local:(rank + 1) * nb_local])
+    rng = np.random.default_rng(5)
+    rag = f1.copy()  # ragged inputs: partial and empty blocks anywhere (the push reads rows through the slot list)
+    rag["nreserved"] = rng.integers(0, 101, size=len(rag)).astype(np.uint32)
+    to_dev = lambda b: torch.from_numpy(np.ascontiguousarray(b).view(np.uint8).reshape(-1).copy()).to(dev)
+    sl = slice(rank * nb_local, (rank + 1) * nb_local)
+    t1, t2, t1r = to_dev(f1[sl]), to_dev(f2[sl]), to_dev(rag[sl])
+    cap = nb_local * world + 8
+    out = torch.empty(cap * BLOCK, dtype=torch.uint8, device=dev)
+    sp = torch.cuda.current_stream().cuda_stream
     res = {}
-    for rep in range(2):  # twice: buffer reuse across steps must be safe
+    for rep, q in enumerate((0, 1, 3)):  # automatic, one region, three key sub-ranges per owner (pipelined); buffers are reused
+        d.set_sub_ranges(q)
         for field in ("1", "0", "2", "3"):
             for op in ("sort", "dedup"):
-                out, info = getattr(d, op)(t1, nb_local, field)
-                res[f"{op}{field}"] = rows_of_image(out, info["out_rows"])
-            out, info = d.hashjoin(t1, nb_local, t2, nb_local, field)
-            res[f"hashjoin{field}"] = rows_of_image(out, info["out_rows"])
-            out, info = d.mergejoin(t1, nb_local, t2, nb_local, field)
-            res[f"mergejoin{field}"] = rows_of_image(out, info["out_rows"])
+                for name, src in (("", t1), ("_rag", t1r)):
+                    n, m = d.sort(src.data_ptr(), nb_local, field, op == "dedup", out.data_ptr(), cap, sp)
+                    res[f"{op}{field}{name}_q{q}"] = rows_of_image(out, n)
+            if rep == 0:
+                k = d.hashjoin(t1.data_ptr(), nb_local, t2.data_ptr(), nb_local, field, out.data_ptr(), cap, sp)
+                res[f"hashjoin{field}"] = rows_of_image(out, k)
+                info = d.mergejoin(t1.data_ptr(), nb_local, t2.data_ptr(), nb_local, field, out.data_ptr(), cap, sp)
+                res[f"mergejoin{field}"] = rows_of_image(out, info["nres"])
+    st = d.stats()
     gathered = [None] * world
     dist.all_gather_object(gathered, res)
     ok = True
     if rank == 0:
+        want = {}
         for field in ("1", "0", "2", "3"):
-            checks = {
-                f"sort{field}": (orc.rows_of(orc.sort(f1, field))["recid"], False),
-                f"dedup{field}": (orc.rows_of(orc.dedup(f1, field))["recid"], False),
-                # u32 keys: replicated build keys => the ranks' outputs concatenate in S file order (exact compare);
-                # str / composite keys: hash partition => compare as sorted multisets
-                f"hashjoin{field}": (orc.rows_of(orc.hashjoin(f1, f2, field))["recid"], field in ("2", "3")),
-                f"mergejoin{field}": (orc.rows_of(orc.mergejoin(f1, f2, field)[0])["recid"], False),
-            }
-            for name, (want, as_set) in checks.items():
-                got = np.concatenate([g[name] for g in gathered])
-                same = np.array_equal(np.sort(got), np.sort(want)) if as_set else np.array_equal(got, want)
-                print(f"{name}: {'OK' if same else 'MISMATCH'} ({len(got)} rows, exchange={d.last_exchange.get('mode')})")
-                ok = ok and same
+            for name, src in (("", f1), ("_rag", rag)):
+                want[f"sort{field}{name}"] = (orc.rows_of(orc.sort(src, field)), False)
+                want[f"dedup{field}{name}"] = (orc.rows_of(orc.dedup(src, field)), False)
+            # u32 keys: replicated build keys => the ranks' outputs concatenate in S file order (exact compare);
+            # str / composite keys: hash partition => compare as multisets of rows
+            want[f"hashjoin{field}"] = (orc.rows_of(orc.hashjoin(f1, f2, field)), field in ("2", "3"))
+            want[f"mergejoin{field}"] = (orc.rows_of(orc.mergejoin(f1, f2, field)[0]), False)
+        for name in sorted(res):
+            base = name.split("_q")[0]
+            w, as_set = want[base]
+            got = np.concatenate([g[name] for g in gathered])
+            if as_set:
+                same = len(got) == len(w) and np.array_equal(np.sort(got.view("V140").astype("S140")), np.sort(w.view("V140").astype("S140")))
+            else:
+                same = got.tobytes() == w.tobytes()  # every row, all 140 bytes, in the global order
+            print(f"{name}: {'OK' if same else 'MISMATCH'} ({len(got)} rows; per rank {[len(g[name]) for g in gathered]})")
+            ok = ok and same
+        print("last op stats", st)
         print("DIST_CHECK_PASSED" if ok else "DIST_CHECK_FAILED")
+    d.barrier()
+    d.close()
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -361,3 +361,19 @@ def test_hashjoin_with_one_memory_block_mirrors_the_reference(dbt, orc, workdir)
         f1, f2 = workdir
         info, ref_out, _ = orc.run_ref("hjoin", "1", 1, f1, f2)
         assert info["a"] == 0 and info["nios"] == 2
+
+
+def test_config0_mergesort_file_of_1m_records_through_the_entry_point(dbt, orc, tmp_path, monkeypatch):
+    """BASELINE configs[0] through the real drop-in call: a 1M-record file (140 MB: several chunks of the file <-> pinned
+    <-> device pipeline in both directions), field num, nmem_blocks = 64.  Image bit-exact, counters = SURVEY Appendix B."""
+    monkeypatch.chdir(tmp_path)
+    f1 = orc.gen_ref(42, 10000, two=False)
+    f1.tofile("file.bin")
+    name, segs, passes, nios = call_mergesort(dbt, "file.bin", "1", 64)
+    assert (segs, passes, nios) == (161, 3, 30048) and name == "segment161.bin"
+    got = read_blocks(orc, name)
+    want = orc.sort(f1, "1")
+    assert H.same_image(got, want), H.first_diff(got, want)
+    u, nios = call_dedup(dbt, "file.bin", "1", 64, "nodup.bin")
+    want = orc.dedup(f1, "1")
+    assert u == orc.count_rows(want) and H.same_image(read_blocks(orc, "nodup.bin"), want)

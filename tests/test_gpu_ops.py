@@ -176,9 +176,10 @@ def test_hashjoin_wide_key_range_and_table_fallback(dbt, orc, monkeypatch):
         e["num"] = pool[rng.integers(0, len(pool), size=e["num"].shape)]
     want = orc.hashjoin(r, s, "1")
     assert 0 < orc.count_rows(want) < orc.count_rows(s)
+    monkeypatch.setenv("DBT_JOIN_FUSED", "1")
     got, n = H.dev_hashjoin(dbt, orc, r, s, "1")          # fused streaming semi-join over the full-range bitmap
     assert H.same_image(got, want), H.first_diff(got, want)
-    monkeypatch.setenv("DBT_JOIN_FUSED", "0")              # the column-based paths behind it:
+    monkeypatch.setenv("DBT_JOIN_FUSED", "0")              # the column-based paths:
     got, n = H.dev_hashjoin(dbt, orc, r, s, "1")          # sliced bitmap
     assert H.same_image(got, want), H.first_diff(got, want)
     monkeypatch.setenv("DBT_JOIN_NO_SLICES", "1")          # -> hash table (span too wide for the single bitmap)
@@ -380,9 +381,10 @@ def test_zipf_generator_is_zipf_and_reproducible_on_any_subrange(dbt, orc):
 
 
 def test_fused_semijoin_edge_cases(dbt, orc, monkeypatch):
-    """Fields '0'/'1' run HashJoin's probe as one streaming pass over S: ragged S blocks (the pass reads nreserved from
-    the block it streams), results that end exactly on a block boundary, empty results, capacity errors carrying the
-    needed size, and agreement with the column-based path."""
+    """DBT_JOIN_FUSED=1: fields '0'/'1' run HashJoin's probe as one streaming pass over S: ragged S blocks (the pass reads
+    nreserved from the block it streams), results that end exactly on a block boundary, empty results, capacity errors
+    carrying the needed size, and agreement with the column-based path."""
+    monkeypatch.setenv("DBT_JOIN_FUSED", "1")
     r, s = orc.gen_ref(77, 240, num_mod=4000)
     rng = np.random.default_rng(3)
     rag = s.copy()
