@@ -255,4 +255,6 @@ class Dist:
     def stats(self) -> dict:
         out = (C.c_double * 16)()
         check(self.L.dbt_dist_stats(self.h, out))
-        return {"nvlink_ms": out[0], "bytes_remote": out[1], "bytes_total": out[2], "sub_ranges": int(out[3])}
+        return {"nvlink_ms": out[0], "bytes_remote": out[1], "bytes_total": out[2], "sub_ranges": int(out[3]),
+                "timeline_ms": {"keys_extracted": round(out[4], 3), "splitters": round(out[5], 3), "pushes_enqueued": round(out[6], 3),
+                                "first_sub_range_done": round(out[7], 3), "done": round(out[8], 3)}}

@@ -90,7 +90,10 @@ struct dbt_dist {
     bool local = false; // ranks are threads of this process
     Ctl *ctl = nullptr;
     size_t ctl_bytes = 0;
-    cudaStream_t side = nullptr;
+    cudaStream_t side = nullptr; // pushes (lowest priority: link-bound, must not keep SMs from the owner-side work)
+    cudaStream_t work = nullptr; // owner-side operators on what has landed (highest priority)
+    cudaEvent_t ev_c = nullptr, ev_q[kMaxSub] = {};
+    Buf send[2]; // per-owner block images waiting for the copy engines
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     SharedBuf stag[2], keys, flags;
     Buf ws, lists;
@@ -184,6 +187,7 @@ static int ensure_shared(dbt_dist *d, SharedBuf &b, size_t need_bytes, cudaStrea
     for (int r = 0; r < d->world; ++r) mx = std::max<uint64_t>(mx, all[r]);
     if (b.own && b.cap >= mx) return 0; // the same decision on every rank: capacities are always set from mx
     DBT_CUDA(cudaStreamSynchronize(main));
+    DBT_CUDA(cudaStreamSynchronize(d->work));
     DBT_CUDA(cudaStreamSynchronize(d->side));
     DBT_TRY(host_barrier(d)); // nobody stores into the old buffers any more
     for (int r = 0; r < d->world; ++r) {
@@ -297,8 +301,13 @@ static int choose_splitters(dbt_dist *d, const std::vector<uint32_t> &mine, uint
     return 0;
 }
 
-// Group the rows by bucket, agree on the layout, grow the staging buffers if needed, and push: sub-range by sub-range on
-// the side stream, every launch spread over all owners, a flag to every owner after each sub-range.
+// Group the rows by bucket, agree on the layout, grow the buffers if needed, and move the records, sub-range by
+// sub-range: the SMs gather a sub-range's rows into one contiguous block image per owner (own rows straight into the own
+// staging buffer, the others into a send buffer), and the COPY ENGINES carry those images over NVLink on the side
+// stream while the SMs go on with the next sub-range -- and, after the last one, with the owner-side work on what has
+// already landed.  Measured on B200 (profiles/micro/p2p_scatter.cu): copy engine 780 GB/s per direction, 16-byte block
+// stores from SMs 716, 140-byte record stores 335, remote record reads 390; and a push kernel that shares the SMs with
+// the owner-side sort only alternates with it (profiles/r02_notes.md).  A flag to every owner follows each sub-range.
 static int exchange_push(dbt_dist *d, int slot, const void *d_in, Routed &r, int mode, uint32_t Q, const uint32_t *splitters,
                          cudaStream_t main, Layout *lay) {
     const uint32_t P = (uint32_t)d->world, nb = P * Q;
@@ -315,27 +324,57 @@ static int exchange_push(dbt_dist *d, int slot, const void *d_in, Routed &r, int
     for (uint32_t s = 0; s < P; ++s)
         for (uint32_t b = 0; b < 64; ++b) lay->cnt[s][b] = every[s][b];
     DIST_TRY(ensure_shared(d, d->stag[slot], (size_t)lay->total_blocks(d->rank) * DBT_BLOCK_BYTES + 256, main));
+    uint64_t send_blocks = 0;
+    for (uint32_t q = 0; q < Q && Q > 1; ++q)
+        for (uint32_t o = 0; o < P; ++o)
+            if ((int)o != d->rank) send_blocks += lay->seg_blocks(d->rank, o, q);
+    DIST_TRY(d->send[slot].ensure((size_t)send_blocks * DBT_BLOCK_BYTES + 256));
     const FlagPtrs fp = flag_ptrs(d);
-    DIST_CUDA(cudaEventRecord(d->ev_a, d->side));
     uint64_t row_off[64];
     row_off[0] = 0;
     for (uint32_t b = 1; b < nb; ++b) row_off[b] = row_off[b - 1] + r.counts[b - 1];
-    uint64_t remote = 0, total = 0;
+    uint64_t remote = 0, total = 0, send_off = 0;
+    bool first_copy = true;
+    const bool first_exchange = d->stats[2] == 0; // (joins exchange two relations: the NVLink phase starts with the first)
     for (uint32_t q = 0; q < Q; ++q) {
         PushPlan plan;
         memset(&plan, 0, sizeof plan);
         plan.nseg = P;
+        struct Copy {
+            void *dst;
+            const void *src;
+            size_t bytes;
+        } copies[kMaxRanks];
+        uint32_t ncopies = 0;
         for (uint32_t k = 0; k < P; ++k) {
-            const uint32_t owner = (d->rank + 1 + k) % P; // segment order rotated by rank: CTA i of every rank starts on a different owner
+            const uint32_t owner = (d->rank + 1 + k) % P; // rotated by rank: at any time the ranks copy to different owners
             const uint32_t b = owner * Q + q;
+            const size_t bytes = (size_t)lay->seg_blocks(d->rank, owner, q) * DBT_BLOCK_BYTES;
+            char *at_owner = (char *)d->stag[slot].peer[owner] + lay->seg_blk0(d->rank, owner, q) * DBT_BLOCK_BYTES;
             plan.seg[k].rows = r.rows + row_off[b];
             plan.seg[k].nrows = r.counts[b];
-            plan.seg[k].out = (uint4 *)((char *)d->stag[slot].peer[owner] + lay->seg_blk0(d->rank, owner, q) * DBT_BLOCK_BYTES);
-            const uint64_t bytes = lay->seg_blocks(d->rank, owner, q) * DBT_BLOCK_BYTES;
             total += bytes;
-            if ((int)owner != d->rank) remote += bytes;
+            if ((int)owner == d->rank || Q == 1) {
+                // my own rows need no copy; and with a single region nothing can overlap the transfer, so the gather
+                // kernel stores straight into the owner's staging buffer over NVLink (gather + exchange in one kernel:
+                // 10.3 ms instead of 6.7 + 9.0 for 7 GB per direction at P = 2)
+                plan.seg[k].out = (uint4 *)at_owner;
+                if ((int)owner != d->rank) remote += bytes;
+            } else {
+                plan.seg[k].out = (uint4 *)((char *)d->send[slot].p + send_off);
+                if (bytes) copies[ncopies++] = Copy{at_owner, (char *)d->send[slot].p + send_off, bytes};
+                send_off += bytes;
+                remote += bytes;
+            }
         }
-        DIST_TRY(launch_gather_push(d_in, r.p.row_slot, plan, d->side));
+        if (Q == 1 && first_copy && first_exchange) DIST_CUDA(cudaEventRecord(d->ev_a, main));
+        DIST_TRY(launch_gather_push(d_in, r.p.row_slot, plan, main));
+        DIST_CUDA(cudaEventRecord(d->ev_q[q], main));
+        DIST_CUDA(cudaStreamWaitEvent(d->side, d->ev_q[q], 0));
+        if (Q > 1 && first_copy && first_exchange) DIST_CUDA(cudaEventRecord(d->ev_a, d->side));
+        first_copy = false;
+        for (uint32_t c = 0; c < ncopies; ++c)
+            DIST_CUDA(cudaMemcpyAsync(copies[c].dst, copies[c].src, copies[c].bytes, cudaMemcpyDeviceToDevice, d->side));
         DIST_TRY(launch_signal(fp, P, (slot ? kFlagSlot1 : 0) + q * kMaxRanks + d->rank, d->epoch, d->side));
     }
     DIST_CUDA(cudaEventRecord(d->ev_b, d->side));
@@ -353,6 +392,7 @@ static int finish_op(dbt_dist *d, cudaStream_t main) {
     uint32_t err = 0;
     DIST_CUDA(cudaMemcpyAsync(&err, d->d_err, 4, cudaMemcpyDeviceToHost, main));
     DIST_CUDA(cudaStreamSynchronize(main));
+    DIST_CUDA(cudaStreamSynchronize(d->work));
     DIST_CUDA(cudaStreamSynchronize(d->side));
     stage_resolve();
     float ms = 0.f;
@@ -388,6 +428,10 @@ template <class F> static int dist_with_ws(dbt_dist *d, int op, uint64_t nbr, ui
         rc = call(d->ws.p, d->ws.cap);
     }
     return rc;
+}
+
+static double ms_since(std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 
 static uint32_t pick_sub_ranges(dbt_dist *d, uint64_t max_blocks) {
@@ -467,7 +511,12 @@ int dbt_dist_init(const char *session, int rank, int world, int device, dbt_dist
     int lo = 0, hi = 0;
     if (!rc && cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) lo = hi = 0;
     if (!rc && cudaStreamCreateWithPriority(&d->side, cudaStreamNonBlocking, lo) != cudaSuccess) rc = DBT_ERR_CUDA;
-    if (!rc && (cudaEventCreate(&d->ev_a) != cudaSuccess || cudaEventCreate(&d->ev_b) != cudaSuccess)) rc = DBT_ERR_CUDA;
+    if (!rc && cudaStreamCreateWithPriority(&d->work, cudaStreamNonBlocking, hi) != cudaSuccess) rc = DBT_ERR_CUDA;
+    if (!rc && (cudaEventCreate(&d->ev_a) != cudaSuccess || cudaEventCreate(&d->ev_b) != cudaSuccess ||
+                cudaEventCreateWithFlags(&d->ev_c, cudaEventDisableTiming) != cudaSuccess))
+        rc = DBT_ERR_CUDA;
+    for (uint32_t q = 0; q < kMaxSub && !rc; ++q)
+        if (cudaEventCreateWithFlags(&d->ev_q[q], cudaEventDisableTiming) != cudaSuccess) rc = DBT_ERR_CUDA;
     if (!rc && cudaMalloc((void **)&d->d_err, 256) != cudaSuccess) rc = DBT_ERR_CUDA;
     if (!rc && cudaMemset(d->d_err, 0, 256) != cudaSuccess) rc = DBT_ERR_CUDA;
     if (rc) {
@@ -500,6 +549,9 @@ int dbt_dist_init_local(int world, const int *devices, dbt_dist **out) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         DBT_CUDA(cudaStreamCreateWithPriority(&d->side, cudaStreamNonBlocking, lo));
+        DBT_CUDA(cudaStreamCreateWithPriority(&d->work, cudaStreamNonBlocking, hi));
+        DBT_CUDA(cudaEventCreateWithFlags(&d->ev_c, cudaEventDisableTiming));
+        for (uint32_t q = 0; q < kMaxSub; ++q) DBT_CUDA(cudaEventCreateWithFlags(&d->ev_q[q], cudaEventDisableTiming));
         DBT_CUDA(cudaEventCreate(&d->ev_a));
         DBT_CUDA(cudaEventCreate(&d->ev_b));
         DBT_CUDA(cudaMalloc((void **)&d->d_err, 256));
@@ -525,6 +577,12 @@ int dbt_dist_destroy(dbt_dist *d) {
     d->lists.release();
     if (d->d_err) cudaFree(d->d_err);
     if (d->side) cudaStreamDestroy(d->side);
+    if (d->work) cudaStreamDestroy(d->work);
+    if (d->ev_c) cudaEventDestroy(d->ev_c);
+    for (cudaEvent_t e : d->ev_q)
+        if (e) cudaEventDestroy(e);
+    d->send[0].release();
+    d->send[1].release();
     if (d->ev_a) cudaEventDestroy(d->ev_a);
     if (d->ev_b) cudaEventDestroy(d->ev_b);
     if (d->ctl) {
@@ -563,6 +621,7 @@ int dbt_dist_sort(dbt_dist *d, const void *d_in, uint64_t nblocks, int field, in
     }
     cudaStream_t main = (cudaStream_t)stream;
     DBT_TRY(begin_op(d, main));
+    const auto t_begin = std::chrono::steady_clock::now();
     const uint32_t P = (uint32_t)d->world;
     uint64_t nbs[kMaxRanks], mxb = 0;
     DIST_TRY(host_allgather(d, &nblocks, 8, nbs));
@@ -573,15 +632,19 @@ int dbt_dist_sort(dbt_dist *d, const void *d_in, uint64_t nblocks, int field, in
     uint32_t *d_carry = A.take<uint32_t>(256);
     Routed r;
     DIST_TRY(route_prepare(d, A, d_in, nblocks, field, main, &r));
+    d->stats[4] = ms_since(t_begin);
     std::vector<uint32_t> samp;
     DIST_TRY(take_samples(d, A, r, (uint32_t)std::min<uint64_t>(kSamplesPerRank, r.n), main, &samp));
     uint32_t splitters[64];
     DIST_TRY(choose_splitters(d, samp, P * Q, splitters));
+    d->stats[5] = ms_since(t_begin);
     Layout lay;
     DIST_TRY(exchange_push(d, 0, d_in, r, 0, Q, splitters, main, &lay));
     d->stats[3] = Q;
 
-    // ---- owner side: sub-range q is processed as soon as its P segments have landed ---------------------------
+    // ---- owner side: sub-range q is processed as soon as its P segments have landed (the copy engines keep moving the
+    // later sub-ranges meanwhile; the SMs are all ours) ------------------------------------------------------------
+    d->stats[6] = ms_since(t_begin);
     uint64_t carry = 0, out_blk = 0, n_in_total = 0;
     const uint64_t cap_rows = out_capacity_blocks * kRpb;
     for (uint32_t q = 0; q < Q; ++q) {
@@ -614,11 +677,14 @@ int dbt_dist_sort(dbt_dist *d, const void *d_in, uint64_t nblocks, int field, in
         });
         DIST_TRY(rc);
         n_in_total += n_in;
+        if (q == 0) d->stats[7] = ms_since(t_begin);
     }
     if (carry) DIST_TRY(gather_records(d->stag[0].own, d_carry, nullptr, carry, (char *)d_out + out_blk * DBT_BLOCK_BYTES, main, 0, (uint32_t)out_blk));
     if (out_rows) *out_rows = out_blk * kRpb + carry;
     if (rows_received) *rows_received = n_in_total;
-    return finish_op(d, main);
+    const int rc_fin = finish_op(d, (cudaStream_t)stream);
+    d->stats[8] = ms_since(t_begin);
+    return rc_fin;
 }
 
 int dbt_dist_hashjoin(dbt_dist *d, const void *d_r, uint64_t nbr, const void *d_s, uint64_t nbs, int field, void *d_out,

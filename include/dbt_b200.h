@@ -242,7 +242,9 @@ int dbt_dist_hashjoin(dbt_dist *d, const void *d_r, uint64_t nblocks_r, const vo
 int dbt_dist_mergejoin(dbt_dist *d, const void *d_r, uint64_t nblocks_r, const void *d_s, uint64_t nblocks_s, int field,
                        void *d_out, uint64_t out_capacity_blocks, void *stream, uint64_t *res /*[4]*/);
 /* last operator on this rank: [0] ms of the NVLink phase (first push .. last flag), [1] bytes stored into other GPUs,
- * [2] bytes stored in total (incl. own staging), [3] sub-ranges used */
+ * [2] bytes stored in total (incl. own staging), [3] sub-ranges used; sort/dedup host timeline in ms since the call:
+ * [4] routing keys extracted, [5] splitters agreed, [6] rows grouped and pushes enqueued, [7] first sub-range done,
+ * [8] everything done */
 int dbt_dist_stats(const dbt_dist *d, double out[16]);
 /* host-only self test of the control block (rendezvous, barriers, all-gathers, splitter choice, layout arithmetic);
  * no CUDA call: runs on machines without a GPU.  *checksum is identical on all ranks. */

@@ -57,7 +57,8 @@ for q in qs:
         gbs = st["bytes_remote"] / (st["nvlink_ms"] * 1e-3) / 1e9 if st["nvlink_ms"] else None
         print(json.dumps({"world": world, "rows_per_gpu": n, "field": field, "dedup": dedup, "sub_ranges": st["sub_ranges"], "ms": round(float(ms.item()), 3),
                           "records_per_s": n_total / (float(ms.item()) * 1e-3), "out_rows_total": int(tot.item()), "expected": U if dedup else n_total,
-                          "push_ms_rank0": round(st["nvlink_ms"], 3), "nvlink_gbs_per_direction_rank0": gbs}), flush=True)
+                          "push_ms_rank0": round(st["nvlink_ms"], 3), "nvlink_gbs_per_direction_rank0": gbs,
+                          "timeline_ms_rank0": st["timeline_ms"]}), flush=True)
 d.barrier()
 d.close()
 dist.barrier()

@@ -80,7 +80,7 @@ def main():
             w, as_set = want[base]
             got = np.concatenate([g[name] for g in gathered])
             if as_set:
-                same = len(got) == len(w) and np.array_equal(np.sort(got.view("V140").astype("S140")), np.sort(w.view("V140").astype("S140")))
+                same = len(got) == len(w) and sorted(x.tobytes() for x in got) == sorted(x.tobytes() for x in w)
             else:
                 same = got.tobytes() == w.tobytes()  # every row, all 140 bytes, in the global order
             print(f"{name}: {'OK' if same else 'MISMATCH'} ({len(got)} rows; per rank {[len(g[name]) for g in gathered]})")
