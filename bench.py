@@ -14,8 +14,10 @@ adjacent-difference unique -> one record gather into the output image.
   cpu_baseline  the untouched reference (oracle/_ref/ref_runner) on a bounded sample, 1 thread.
 
 `--impl reference` times the reference's own CPU implementation instead (rank 0 only).
-N>1 (torchrun): every rank holds its own 100M-row shard of one global relation; sample-sort splitters,
-one all-to-all of (key, row) pairs and one of the surviving records (see dist_ops.py).
+N>1 (torchrun): every rank holds its own 100M-row shard of one global relation; the C++ multi-GPU layer
+(csrc/dist.cu, dbt_dist_*) range-partitions it with sample-sort splitters and moves per-owner block images over NVLink
+with the copy engines, key sub-range by key sub-range; every result is checked in the run (bench_verify.py) and the
+BASELINE configs[2..4] run as verified legs.
 """
 from __future__ import annotations
 
@@ -145,10 +147,11 @@ def run_reference_arm(args):
 
 def workload_config(args, world):
     return {
-        "workload": f"EliminateDuplicates field=num, {args.rows} records per GPU, 10% duplicate rows (BASELINE configs[1]: 100M records, 1 B200)",
+        "workload": f"EliminateDuplicates field=num, {args.rows} records per GPU, 10% duplicate rows (BASELINE configs[1]: 100M records, 1 B200)"
+                    + (f"; reference arm: timed on a {args.ref_rows}-record sample of the same distribution" if getattr(args, "impl", "") == "reference" else ""),
         "rows_per_gpu": args.rows, "distinct_keys_per_gpu": (args.rows * 9) // 10, "nmem_blocks": NMEM,
         "key_bits": 32, "record_bytes": 140, "cache": "input image (14 GB at 100M rows) is far larger than the 126 MB L2; no flush needed",
-        "parallelism": "1 GPU" if world == 1 else f"{world} GPUs, sample-sort range partition + all-to-all",
+        "parallelism": "1 GPU" if world == 1 else f"{world} GPUs, sample-sort key ranges, one exchange of per-owner block images over NVLink (copy engines), pipelined by key sub-range",
     }
 
 
@@ -164,6 +167,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--leg-rows", type=int, default=0, help="N>1 legs: records per GPU of the configs[2]/[4] legs (default 125M)")
+    ap.add_argument("--join-r", type=int, default=0, help="N>1 legs: total R records of the configs[3] leg (default 100M)")
+    ap.add_argument("--join-s", type=int, default=0, help="N>1 legs: total S records of the configs[3] leg (default 1B)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
@@ -361,21 +367,52 @@ def main():
     return 0
 
 
+def _timed(torch, dist, dev, stream, fn, steps, warmup):
+    """W untimed + K timed calls of fn, CUDA events on `stream`, barrier + synchronize on both sides, max over ranks."""
+    out = None
+    for _ in range(warmup):
+        out = fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(steps):
+        out = fn()
+    e1.record(stream)
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item()) / steps, out
+
+
+def _ok(d: dict) -> bool:
+    return all(v for v in d.values() if isinstance(v, bool))
+
+
 def bench_dist(args, dbt, rank, world, local_rank):
-    """N>1: one global relation of N x rows records (10% duplicate rows globally), rank r holds rows
-    [r*rows, (r+1)*rows).  A step = distributed EliminateDuplicates: range-partition by sample-sort
-    splitters, one all-to-all of record images over NVLink, local dedup; the concatenation of the ranks'
-    outputs is the globally sorted duplicate-free file (weak scaling: rows per GPU fixed)."""
+    """N>1, one process per GPU.  Headline: one global relation of N x rows records (10% duplicate rows globally), rank r
+    holds rows [r*rows, (r+1)*rows); a step = distributed EliminateDuplicates through the C++ multi-GPU layer
+    (dbt_dist_sort: sample-sort splitters, per-owner block images carried over NVLink by the copy engines sub-range by
+    sub-range, the single-GPU operator on every landed sub-range); the concatenation of the ranks' outputs is the
+    globally sorted duplicate-free file (weak scaling: rows per GPU fixed).  torch.distributed (NCCL) does the contract's
+    barriers / max-over-ranks and the reductions of the independent result checks; it moves no record.
+    Legs (after the headline, each verified in the run): BASELINE configs[2] MergeSort field=str (125M records per GPU =
+    1B at 8), configs[3] HashJoin field=num R=100M x S=1B split over the GPUs (strong scaling), uniform and Zipf(1.1),
+    configs[4] MergeJoin field=num+str (62.5M + 62.5M records per GPU = 2 x 500M at 8), and a small instance of every
+    operator compared bit for bit with the CPU oracle."""
     import ctypes as C
 
     import torch
     import torch.distributed as dist
 
-    dmod = importlib.import_module("database-technology-algorithms_b200.dist")
+    import bench_verify as V
+
     L = dbt.lib()
     dev = torch.device("cuda", local_rank)
-    ops = dmod.LocalOps(dev)
-    d = dmod.DistOps(ops)
+    tok = [f"{os.environ.get('MASTER_PORT', '0')}_{os.getpid()}_{int(time.time() * 1e3) % 1000000}"]
+    dist.broadcast_object_list(tok, src=0)
+    d = dbt.Dist(tok[0], rank, world, local_rank)
     peak, peak_src = load_peaks()
     n = args.rows
     n_total = n * world
@@ -383,129 +420,299 @@ def bench_dist(args, dbt, rank, world, local_rank):
     nblocks = (n + RPB - 1) // RPB
     img_bytes = nblocks * BLOCK_BYTES
     stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+    steps, warmup = args.steps, max(args.warmup, 3)
     d_in = torch.empty(img_bytes, dtype=torch.uint8, device=dev)
-    dbt.check(L.dbt_gen_syn(42, n_total, U, 0, rank * n, n, 0, d_in.data_ptr(), stream.cuda_stream))
+    dbt.check(L.dbt_gen_syn(42, n_total, U, 0, rank * n, n, 0, d_in.data_ptr(), sp))
+    cap = nblocks + nblocks // 4 + 64  # splitters come from a sample: leave headroom for an uneven cut
+    d_out = torch.empty(cap * BLOCK_BYTES, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
 
     def step():
-        out, info = d.dedup(d_in, nblocks, FIELD)
-        return out, info
+        return d.sort(d_in.data_ptr(), nblocks, FIELD, True, d_out.data_ptr(), cap, sp)
 
-    for _ in range(max(args.warmup, 3)):
-        out, info = step()
-    got = d.total(info["out_rows"])
-    assert got == U, f"wrong global result: {got} unique rows, expected {U}"
-    del out
-
+    for _ in range(warmup):
+        out_rows, _ = step()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         L.dbt_stage_timing_enable(1)
         L.dbt_stage_timing_reset()
     launches0 = L.dbt_kernel_launches()
-    xms, xbytes = [], 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dist.barrier()
-    torch.cuda.synchronize()
-    e0.record(stream)
-    for _ in range(args.steps):
-        out, info = step()
-        ev = d.last_exchange.get("gather_events") or d.last_exchange["events"]
-        xbytes = d.last_exchange.get("remote_record_bytes_read") or d.last_exchange["bytes_sent_remote"]
-        xms.append(ev)
-        del out
-    e1.record(stream)
-    dist.barrier()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_step = float(ms.item()) / args.steps
+    ms_step, (out_rows, recv_rows) = _timed(torch, dist, dev, stream, step, steps, 0)
     launches = int(L.dbt_kernel_launches() - launches0)
-    a2a_ms = sum(a.elapsed_time(b) for a, b in xms) / len(xms)
-    a2a = torch.tensor([a2a_ms, float(xbytes)], device=dev, dtype=torch.float64)
-    dist.all_reduce(a2a, op=dist.ReduceOp.MAX)
-    stages, clocks = {}, None
-    timeline = None
-    if rank == 0 and "timeline" in d.last_exchange:
-        tl = d.last_exchange["timeline"]
-        timeline = {name: round(tl[0][1].elapsed_time(e), 3) for name, e in tl}
-        pe = d.last_exchange["events"]
-        timeline["push_start"] = round(tl[0][1].elapsed_time(pe[0]), 3)
-        timeline["push_end"] = round(tl[0][1].elapsed_time(pe[1]), 3)
+    st = d.stats()
+    stages = dbt.stage_report() if rank == 0 else {}
     if rank == 0:
-        stages = dbt.stage_report()
         L.dbt_stage_timing_enable(0)
-        clocks = sampler.stop()
     value = n_total / (ms_step * 1e-3)
+    x = torch.tensor([st["nvlink_ms"], st["bytes_remote"]], device=dev, dtype=torch.float64)
+    dist.all_reduce(x, op=dist.ReduceOp.MAX)
+    nv_ms, nv_bytes = float(x[0].item()), float(x[1].item())
 
-    # e2e: pinned host shard in, pinned host result out, copies inside the timed region (per rank)
+    # ---- independent check of the headline result (torch only, full size) ------------------------------
+    checks = {}
+    try:
+        checks["cfg1_dedup_num"] = V.check_dedup_u32(d_in, n, d_out, out_rows, 1, dist)
+        checks["cfg1_dedup_num"]["rows_expected"] = U
+        checks["cfg1_dedup_num"]["count_ok"] = checks["cfg1_dedup_num"]["rows"] == U
+    except Exception as e:  # noqa: BLE001
+        checks["cfg1_dedup_num"] = {"error": str(e)[:160]}
+    torch.cuda.empty_cache()
+
+    # ---- e2e: pinned host shard in, pinned host result out, every step's copies inside the timed region; the upload of
+    # step i+1 and the download of step i-1 run on their own streams under step i's operator ---------------------------
     e2e = None
     if not args.no_e2e:
-        try:
-            import psutil
+        e2e = e2e_dist(args, dbt, d, torch, dist, dev, d_in, nblocks, cap, n_total, world, U)
+    clocks = sampler.stop() if rank == 0 else None
+    del d_in, d_out
+    torch.cuda.empty_cache()
 
-            avail = psutil.virtual_memory().available
-        except Exception:  # noqa: BLE001
-            avail = 0
-        need = 2 * img_bytes * world * 1.25
-        if avail > need:
-            h_in = torch.empty(img_bytes, dtype=torch.uint8).pin_memory()
-            h_out = torch.empty(img_bytes + img_bytes // 4, dtype=torch.uint8).pin_memory()
-            h_in.copy_(d_in)
-            d_stage = torch.empty_like(d_in)
+    legs = {}
+    if not args.no_extra:
+        legs = dist_legs(args, dbt, d, torch, dist, V, dev, rank, world, checks)
 
-            def e2e_step():
-                d_stage.copy_(h_in, non_blocking=True)
-                o, inf = d.dedup(d_stage, nblocks, FIELD)
-                nb_out = (inf["out_rows"] + RPB - 1) // RPB
-                h_out[: nb_out * BLOCK_BYTES].copy_(o[: nb_out * BLOCK_BYTES], non_blocking=True)
-                torch.cuda.synchronize()
-                return nb_out * BLOCK_BYTES
-
-            e2e_step()
-            dist.barrier()
-            t0 = time.perf_counter()
-            ob = 0
-            for _ in range(args.steps):
-                ob = e2e_step()
-            dist.barrier()
-            sec = torch.tensor([(time.perf_counter() - t0) / args.steps], device=dev, dtype=torch.float64)
-            dist.all_reduce(sec, op=dist.ReduceOp.MAX)
-            e2e = {"value": n_total / float(sec.item()), "unit": "records/s", "h2d_bytes_per_step": img_bytes * world,
-                   "d2h_bytes_per_step": ob * world, "ms_per_step": float(sec.item()) * 1e3,
-                   "api": "pinned host shard -> DistOps.dedup (C-ABI kernels + NCCL all-to-all) -> pinned host result, per rank"}
-        else:
-            e2e = {"value": None, "unit": "records/s", "h2d_bytes_per_step": img_bytes * world, "d2h_bytes_per_step": None,
-                   "skipped": f"needs {need/1e9:.0f} GB of pinned host memory, {avail/1e9:.0f} GB available"}
-
+    all_ok = all(_ok(c) for c in checks.values())  # a comparison that came out wrong fails the run; a check that could not run is reported
     if rank == 0:
         dom = max(stages.items(), key=lambda kv: kv[1][0])[0] if stages else None
         roofline = None
         if dom == "record_gather":
-            # per step on this rank: the P per-destination gathers (n rows) + the final gather (rows received, ~0.9 n)
-            ms_dom = stages[dom][0] / args.steps
-            rows_moved = n + info["out_rows"]
+            # per step on this rank: the per-owner gathers of its n rows + the owner-side gathers of the rows it emits
+            ms_dom = stages[dom][0] / steps
+            rows_moved = n + out_rows
             achieved = 280.0 * rows_moved / (ms_dom * 1e-3) / 1e9
             roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": load_traffic(dom), "peak_source": peak_src, "ms_per_step_all_launches": ms_dom,
-                        "algorithmic_bytes_per_step": 280.0 * rows_moved}
-        nvlink = {"exchange": d.last_exchange.get("mode"),
-                  "what": "record bytes crossing NVLink per GPU per step, and the duration of the phase that moves them (max over ranks)",
-                  "bytes_sent_per_gpu": float(a2a[1].item()), "all_to_all_ms": float(a2a[0].item()),
-                  "achieved_gbs_per_direction": float(a2a[1].item()) / (float(a2a[0].item()) * 1e-3) / 1e9 if a2a[0].item() > 0 else None,
-                  "peak_gbs_per_direction": 770.0, "peak_source": "B200_PROFILING.md measured peer copy"}
+                        "traffic": None, "traffic_note": "no ncu capture of the multi-GPU step (ncu is single-GPU only here)",
+                        "peak_source": peak_src, "ms_per_step_all_launches": ms_dom, "algorithmic_bytes_per_step": 280.0 * rows_moved}
+        nvlink = {"what": "record bytes this GPU sends to the other GPUs per step (copy engines, per-owner block images) and the "
+                          "duration of that phase, first copy .. last flag (max over ranks)",
+                  "bytes_sent_per_gpu": nv_bytes, "phase_ms": nv_ms, "sub_ranges": st["sub_ranges"],
+                  "achieved_gbs_per_direction": nv_bytes / (nv_ms * 1e-3) / 1e9 if nv_ms > 0 else None,
+                  "peak_gbs_per_direction": 780.0, "peak_source": "profiles/micro/p2p_scatter.cu: cudaMemcpyPeer between two B200 of this pool"}
+        summary = {"checks_ok": all_ok, "check_errors": sum(1 for c in checks.values() if "error" in c),
+                   "cfg1": {"ms": round(ms_step, 2), "Grec_s": round(value / 1e9, 2), "ok": _ok(checks.get("cfg1_dedup_num", {}))}}
+        for k, v in legs.items():
+            summary[k] = {a: b for a, b in v.items() if a in ("ms", "Grec_s", "Gtup_s", "ok", "rows", "nres", "error", "skipped")}
         line = {
-            "metric": "records_per_second", "value": value, "unit": "records/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "metric": "records_per_second", "value": value, "unit": "records/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": workload_config(args, world),
-            "e2e": e2e, "roofline": roofline, "nvlink": nvlink, "cpu_baseline": None, "clocks": clocks,
-            "gpu_launches": launches, "stage_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in stages.items()},
-            "timeline_ms_last_step_rank0": timeline,
+            "e2e": e2e, "roofline": roofline, "cpu_baseline": None, "clocks": clocks, "gpu_launches": launches,
+            "nvlink": nvlink, "stage_ms_per_step": {k: round(v[0] / steps, 4) for k, v in stages.items()},
+            "timeline_ms_last_step_rank0": st["timeline_ms"], "checks": checks, "legs": legs, "summary": summary,
         }
         print(json.dumps(line))
+    d.barrier()
+    d.close()
     dist.barrier()
     dist.destroy_process_group()
-    return 0
+    return 0 if all_ok else 1
+
+
+def e2e_dist(args, dbt, d, torch, dist, dev, d_in, nblocks, cap, n_total, world, U):
+    """Every rank: pinned host shard -> device -> distributed dedup -> pinned host result, all inside the timed region.
+    Two device input buffers and two output buffers: step i+1's upload and step i-1's download run on their own streams
+    while step i's operator runs (PCIe is full duplex; the operator itself takes ~25 ms of a ~300 ms step)."""
+    img_bytes = nblocks * BLOCK_BYTES
+    try:
+        import psutil
+
+        avail = psutil.virtual_memory().available
+    except Exception:  # noqa: BLE001
+        avail = 0
+    out_bytes = cap * BLOCK_BYTES
+    need = (img_bytes + out_bytes) * world * 1.15
+    free_dev, _ = torch.cuda.mem_get_info(dev)
+    if avail < need or free_dev < 2 * img_bytes + 2 * out_bytes + (8 << 30):
+        return {"value": None, "unit": "records/s", "h2d_bytes_per_step": img_bytes * world, "d2h_bytes_per_step": None,
+                "skipped": f"needs {need / 1e9:.0f} GB of pinned host memory ({avail / 1e9:.0f} available) and "
+                           f"{(2 * img_bytes + 2 * out_bytes) / 1e9:.0f} GB of device memory ({free_dev / 1e9:.0f} free)"}
+    h_in = torch.empty(img_bytes, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(out_bytes, dtype=torch.uint8).pin_memory()
+    h_in.copy_(d_in)
+    bufs_in = [d_in, torch.empty_like(d_in)]
+    bufs_out = [torch.empty(out_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+    s_up, s_down = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream()
+    sp = main.cuda_stream
+
+    def run(steps):
+        up = [None, None]
+        down = [None, None]
+        with torch.cuda.stream(s_up):
+            bufs_in[0].copy_(h_in, non_blocking=True)
+            up[0] = s_up.record_event()
+        out_b = 0
+        for i in range(steps):
+            k = i & 1
+            if i + 1 < steps:  # next step's input comes in under this step's operator
+                if down[k ^ 1] is not None:
+                    pass  # (its input buffer was consumed by step i-1, which has returned)
+                with torch.cuda.stream(s_up):
+                    bufs_in[k ^ 1].copy_(h_in, non_blocking=True)
+                    up[k ^ 1] = s_up.record_event()
+            main.wait_event(up[k])
+            if down[k] is not None:
+                main.wait_event(down[k])  # the output buffer of step i-2 is home
+            rows, _ = d.sort(bufs_in[k].data_ptr(), nblocks, FIELD, True, bufs_out[k].data_ptr(), cap, sp)  # returns when done
+            assert rows > 0
+            nb_out = (rows + RPB - 1) // RPB
+            out_b = nb_out * BLOCK_BYTES
+            with torch.cuda.stream(s_down):  # (one host buffer: the downloads are ordered on their stream)
+                h_out[:out_b].copy_(bufs_out[k][:out_b], non_blocking=True)
+                down[k] = s_down.record_event()
+        torch.cuda.synchronize()
+        return out_b
+
+    run(2)
+    dist.barrier()
+    t0 = time.perf_counter()
+    ob = run(args.steps)
+    dist.barrier()
+    sec = torch.tensor([(time.perf_counter() - t0) / args.steps], device=dev, dtype=torch.float64)
+    dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+    tot = torch.tensor([ob], device=dev, dtype=torch.float64)
+    dist.all_reduce(tot)
+    del h_in, h_out, bufs_out
+    return {"value": n_total / float(sec.item()), "unit": "records/s", "h2d_bytes_per_step": img_bytes * world,
+            "d2h_bytes_per_step": float(tot.item()), "ms_per_step": float(sec.item()) * 1e3,
+            "api": "per rank: pinned host shard -> cudaMemcpyAsync -> dbt_dist_sort (C-ABI, dedup) -> cudaMemcpyAsync -> pinned host "
+                   "result; uploads and downloads of neighbouring steps overlap the operator on their own streams"}
+
+
+def dist_legs(args, dbt, d, torch, dist, V, dev, rank, world, checks):
+    """BASELINE configs[2..4] at the scale the GPU count allows, each timed (3 steps after 1 warm-up, CUDA events, max
+    over ranks) and checked in the run, plus a small instance of every operator against the CPU oracle."""
+    import ctypes as C
+
+    L = dbt.lib()
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+    legs = {}
+
+    def gen(seed, n_total, U, kind, row0, nrows):
+        nb = (nrows + RPB - 1) // RPB
+        t = torch.empty(nb * BLOCK_BYTES, dtype=torch.uint8, device=dev)
+        dbt.check(L.dbt_gen_syn(seed, n_total, U, kind, row0, nrows, 0, t.data_ptr(), sp))
+        torch.cuda.synchronize()
+        return t, nb
+
+    def agree(local_error):
+        """A leg that failed on one rank must be abandoned by all of them (the operators are collective)."""
+        f = torch.tensor([1 if local_error else 0], device=dev)
+        dist.all_reduce(f, op=dist.ReduceOp.MAX)
+        return bool(f.item())
+
+    # ---- configs[2]: MergeSort field=str, 125M records per GPU (1B at 8 GPUs) --------------------------------------
+    try:
+        d.trim()
+        n2 = args.leg_rows or 125_000_000
+        img, nb = gen(77, n2 * world, n2 * world, 1, rank * n2, n2)
+        cap = nb + nb // 4 + 64
+        out = torch.empty(cap * BLOCK_BYTES, dtype=torch.uint8, device=dev)
+        ms, (rows, _) = _timed(torch, dist, dev, stream, lambda: d.sort(img.data_ptr(), nb, "2", False, out.data_ptr(), cap, sp), 3, 1)
+        st = d.stats()
+        chk = V.check_sort(img, n2, out, rows, V.str_key64, dist)
+        checks["cfg2_sort_str"] = chk
+        legs["cfg2_sort_str"] = {"workload": f"MergeSort field=str, {n2} records per GPU x {world} GPUs = {n2 * world} records (BASELINE configs[2]: 1B on 8)",
+                                 "ms": round(ms, 2), "Grec_s": round(n2 * world / ms / 1e6, 2), "rows": chk["rows"], "ok": _ok(chk),
+                                 "nvlink_gbs_per_direction": round(st["bytes_remote"] / max(st["nvlink_ms"], 1e-9) / 1e6, 1), "timeline_ms": st["timeline_ms"]}
+        del img, out
+    except Exception as e:  # noqa: BLE001
+        legs["cfg2_sort_str"] = {"error": str(e)[:200]}
+    torch.cuda.empty_cache()
+
+    # ---- configs[3]: HashJoin field=num, R = 100M x S = 1B over the GPUs (strong scaling), uniform and Zipf(1.1) -------
+    for kind, label in ((1, "uniform"), (4, "zipf1.1")):
+        name = f"cfg3_hashjoin_{label}"
+        try:
+            d.trim()
+            NR, NS, D = args.join_r or 100_000_000, args.join_s or 1_000_000_000, 100_000_000
+            nr, ns = NR // world // RPB * RPB, NS // world // RPB * RPB
+            r_img, nbr = gen(7, NR, D, 1, rank * nr, nr)
+            s_img, nbs = gen(9, NS, D, kind, rank * ns, ns)
+            cap = int(nbs * 0.78) + 64
+            out = torch.empty(cap * BLOCK_BYTES, dtype=torch.uint8, device=dev)
+            ms, k = _timed(torch, dist, dev, stream,
+                           lambda: d.hashjoin(r_img.data_ptr(), nbr, s_img.data_ptr(), nbs, "1", out.data_ptr(), cap, sp), 3, 1)
+            chk = V.check_semijoin_u32(r_img, nr, s_img, ns, out, k, 1, D, dist)
+            checks[name] = chk
+            legs[name] = {"workload": f"HashJoin field=num, R={nr * world} x S={ns * world} records over {world} GPUs, S keys {label} over [0,1e8) "
+                                      "(BASELINE configs[3]); semi-join: S rows in S order whose key is in keys(R)",
+                          "ms": round(ms, 2), "Gtup_s": round(ns * world / ms / 1e6, 2), "nres": chk["rows"], "ok": _ok(chk)}
+            del r_img, s_img, out
+        except Exception as e:  # noqa: BLE001
+            legs[name] = {"error": str(e)[:200]}
+        torch.cuda.empty_cache()
+
+    # ---- configs[4]: MergeJoin field=num+str, 62.5M + 62.5M records per GPU (2 x 500M at 8 GPUs) ---------------------
+    try:
+        d.trim()
+        n4 = args.leg_rows // 2 if args.leg_rows else 62_500_000
+        U4 = max(1000, int(0.3 * n4 * world))
+        r_img, nb = gen(21, n4 * world, U4, 1, rank * n4, n4)
+        s_img, _ = gen(21 ^ 0x5EED, n4 * world, U4, 3, rank * n4, n4)
+        cap = nb + nb // 4 + 64
+        out = torch.empty(cap * BLOCK_BYTES, dtype=torch.uint8, device=dev)
+        ms, info = _timed(torch, dist, dev, stream,
+                          lambda: d.mergejoin(r_img.data_ptr(), nb, s_img.data_ptr(), nb, "3", out.data_ptr(), cap, sp), 3, 1)
+        chk = V.check_mergejoin_composite(r_img, n4, s_img, n4, out, info["nres"], dist)
+        checks["cfg4_mergejoin_numstr"] = chk
+        legs["cfg4_mergejoin_numstr"] = {"workload": f"MergeJoin field=num+str, 2 x {n4 * world} records over {world} GPUs (BASELINE configs[4]: 2 x 500M on 8)",
+                                         "ms": round(ms, 2), "Gtup_s": round(2 * n4 * world / ms / 1e6, 2), "nres": chk["rows"], "ok": _ok(chk)}
+        del r_img, s_img, out
+    except Exception as e:  # noqa: BLE001
+        legs["cfg4_mergejoin_numstr"] = {"error": str(e)[:200]}
+    torch.cuda.empty_cache()
+
+    # ---- a small instance of every operator, bit for bit against the CPU oracle (rank 0 runs the oracle) -----------
+    try:
+        d.trim()
+        from oracle import pyoracle as orc  # checker only
+
+        import numpy as np
+
+        nloc = 20_000
+        nbl = nloc // RPB
+        r_img, _ = gen(5, nloc * world, nloc * world // 3, 1, rank * nloc, nloc)
+        s_img, _ = gen(5 ^ 0x5EED, nloc * world, nloc * world // 3, 3, rank * nloc, nloc)
+        cap = nbl * world + 8
+        out = torch.empty(cap * BLOCK_BYTES, dtype=torch.uint8, device=dev)
+        got = {}
+
+        def rows_of(k):
+            nbk = (k + RPB - 1) // RPB
+            return out[: nbk * BLOCK_BYTES].cpu().numpy().tobytes(), k
+
+        k, _ = d.sort(r_img.data_ptr(), nbl, "3", False, out.data_ptr(), cap, sp)
+        got["sort3"] = rows_of(k)
+        k, _ = d.sort(r_img.data_ptr(), nbl, "1", True, out.data_ptr(), cap, sp)
+        got["dedup1"] = rows_of(k)
+        k = d.hashjoin(r_img.data_ptr(), nbl, s_img.data_ptr(), nbl, "1", out.data_ptr(), cap, sp)
+        got["hashjoin1"] = rows_of(k)
+        k = d.mergejoin(r_img.data_ptr(), nbl, s_img.data_ptr(), nbl, "3", out.data_ptr(), cap, sp)["nres"]
+        got["mergejoin3"] = rows_of(k)
+        every = [None] * world
+        dist.all_gather_object(every, got)
+        res = {}
+        if rank == 0:
+            orc.build()
+            R = orc.gen_syn(5, nloc * world, nloc * world // 3, 1)
+            S = orc.gen_syn(5 ^ 0x5EED, nloc * world, nloc * world // 3, 3)
+            want = {"sort3": orc.sort(R, "3"), "dedup1": orc.dedup(R, "1"), "hashjoin1": orc.hashjoin(R, S, "1"),
+                    "mergejoin3": orc.mergejoin(R, S, "3")[0]}
+            for name, w in want.items():
+                rows = [orc.rows_of(orc.as_blocks(np.frombuffer(g[name][0], dtype=np.uint8).copy()))[: g[name][1]] for g in every]
+                res[name] = np.concatenate(rows).tobytes() == orc.rows_of(w).tobytes()  # every row, all 140 bytes, global order
+        checks["oracle_small"] = res if rank == 0 else {"rank": True}
+        legs["oracle_small"] = {"workload": f"{nloc} records per GPU: sort field 3, dedup field 1, hashjoin field 1, mergejoin field 3 vs oracle/dbt_oracle.c, all 140 bytes of every row",
+                                "ok": _ok(res) if rank == 0 else True}
+        del r_img, s_img, out
+    except Exception as e:  # noqa: BLE001
+        legs["oracle_small"] = {"error": str(e)[:200]}
+    torch.cuda.empty_cache()
+    return legs
 
 
 def load_traffic(kernel: str):

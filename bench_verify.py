@@ -27,7 +27,7 @@ def column(img_u8, nrows: int, word: int):
     if nb == 0:
         return torch.zeros(0, dtype=torch.int64, device=img_u8.device)
     t = _words(img_u8, nb)
-    v = torch.as_strided(t, (nb, RPB), (BLOCK_WORDS, REC_WORDS), 2 + word)
+    v = torch.as_strided(t, (nb, RPB), (BLOCK_WORDS, REC_WORDS), t.storage_offset() + 2 + word)  # (as_strided offsets are absolute)
     return (v.reshape(-1)[:nrows].to(torch.int64)) & _MASK32
 
 
@@ -68,7 +68,7 @@ def row_hashes(img_u8, nrows: int, chunk_blocks: int = 32768):
     t = _words(img_u8, nb)
     for b0 in range(0, nb, chunk_blocks):
         b1 = min(nb, b0 + chunk_blocks)
-        v = torch.as_strided(t, (b1 - b0, RPB, REC_WORDS), (BLOCK_WORDS, REC_WORDS, 1), 2 + b0 * BLOCK_WORDS)
+        v = torch.as_strided(t, (b1 - b0, RPB, REC_WORDS), (BLOCK_WORDS, REC_WORDS, 1), t.storage_offset() + 2 + b0 * BLOCK_WORDS)
         h = ((v.to(torch.int64) & _MASK32) * _W).sum(-1)
         h = (h ^ (h >> 29)) * -4658895280553007687  # 0xBF58476D1CE4E5B9 as int64
         h = h ^ (h >> 32)
@@ -137,28 +137,42 @@ def check_dedup_u32(in_img, n_in: int, out_img, n_out: int, word: int, dist=None
             "rows": rows_out, "distinct_keys_in_input": distinct, "record_multiset_hash_equal": h_in == h_out and rows_out == distinct}
 
 
-def check_semijoin_u32(r_img, n_r: int, s_img, n_s: int, out_img, n_out: int, word: int, domain: int, dist=None):
+def check_semijoin_u32(r_img, n_r: int, s_img, n_s: int, out_img, n_out: int, word: int, domain: int, dist=None,
+                       chunk_rows: int = 50_000_000):
     """HashJoin fields '0'/'1' (set semantics): the output is exactly the S rows, in S file order, whose key is in
-    keys(R) -- compared row by row, all 140 bytes, against a torch boolean-table filter of the S shard."""
+    keys(R) -- compared row by row, all 140 bytes, against a torch boolean-table filter of the S shard (S is walked
+    in chunks of whole blocks so that the temporaries stay small)."""
     dev = s_img.device
     table = torch.zeros(domain, dtype=torch.uint8, device=dev)
     kr = column(r_img, n_r, word)
-    table[kr] = 1
+    table[kr[kr < domain]] = 1
     if dist is not None:
         dist.all_reduce(table, op=dist.ReduceOp.MAX)
-    ks = column(s_img, n_s, word)
-    inside = ks < domain
-    mask = torch.zeros(n_s, dtype=torch.bool, device=dev)
-    mask[inside] = table[ks[inside]].bool()
-    want = int(mask.sum().item())
-    same_count = want == n_out
-    same_rows = False
-    if same_count:
-        hs = row_hashes(s_img, n_s)[mask]
-        ho = row_hashes(out_img, n_out)
-        same_rows = bool((hs == ho).all().item())  # position by position: same rows in the same (S file) order
+    del kr
+    chunk_rows = max(RPB, chunk_rows // RPB * RPB)
+    want, same_rows, pos = 0, True, 0
+    for r0 in range(0, n_s, chunk_rows):
+        m = min(chunk_rows, n_s - r0)
+        sub = s_img[(r0 // RPB) * BLOCK_WORDS * 4:]
+        ks = column(sub, m, word)
+        inside = ks < domain
+        mask = torch.zeros(m, dtype=torch.bool, device=dev)
+        mask[inside] = table[ks[inside]].bool()
+        k = int(mask.sum().item())
+        want += k
+        if same_rows and pos + k <= n_out and k:
+            hs = row_hashes(sub, m)[mask]
+            # output rows [pos, pos + k): they start in the middle of an output block, so hash a block-aligned window
+            b0 = pos // RPB
+            ho = row_hashes(out_img[b0 * BLOCK_WORDS * 4:], (pos - b0 * RPB) + k)[pos - b0 * RPB:]
+            same_rows = bool((hs == ho).all().item())  # position by position: same rows in the same (S file) order
+            del hs, ho
+        elif pos + k > n_out:
+            same_rows = False
+        pos += k
+        del ks, inside, mask
     del table
-    return {"rows": _allsum(n_out, dist, dev), "rows_expected": _allsum(want, dist, dev), "same_rows_in_s_order": same_rows and same_count}
+    return {"rows": _allsum(n_out, dist, dev), "rows_expected": _allsum(want, dist, dev), "same_rows_in_s_order": same_rows and want == n_out}
 
 
 def check_mergejoin_composite(r_img, n_r: int, s_img, n_s: int, out_img, n_out: int, dist=None):

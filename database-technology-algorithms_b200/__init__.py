@@ -36,7 +36,7 @@ C_ABI_SYMBOLS = [
     "dbt_host_mergesort_begin", "dbt_host_dedup_begin", "dbt_host_mergejoin_begin", "dbt_host_hashjoin_begin",
     "dbt_host_job_wait", "dbt_host_job_slots", "dbt_host_trim", "dbt_host_set_chunk_blocks", "dbt_host_ooc_stats",
     "dbt_host_alloc", "dbt_host_free", "dbt_gen_syn",
-    "dbt_dist_init", "dbt_dist_init_local", "dbt_dist_destroy", "dbt_dist_rank", "dbt_dist_world", "dbt_dist_barrier",
+    "dbt_dist_init", "dbt_dist_init_local", "dbt_dist_destroy", "dbt_dist_rank", "dbt_dist_world", "dbt_dist_barrier", "dbt_dist_trim",
     "dbt_dist_set_sub_ranges", "dbt_dist_allgather_host", "dbt_dist_sort", "dbt_dist_hashjoin", "dbt_dist_mergejoin",
     "dbt_dist_stats", "dbt_dist_selftest_host",
     "dbt_stage_timing_enable", "dbt_stage_timing_reset", "dbt_stage_count", "dbt_stage_name", "dbt_stage_ms",
@@ -135,6 +135,7 @@ def lib() -> C.CDLL:
     L.dbt_dist_rank.argtypes = [vp]
     L.dbt_dist_world.argtypes = [vp]
     L.dbt_dist_barrier.argtypes = [vp]
+    L.dbt_dist_trim.argtypes = [vp]
     L.dbt_dist_set_sub_ranges.argtypes = [vp, u32]
     L.dbt_dist_allgather_host.argtypes = [vp, vp, sz, vp]
     L.dbt_dist_sort.argtypes = [vp, vp, u64, ci, ci, vp, u64, vp, pu64, pu64]
@@ -232,6 +233,9 @@ class Dist:
 
     def barrier(self):
         check(self.L.dbt_dist_barrier(self.h))
+
+    def trim(self):
+        check(self.L.dbt_dist_trim(self.h))
 
     def set_sub_ranges(self, q: int):
         check(self.L.dbt_dist_set_sub_ranges(self.h, q))

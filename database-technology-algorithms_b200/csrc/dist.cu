@@ -602,6 +602,31 @@ int dbt_dist_set_sub_ranges(dbt_dist *d, uint32_t q) {
     d->nsub = q; // 0 = automatic
     return 0;
 }
+// Collective: release the staging, send, list and workspace buffers (they are grown again on demand).  Callers that go
+// from one large workload to a differently shaped one use it to get the memory back.
+int dbt_dist_trim(dbt_dist *d) {
+    if (!d) return DBT_ERR_ARG;
+    DBT_CUDA(cudaSetDevice(d->device));
+    DBT_CUDA(cudaDeviceSynchronize());
+    DBT_TRY(host_barrier(d)); // nobody stores into my buffers any more
+    for (SharedBuf *b : {&d->stag[0], &d->stag[1], &d->keys}) {
+        for (int r = 0; r < d->world; ++r) {
+            if (r != d->rank && b->peer[r] && !d->local) cudaIpcCloseMemHandle(b->peer[r]);
+            b->peer[r] = nullptr;
+        }
+    }
+    DBT_TRY(host_barrier(d)); // every mapping of my buffers is closed
+    for (SharedBuf *b : {&d->stag[0], &d->stag[1], &d->keys}) {
+        if (b->own) cudaFree(b->own);
+        b->own = nullptr;
+        b->cap = 0;
+    }
+    d->send[0].release();
+    d->send[1].release();
+    d->ws.release();
+    d->lists.release();
+    return host_barrier(d);
+}
 int dbt_dist_stats(const dbt_dist *d, double out[16]) {
     if (!d || !out) return DBT_ERR_ARG;
     memcpy(out, d->stats, sizeof d->stats);

@@ -229,6 +229,7 @@ int dbt_dist_destroy(dbt_dist *d);
 int dbt_dist_rank(const dbt_dist *d);
 int dbt_dist_world(const dbt_dist *d);
 int dbt_dist_barrier(dbt_dist *d); /* host barrier over the control block */
+int dbt_dist_trim(dbt_dist *d);    /* collective: give the staging / send / list / workspace buffers back */
 /* key sub-ranges per owner for sort/dedup (the pipeline depth); 0 = automatic: 4, or 1 for small shards */
 int dbt_dist_set_sub_ranges(dbt_dist *d, uint32_t q);
 /* every rank contributes `bytes` (<= 32 KB) of host memory; out receives world * bytes in rank order */

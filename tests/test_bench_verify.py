@@ -75,6 +75,7 @@ def test_join_checks(orc, data):
     out = orc.hashjoin(r, s, "1")
     k = orc.count_rows(out)
     assert V.check_semijoin_u32(t(r), nr, t(s), ns, t(out), k, 1, 6000)["same_rows_in_s_order"]
+    assert V.check_semijoin_u32(t(r), nr, t(s), ns, t(out), k, 1, 6000, chunk_rows=4700)["same_rows_in_s_order"]  # S walked in chunks
     bad = out.copy()
     e = bad["entries"].reshape(-1).copy()
     e[[0, 1]] = e[[1, 0]]
