@@ -522,14 +522,15 @@ def e2e_dist(args, dbt, d, torch, dist, dev, d_in, nblocks, cap, n_total, world,
     except Exception:  # noqa: BLE001
         avail = 0
     out_bytes = cap * BLOCK_BYTES
-    need = (img_bytes + out_bytes) * world * 1.15
+    host_out_bytes = (nblocks + nblocks // 16 + 8) * BLOCK_BYTES  # a rank emits about its share (0.9 of its rows here)
+    need = (img_bytes + host_out_bytes) * world * 1.15
     free_dev, _ = torch.cuda.mem_get_info(dev)
     if avail < need or free_dev < 2 * img_bytes + 2 * out_bytes + (8 << 30):
         return {"value": None, "unit": "records/s", "h2d_bytes_per_step": img_bytes * world, "d2h_bytes_per_step": None,
                 "skipped": f"needs {need / 1e9:.0f} GB of pinned host memory ({avail / 1e9:.0f} available) and "
                            f"{(2 * img_bytes + 2 * out_bytes) / 1e9:.0f} GB of device memory ({free_dev / 1e9:.0f} free)"}
     h_in = torch.empty(img_bytes, dtype=torch.uint8).pin_memory()
-    h_out = torch.empty(out_bytes, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(host_out_bytes, dtype=torch.uint8).pin_memory()
     h_in.copy_(d_in)
     bufs_in = [d_in, torch.empty_like(d_in)]
     bufs_out = [torch.empty(out_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
@@ -559,6 +560,7 @@ def e2e_dist(args, dbt, d, torch, dist, dev, d_in, nblocks, cap, n_total, world,
             assert rows > 0
             nb_out = (rows + RPB - 1) // RPB
             out_b = nb_out * BLOCK_BYTES
+            assert out_b <= host_out_bytes
             with torch.cuda.stream(s_down):  # (one host buffer: the downloads are ordered on their stream)
                 h_out[:out_b].copy_(bufs_out[k][:out_b], non_blocking=True)
                 down[k] = s_down.record_event()
