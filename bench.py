@@ -625,6 +625,25 @@ def dist_legs(args, dbt, d, torch, dist, V, dev, rank, world, checks):
         legs["cfg2_sort_str"] = {"error": str(e)[:200]}
     torch.cuda.empty_cache()
 
+    # ---- north_star: MergeSort field=num at operator scope, 125M records per GPU (1B records on 8 GPUs) ---------------
+    try:
+        d.trim()
+        n2 = args.leg_rows or 125_000_000
+        img, nb = gen(78, n2 * world, 1 << 32, 1, rank * n2, n2)  # num uniform over the full 32-bit range
+        cap = nb + nb // 4 + 64
+        out = torch.empty(cap * BLOCK_BYTES, dtype=torch.uint8, device=dev)
+        ms, (rows, _) = _timed(torch, dist, dev, stream, lambda: d.sort(img.data_ptr(), nb, "1", False, out.data_ptr(), cap, sp), 3, 1)
+        st = d.stats()
+        chk = V.check_sort(img, n2, out, rows, lambda im, m: V.column(im, m, 1), dist)
+        checks["northstar_sort_num"] = chk
+        legs["northstar_sort_num"] = {"workload": f"MergeSort field=num, {n2} records per GPU x {world} GPUs = {n2 * world} records, full 32-bit keys (north_star: 1B-record num-key MergeSort; 140 GB of records only fit on 8 GPUs)",
+                                      "ms": round(ms, 2), "Grec_s": round(n2 * world / ms / 1e6, 2), "rows": chk["rows"], "ok": _ok(chk),
+                                      "nvlink_gbs_per_direction": round(st["bytes_remote"] / max(st["nvlink_ms"], 1e-9) / 1e6, 1), "timeline_ms": st["timeline_ms"]}
+        del img, out
+    except Exception as e:  # noqa: BLE001
+        legs["northstar_sort_num"] = {"error": str(e)[:200]}
+    torch.cuda.empty_cache()
+
     # ---- configs[3]: HashJoin field=num, R = 100M x S = 1B over the GPUs (strong scaling), uniform and Zipf(1.1) -------
     for kind, label in ((1, "uniform"), (4, "zipf1.1")):
         name = f"cfg3_hashjoin_{label}"

@@ -190,6 +190,10 @@ int build_key_bitmap(const uint32_t *d_keys, uint64_t n, Arena &ws, cudaStream_t
 // d_total: 16 bytes on the device {u64 matches, u32 look-back error flag}
 int semijoin_stream(const void *d_s_img, uint64_t nblocks_s, int field, const uint32_t *d_bitmap, uint32_t base, uint32_t span,
                     void *d_out, uint64_t cap_rows, uint64_t *d_total, Arena &ws, cudaStream_t st);
+// two streaming passes (count per block, then copy to the scanned offsets); *h_total = matches (nothing is written when
+// they exceed cap_rows); synchronises the stream once (the total decides whether the copy pass runs)
+int semijoin_two_pass(const void *d_s_img, uint64_t nblocks_s, int field, const uint32_t *d_bitmap, uint32_t base, uint32_t span,
+                      void *d_out, uint64_t cap_rows, uint64_t *d_total, uint64_t *h_total, Arena &ws, cudaStream_t st);
 int hash_join_counts(const KeyCols &r, const KeyCols &s, int field, uint32_t *d_counts /*[s.n]*/, Arena &ws,
                      cudaStream_t st);
 // sorted unique row lists of R and S -> per-R-unique-row 0/1 match flags, and the reference walk's read count

@@ -740,15 +740,15 @@ extern "C" int dbt_dev_mergejoin(const void *d_in_r, uint64_t nbr, const void *d
     return finish(st);
 }
 
-// Fields '0'/'1' with a key bitmap at hand: the fused streaming semi-join (one read of S, no extraction, no gather).
-// *done = false when the bitmap did not fit the workspace (the caller then runs the column-based path).
+// Fields '0'/'1' with a key bitmap at hand: the probe phase as streaming passes over the S image -- no extraction of S,
+// no row lists, no random gather (kernels_semijoin.cu).  DBT_JOIN_FUSED: 2 (default) = two streaming passes (count, then
+// copy), 1 = one chained pass (exact, but latency-bound: profiles/r02_notes.md), 0 = the column path (extract, probe,
+// compact, gather).  *done = false when the bitmap did not fit the workspace (the caller then runs the column path).
 static int fused_semijoin(const uint32_t *d_rkeys, uint64_t nr, const void *d_in_s, uint64_t nbs, int field, void *d_out,
                           uint64_t cap_blocks, Arena &ws, cudaStream_t st, uint64_t *nres, bool *done) {
     *done = false;
-    // opt-in for now (DBT_JOIN_FUSED=1): the chained single pass is exact but runs at 0.35 of the HBM roofline -- every
-    // tile pays ~4 serialized L2 round trips (ticket, bitmap, 1.7 look-back rounds) of ~3.7 us each under streaming
-    // load, profiles/r02_notes.md -- which is slower than the column path it is meant to replace (42.8 vs 32.7 ms)
-    if (!getenv("DBT_JOIN_FUSED") || atoi(getenv("DBT_JOIN_FUSED")) == 0) return 0;
+    const int mode = getenv("DBT_JOIN_FUSED") ? atoi(getenv("DBT_JOIN_FUSED")) : 2;
+    if (mode == 0) return 0;
     if (!nr || !nbs || nbs >= (1ull << 32)) return 0;
     const size_t m0 = ws.mark();
     uint32_t *bm, base, span;
@@ -758,9 +758,13 @@ static int fused_semijoin(const uint32_t *d_rkeys, uint64_t nr, const void *d_in
         ws.release(m0);
         return 0;
     }
-    DBT_TRY(semijoin_stream(d_in_s, nbs, field, bm, base, span, d_out, cap_blocks * kRpb, d_total, ws, st));
     uint64_t h[2] = {0, 0};
-    DBT_TRY(read_u64(d_total, h, 2, st));
+    if (mode == 1) {
+        DBT_TRY(semijoin_stream(d_in_s, nbs, field, bm, base, span, d_out, cap_blocks * kRpb, d_total, ws, st));
+        DBT_TRY(read_u64(d_total, h, 2, st));
+    } else {
+        DBT_TRY(semijoin_two_pass(d_in_s, nbs, field, bm, base, span, d_out, cap_blocks * kRpb, d_total, &h[0], ws, st));
+    }
     *done = true;
     *nres = h[0];
     if ((uint32_t)h[1]) {

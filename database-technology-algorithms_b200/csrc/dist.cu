@@ -94,6 +94,8 @@ struct dbt_dist {
     cudaStream_t work = nullptr; // owner-side operators on what has landed (highest priority)
     cudaEvent_t ev_c = nullptr, ev_q[kMaxSub] = {};
     Buf send[2]; // per-owner block images waiting for the copy engines
+    cudaStream_t cp[kMaxRanks] = {}; // one copy stream per destination: the P-1 transfers of a sub-range run side by side
+    cudaEvent_t ev_cp[kMaxRanks] = {};
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     SharedBuf stag[2], keys, flags;
     Buf ws, lists;
@@ -189,6 +191,7 @@ static int ensure_shared(dbt_dist *d, SharedBuf &b, size_t need_bytes, cudaStrea
     DBT_CUDA(cudaStreamSynchronize(main));
     DBT_CUDA(cudaStreamSynchronize(d->work));
     DBT_CUDA(cudaStreamSynchronize(d->side));
+    for (int k = 0; k + 1 < d->world; ++k) DBT_CUDA(cudaStreamSynchronize(d->cp[k]));
     DBT_TRY(host_barrier(d)); // nobody stores into the old buffers any more
     for (int r = 0; r < d->world; ++r) {
         if (r != d->rank && b.peer[r] && !d->local) cudaIpcCloseMemHandle(b.peer[r]);
@@ -344,10 +347,12 @@ static int exchange_push(dbt_dist *d, int slot, const void *d_in, Routed &r, int
             void *dst;
             const void *src;
             size_t bytes;
+            uint32_t owner;
         } copies[kMaxRanks];
         uint32_t ncopies = 0;
+        bool direct_remote = false;
         for (uint32_t k = 0; k < P; ++k) {
-            const uint32_t owner = (d->rank + 1 + k) % P; // rotated by rank: at any time the ranks copy to different owners
+            const uint32_t owner = (d->rank + 1 + k) % P; // rotated by rank: CTA i of every rank starts on a different owner
             const uint32_t b = owner * Q + q;
             const size_t bytes = (size_t)lay->seg_blocks(d->rank, owner, q) * DBT_BLOCK_BYTES;
             char *at_owner = (char *)d->stag[slot].peer[owner] + lay->seg_blk0(d->rank, owner, q) * DBT_BLOCK_BYTES;
@@ -359,10 +364,13 @@ static int exchange_push(dbt_dist *d, int slot, const void *d_in, Routed &r, int
                 // kernel stores straight into the owner's staging buffer over NVLink (gather + exchange in one kernel:
                 // 10.3 ms instead of 6.7 + 9.0 for 7 GB per direction at P = 2)
                 plan.seg[k].out = (uint4 *)at_owner;
-                if ((int)owner != d->rank) remote += bytes;
+                if ((int)owner != d->rank) {
+                    remote += bytes;
+                    direct_remote = true;
+                }
             } else {
                 plan.seg[k].out = (uint4 *)((char *)d->send[slot].p + send_off);
-                if (bytes) copies[ncopies++] = Copy{at_owner, (char *)d->send[slot].p + send_off, bytes};
+                copies[ncopies++] = Copy{at_owner, (char *)d->send[slot].p + send_off, bytes, owner};
                 send_off += bytes;
                 remote += bytes;
             }
@@ -370,13 +378,38 @@ static int exchange_push(dbt_dist *d, int slot, const void *d_in, Routed &r, int
         if (Q == 1 && first_copy && first_exchange) DIST_CUDA(cudaEventRecord(d->ev_a, main));
         DIST_TRY(launch_gather_push(d_in, r.p.row_slot, plan, main));
         DIST_CUDA(cudaEventRecord(d->ev_q[q], main));
-        DIST_CUDA(cudaStreamWaitEvent(d->side, d->ev_q[q], 0));
-        if (Q > 1 && first_copy && first_exchange) DIST_CUDA(cudaEventRecord(d->ev_a, d->side));
+        const uint32_t flag_idx = (slot ? kFlagSlot1 : 0) + q * kMaxRanks + d->rank;
+        if (Q == 1) { // everything was stored by the gather kernel itself: one flag to everybody
+            (void)direct_remote;
+            DIST_CUDA(cudaStreamWaitEvent(d->side, d->ev_q[q], 0));
+            DIST_TRY(launch_signal(fp, P, flag_idx, d->epoch, d->side));
+        } else {
+            // my own segment is in place as soon as the gather is done; every other owner gets its segment through its own
+            // copy stream (the P-1 transfers of a sub-range run concurrently: uniform all-to-all flows, no owner is the
+            // target of two full-rate copies at once) and its flag right behind the copy
+            FlagPtrs self;
+            memset(&self, 0, sizeof self);
+            self.p[0] = fp.p[d->rank];
+            DIST_CUDA(cudaStreamWaitEvent(d->side, d->ev_q[q], 0));
+            if (first_copy && first_exchange) DIST_CUDA(cudaEventRecord(d->ev_a, d->side));
+            DIST_TRY(launch_signal(self, 1, flag_idx, d->epoch, d->side));
+            for (uint32_t c = 0; c < ncopies; ++c) {
+                cudaStream_t cs = d->cp[c];
+                DIST_CUDA(cudaStreamWaitEvent(cs, d->ev_q[q], 0));
+                if (copies[c].bytes) DIST_CUDA(cudaMemcpyAsync(copies[c].dst, copies[c].src, copies[c].bytes, cudaMemcpyDeviceToDevice, cs));
+                FlagPtrs one;
+                memset(&one, 0, sizeof one);
+                one.p[0] = fp.p[copies[c].owner];
+                DIST_TRY(launch_signal(one, 1, flag_idx, d->epoch, cs));
+            }
+        }
         first_copy = false;
-        for (uint32_t c = 0; c < ncopies; ++c)
-            DIST_CUDA(cudaMemcpyAsync(copies[c].dst, copies[c].src, copies[c].bytes, cudaMemcpyDeviceToDevice, d->side));
-        DIST_TRY(launch_signal(fp, P, (slot ? kFlagSlot1 : 0) + q * kMaxRanks + d->rank, d->epoch, d->side));
     }
+    if (Q > 1) // the NVLink phase ends when the last copy stream is done
+        for (uint32_t c = 0; c + 1 < P; ++c) {
+            DIST_CUDA(cudaEventRecord(d->ev_cp[c], d->cp[c]));
+            DIST_CUDA(cudaStreamWaitEvent(d->side, d->ev_cp[c], 0));
+        }
     DIST_CUDA(cudaEventRecord(d->ev_b, d->side));
     d->stats[1] += (double)remote;
     d->stats[2] += (double)total;
@@ -394,6 +427,7 @@ static int finish_op(dbt_dist *d, cudaStream_t main) {
     DIST_CUDA(cudaStreamSynchronize(main));
     DIST_CUDA(cudaStreamSynchronize(d->work));
     DIST_CUDA(cudaStreamSynchronize(d->side));
+    for (int k = 0; k + 1 < d->world; ++k) DIST_CUDA(cudaStreamSynchronize(d->cp[k]));
     stage_resolve();
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, d->ev_a, d->ev_b) == cudaSuccess) d->stats[0] = ms;
@@ -438,7 +472,9 @@ static uint32_t pick_sub_ranges(dbt_dist *d, uint64_t max_blocks) {
     uint32_t Q = d->nsub; // 0 = automatic
     if (!Q)
         if (const char *e = getenv("DBT_DIST_SUBRANGES")) Q = (uint32_t)atoi(e);
-    if (!Q) Q = (max_blocks < 20000) ? 1 : 4; // small shards: the pipeline's per-sub-range launches would dominate
+    // small shards: the pipeline's per-sub-range launches would dominate; many ranks: the tail after the last transfer
+    // (the operator on the last sub-range) is what remains exposed, so cut finer
+    if (!Q) Q = (max_blocks < 20000) ? 1 : (d->world <= 2 ? 4 : 8);
     Q = std::max<uint32_t>(1, std::min<uint32_t>(Q, std::min<uint32_t>(kMaxSub, 64u / (uint32_t)d->world)));
     return Q;
 }
@@ -512,6 +548,10 @@ int dbt_dist_init(const char *session, int rank, int world, int device, dbt_dist
     if (!rc && cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) lo = hi = 0;
     if (!rc && cudaStreamCreateWithPriority(&d->side, cudaStreamNonBlocking, lo) != cudaSuccess) rc = DBT_ERR_CUDA;
     if (!rc && cudaStreamCreateWithPriority(&d->work, cudaStreamNonBlocking, hi) != cudaSuccess) rc = DBT_ERR_CUDA;
+    for (int k = 0; k + 1 < world && !rc; ++k)
+        if (cudaStreamCreateWithFlags(&d->cp[k], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&d->ev_cp[k], cudaEventDisableTiming) != cudaSuccess)
+            rc = DBT_ERR_CUDA;
     if (!rc && (cudaEventCreate(&d->ev_a) != cudaSuccess || cudaEventCreate(&d->ev_b) != cudaSuccess ||
                 cudaEventCreateWithFlags(&d->ev_c, cudaEventDisableTiming) != cudaSuccess))
         rc = DBT_ERR_CUDA;
@@ -550,6 +590,10 @@ int dbt_dist_init_local(int world, const int *devices, dbt_dist **out) {
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         DBT_CUDA(cudaStreamCreateWithPriority(&d->side, cudaStreamNonBlocking, lo));
         DBT_CUDA(cudaStreamCreateWithPriority(&d->work, cudaStreamNonBlocking, hi));
+        for (int k = 0; k + 1 < world; ++k) {
+            DBT_CUDA(cudaStreamCreateWithFlags(&d->cp[k], cudaStreamNonBlocking));
+            DBT_CUDA(cudaEventCreateWithFlags(&d->ev_cp[k], cudaEventDisableTiming));
+        }
         DBT_CUDA(cudaEventCreateWithFlags(&d->ev_c, cudaEventDisableTiming));
         for (uint32_t q = 0; q < kMaxSub; ++q) DBT_CUDA(cudaEventCreateWithFlags(&d->ev_q[q], cudaEventDisableTiming));
         DBT_CUDA(cudaEventCreate(&d->ev_a));
@@ -578,6 +622,10 @@ int dbt_dist_destroy(dbt_dist *d) {
     if (d->d_err) cudaFree(d->d_err);
     if (d->side) cudaStreamDestroy(d->side);
     if (d->work) cudaStreamDestroy(d->work);
+    for (cudaStream_t c : d->cp)
+        if (c) cudaStreamDestroy(c);
+    for (cudaEvent_t e : d->ev_cp)
+        if (e) cudaEventDestroy(e);
     if (d->ev_c) cudaEventDestroy(d->ev_c);
     for (cudaEvent_t e : d->ev_q)
         if (e) cudaEventDestroy(e);
@@ -659,7 +707,7 @@ int dbt_dist_sort(dbt_dist *d, const void *d_in, uint64_t nblocks, int field, in
     DIST_TRY(route_prepare(d, A, d_in, nblocks, field, main, &r));
     d->stats[4] = ms_since(t_begin);
     std::vector<uint32_t> samp;
-    DIST_TRY(take_samples(d, A, r, (uint32_t)std::min<uint64_t>(kSamplesPerRank, r.n), main, &samp));
+    DIST_TRY(take_samples(d, A, r, (uint32_t)std::min<uint64_t>(std::max<uint32_t>(1024u, 2 * kSamplesPerRank / P), r.n), main, &samp));
     uint32_t splitters[64];
     DIST_TRY(choose_splitters(d, samp, P * Q, splitters));
     d->stats[5] = ms_since(t_begin);

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 namespace dbt {
 
@@ -93,6 +94,15 @@ int ooc_hashjoin(HostCtx &c, const void *h_in_r, uint64_t nbr, const void *h_in_
                  uint64_t out_capacity_blocks, uint64_t chunk_blocks, uint64_t *nres);
 int ooc_mergejoin(HostCtx &c, const void *h_in_r, uint64_t nbr, const void *h_in_s, uint64_t nbs, int field, void *h_out_ur,
                   void *h_out_us, void *h_out, uint64_t chunk_blocks, uint64_t res[4]);
+
+// several GPUs of one box, single process (host_multi.cu); DBT_DEVICES = "all" | "<count>" | "i,j,k"
+int multi_devices(std::vector<int> *devs); // number of devices to use (0 = the single-GPU path)
+int multi_sort(const std::vector<int> &devs, const void *h_in, uint64_t nblocks, int field, bool dedup, void *h_out, uint64_t *nrows_in,
+               uint64_t *nrows_out);
+int multi_hashjoin(const std::vector<int> &devs, const void *h_r, uint64_t nbr, const void *h_s, uint64_t nbs, int field, void *h_out,
+                   uint64_t out_capacity_blocks, uint64_t *nres);
+int multi_mergejoin(const std::vector<int> &devs, const void *h_r, uint64_t nbr, const void *h_s, uint64_t nbs, int field, void *h_out_ur,
+                    void *h_out_us, void *h_out, uint64_t res[4]);
 
 } // namespace dbt
 

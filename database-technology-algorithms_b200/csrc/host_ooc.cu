@@ -586,7 +586,7 @@ static int host_key_cmp(const unsigned char *a, const unsigned char *b, int fiel
 }
 // block reads after the first two of the reference's two-pointer walk over two sorted unique images
 // (the closed form of kernels_join.cu: walk_reads_kernel, evaluated on the host images)
-static uint64_t host_walk_reads(const void *ur, uint64_t nr, const void *us, uint64_t ns, int field) {
+uint64_t host_walk_reads(const void *ur, uint64_t nr, const void *us, uint64_t ns, int field) {
     if (!nr || !ns) return 0;
     auto lower_bound = [&](const void *img, uint64_t n, const unsigned char *key) {
         uint64_t lo = 0, hi = n;

@@ -503,6 +503,21 @@ struct SortOut {
 
 // sort (or dedup) a file into `outpath`; returns counters
 SortOut sort_file(const char *infile, unsigned char field, unsigned nmem, const char *outpath, bool dedup, uint64_t *nunique) {
+    std::vector<int> devs;
+    if (multi_devices(&devs) && file_blocks(infile) >= 64 * devs.size()) {
+        // DBT_DEVICES names several GPUs: every one takes a contiguous range of the file's blocks (host_multi.cu)
+        const uint64_t nblocks = read_file(infile, g_files.pin[0]);
+        SortOut o{};
+        must(dbt_sort_counters(nblocks, nmem, &o.segs, &o.passes, &o.nios), "dbt_sort_counters");
+        must(g_files.pin[2].ensure((size_t)(nblocks + 8) * DBT_BLOCK_BYTES), "pinned staging");
+        uint64_t n = 0, u = 0;
+        must(multi_sort(devs, g_files.pin[0].p, nblocks, field, dedup, g_files.pin[2].p, &n, &u), "multi-GPU sort");
+        o.nrows = n;
+        if (nunique) *nunique = u;
+        if (outpath) write_file(outpath, g_files.pin[2].p, blocks_for(u) * DBT_BLOCK_BYTES);
+        stage_resolve();
+        return o;
+    }
     HostCtx &c = ctx();
     const int op_id = dedup ? DBT_OP_DEDUP : DBT_OP_SORT;
     if (const uint64_t chunk = ooc_chunk_blocks(op_id, file_blocks(infile), 0, field, c.cached_device_bytes())) {
@@ -582,6 +597,26 @@ void MergeJoin(char *infile1, char *infile2, unsigned char field, block_t *, uns
     std::cout << "Merge Sorting..." << std::endl;
     check_nmem_or_exit(nmem_blocks);
     check_field_or_exit(field);
+    std::vector<int> devs;
+    if (multi_devices(&devs) && std::min(file_blocks(infile1), file_blocks(infile2)) >= 64 * devs.size()) {
+        const uint64_t nbr = read_file(infile1, g_files.pin[0]);
+        const uint64_t nbs = read_file(infile2, g_files.pin[1]);
+        must(g_files.pin[2].ensure((size_t)(nbr + 8) * DBT_BLOCK_BYTES), "pinned staging");
+        must(g_files.pin[3].ensure((size_t)(nbs + 8) * DBT_BLOCK_BYTES), "pinned staging");
+        must(g_files.pin[4].ensure((size_t)(std::min(nbr, nbs) + 8) * DBT_BLOCK_BYTES), "pinned staging");
+        uint64_t res[4] = {0, 0, 0, 0};
+        must(multi_mergejoin(devs, g_files.pin[0].p, nbr, g_files.pin[1].p, nbs, field, g_files.pin[2].p, g_files.pin[3].p, g_files.pin[4].p, res),
+             "multi-GPU merge join");
+        std::cout << "Eliminating Duplicates..." << std::endl << "Merge Sorting..." << std::endl
+                  << "Eliminating Duplicates..." << std::endl;
+        write_file("1outfile.bin", g_files.pin[2].p, blocks_for(res[1]) * DBT_BLOCK_BYTES);
+        write_file("2outfile.bin", g_files.pin[3].p, blocks_for(res[2]) * DBT_BLOCK_BYTES);
+        write_file(outfile, g_files.pin[4].p, blocks_for(res[0]) * DBT_BLOCK_BYTES);
+        stage_resolve();
+        *nres = clamp32(res[0]);
+        *nios = clamp32(dbt_mergejoin_nios(nbr, nbs, nmem_blocks, res));
+        return;
+    }
     HostCtx &c = ctx();
     if (const uint64_t chunk = ooc_chunk_blocks(DBT_OP_MERGEJOIN, file_blocks(infile1), file_blocks(infile2), field, c.cached_device_bytes())) {
         // larger than the device: both dedups and the intersection run out of core through host memory (host_ooc.cu)
@@ -634,6 +669,21 @@ void HashJoin(char *infile1, char *infile2, unsigned char field, block_t *, unsi
         close(fd);
         *nres = 0;
         *nios = 2;
+        return;
+    }
+    std::vector<int> devs;
+    if ((field == '0' || field == '1') && multi_devices(&devs) && std::min(file_blocks(infile1), file_blocks(infile2)) >= 64 * devs.size()) {
+        // u32 keys on several GPUs: R's keys are replicated, every GPU probes its range of S's blocks in place, the outputs
+        // concatenate in S file order (str / composite keys would come back hash-partitioned: they stay on one GPU)
+        const uint64_t nbr = read_file(infile1, g_files.pin[0]);
+        const uint64_t nbs = read_file(infile2, g_files.pin[1]);
+        must(g_files.pin[2].ensure((size_t)(nbs + 8) * DBT_BLOCK_BYTES), "pinned staging");
+        uint64_t n = 0;
+        must(multi_hashjoin(devs, g_files.pin[0].p, nbr, g_files.pin[1].p, nbs, field, g_files.pin[2].p, nbs, &n), "multi-GPU hash join");
+        write_file(outfile, g_files.pin[2].p, blocks_for(n) * DBT_BLOCK_BYTES);
+        stage_resolve();
+        *nres = clamp32(n);
+        *nios = clamp32(dbt_hashjoin_nios(nbr, nbs, nmem_blocks, n));
         return;
     }
     HostCtx &c = ctx();

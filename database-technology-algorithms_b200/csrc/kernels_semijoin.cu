@@ -275,4 +275,202 @@ int semijoin_stream(const void *d_s_img, uint64_t nblocks_s, int field, const ui
     return 0;
 }
 
+// =====================================================================================================
+// Two streaming passes (the default): no chain, nothing to wait for.
+//
+//   pass 1  streams S (cp.async.bulk, three blocks in flight per CTA), tests every live row's key against the bitmap
+//           and writes, per S block, the 100-bit match mask and the match count (20 bytes per 14 KB block);
+//   scan    exclusive prefix of the per-block counts (the device-wide scan of kernels_gather.cu) = the output row of
+//           every block's first match, and the total -- so a result that does not fit is refused before a byte moves;
+//   pass 2  streams S again and copies every matching 140-byte record from shared memory to its final place in the
+//           packed output image (one warp per record: 35 consecutive words, consecutive matches are contiguous).
+//
+// DRAM traffic 280 B per S row + 140 B per match against ~141 + 8 + 8 + 4 + (267 + 140) per match for the column path
+// (extraction, probe, compaction, random gather): S is read twice, but sequentially, and the scattered second read of
+// the gather (267 B per 140-byte row) is gone.
+// =====================================================================================================
+constexpr int kTpThreads = 128;
+constexpr int kTpStages = 3;
+
+struct TpPipe { // per-CTA bulk-copy pipeline over the blocks b = first + k * step
+    uint32_t (*stage)[kBlockWords];
+    uint64_t *mbar;
+};
+__device__ __forceinline__ void tp_issue(const TpPipe &p, const uint32_t *img, uint64_t block, int sidx) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sj_smem_u32(&p.mbar[sidx])), "r"((uint32_t)DBT_BLOCK_BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sj_smem_u32(p.stage[sidx])),
+                 "l"(img + block * kBlockWords), "r"((uint32_t)DBT_BLOCK_BYTES), "r"(sj_smem_u32(&p.mbar[sidx]))
+                 : "memory");
+}
+__device__ __forceinline__ void tp_wait(const TpPipe &p, int sidx, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                     : "=r"(ok)
+                     : "r"(sj_smem_u32(&p.mbar[sidx])), "r"(parity)
+                     : "memory");
+}
+
+template <int FIELD>
+__global__ void __launch_bounds__(kTpThreads)
+semijoin_count_kernel(const uint32_t *__restrict__ img, uint64_t nblocks, const uint32_t *__restrict__ bm, uint32_t base, uint32_t span,
+                      uint4 *__restrict__ masks /*[nblocks]: 100 match bits*/, uint32_t *__restrict__ counts /*[nblocks]*/) {
+    extern __shared__ __align__(128) unsigned char tp_raw[];
+    TpPipe pipe{reinterpret_cast<uint32_t(*)[kBlockWords]>(tp_raw),
+                reinterpret_cast<uint64_t *>(tp_raw + sizeof(uint32_t) * kBlockWords * kTpStages)};
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t first = blockIdx.x, step = gridDim.x;
+    const uint64_t mine = first < nblocks ? (nblocks - first + step - 1) / step : 0;
+    if (tid == 0) {
+        for (int i = 0; i < kTpStages; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sj_smem_u32(&pipe.mbar[i])), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (uint64_t k = 0; k < (uint64_t)(kTpStages - 1) && k < mine; ++k) tp_issue(pipe, img, first + k * step, (int)k);
+    }
+    __syncthreads();
+    __shared__ uint32_t s_mask[4];
+    for (uint64_t k = 0; k < mine; ++k) {
+        if (tid == 0 && k + kTpStages - 1 < mine) tp_issue(pipe, img, first + (k + kTpStages - 1) * step, (int)((k + kTpStages - 1) % kTpStages));
+        const int sidx = (int)(k % kTpStages);
+        tp_wait(pipe, sidx, (uint32_t)((k / kTpStages) & 1));
+        const uint32_t *blk = pipe.stage[sidx];
+        const uint32_t nres = min(blk[1], kRpb);
+        bool match = false;
+        if (tid < (int)nres) {
+            const uint32_t v = blk[kEntriesWord + tid * kRecWords + (FIELD == 0 ? 0 : 1)] - base;
+            match = (v <= span) && ((__ldg(bm + (v >> 5)) >> (v & 31)) & 1u);
+        }
+        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, match);
+        if (lane == 0) s_mask[warp] = ballot;
+        __syncthreads(); // (also: everyone is done with this stage before it is refilled)
+        if (tid == 0) {
+            const uint64_t b = first + k * step;
+            const uint4 m = make_uint4(s_mask[0], s_mask[1], s_mask[2], s_mask[3]);
+            masks[b] = m;
+            counts[b] = __popc(m.x) + __popc(m.y) + __popc(m.z) + __popc(m.w);
+        }
+        __syncthreads(); // s_mask is rewritten by the next block
+    }
+}
+
+__global__ void __launch_bounds__(kTpThreads)
+semijoin_copy_kernel(const uint32_t *__restrict__ img, uint64_t nblocks, const uint4 *__restrict__ masks, const uint32_t *__restrict__ counts,
+                     const uint32_t *__restrict__ offs /*[nblocks] output row of the block's first match*/, uint32_t *__restrict__ out) {
+    extern __shared__ __align__(128) unsigned char tp_raw[];
+    TpPipe pipe{reinterpret_cast<uint32_t(*)[kBlockWords]>(tp_raw),
+                reinterpret_cast<uint64_t *>(tp_raw + sizeof(uint32_t) * kBlockWords * kTpStages)};
+    __shared__ uint32_t s_src[kRpb], s_dst[kRpb]; // word offset of the k-th match inside the stage / relative output word offset
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t first = blockIdx.x, step = gridDim.x;
+    const uint64_t mine = first < nblocks ? (nblocks - first + step - 1) / step : 0;
+    if (tid == 0) {
+        for (int i = 0; i < kTpStages; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sj_smem_u32(&pipe.mbar[i])), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (uint64_t k = 0; k < (uint64_t)(kTpStages - 1) && k < mine; ++k) tp_issue(pipe, img, first + k * step, (int)k);
+    }
+    __syncthreads();
+    for (uint64_t k = 0; k < mine; ++k) {
+        if (tid == 0 && k + kTpStages - 1 < mine) tp_issue(pipe, img, first + (k + kTpStages - 1) * step, (int)((k + kTpStages - 1) % kTpStages));
+        const int sidx = (int)(k % kTpStages);
+        tp_wait(pipe, sidx, (uint32_t)((k / kTpStages) & 1));
+        const uint64_t b = first + k * step;
+        const uint32_t m = counts[b];
+        const uint32_t *blk = pipe.stage[sidx];
+        const uint64_t g0 = offs[b];
+        const uint64_t off0 = slot_word(g0);
+        if (tid < (int)kRpb) {
+            const uint4 mk = masks[b];
+            const uint32_t w = tid >> 5, bit = tid & 31;
+            const uint32_t word = w == 0 ? mk.x : (w == 1 ? mk.y : (w == 2 ? mk.z : mk.w));
+            if ((word >> bit) & 1u) {
+                uint32_t r = __popc(word & ((1u << bit) - 1u));
+                if (w > 0) r += __popc(mk.x);
+                if (w > 1) r += __popc(mk.y);
+                if (w > 2) r += __popc(mk.z);
+                const uint64_t g = g0 + r, ob = g / kRpb;
+                const uint32_t e = (uint32_t)(g - ob * kRpb);
+                s_src[r] = kEntriesWord + (uint32_t)tid * kRecWords;
+                s_dst[r] = (uint32_t)(ob * kBlockWords + kEntriesWord + (uint64_t)e * kRecWords - off0);
+                if (e == 0) { // first row of an output block: its header (the last block's is fixed afterwards)
+                    uint32_t *o = out + ob * kBlockWords;
+                    o[0] = (uint32_t)ob;
+                    o[1] = kRpb;
+                    o[kTrailerWord] = 1;
+                    o[kTrailerWord + 1] = kRpb;
+                }
+            }
+        }
+        __syncthreads();
+        for (uint32_t r = warp; r < m; r += kTpThreads / 32) { // one warp per record: 32 + 3 consecutive words
+            const uint32_t *src = blk + s_src[r];
+            uint32_t *dst = out + off0 + s_dst[r];
+            dst[lane] = src[lane];
+            if (lane < 3) dst[32 + lane] = src[32 + lane];
+        }
+        __syncthreads(); // stage and lists are free again
+    }
+}
+
+int semijoin_two_pass(const void *d_s_img, uint64_t nblocks_s, int field, const uint32_t *d_bitmap, uint32_t base, uint32_t span,
+                      void *d_out, uint64_t cap_rows, uint64_t *d_total, uint64_t *h_total, Arena &ws, cudaStream_t st) {
+    *h_total = 0;
+    DBT_CUDA(cudaMemsetAsync(d_total, 0, 16, st));
+    if (nblocks_s == 0) return 0;
+    if (nblocks_s >= (1ull << 32)) {
+        set_error("semijoin: S must have fewer than 2^32 blocks");
+        return DBT_ERR_UNSUPPORTED;
+    }
+    const size_t m0 = ws.mark();
+    uint4 *masks = ws.take<uint4>(nblocks_s);
+    uint32_t *counts = ws.take<uint32_t>(nblocks_s), *offs = ws.take<uint32_t>(nblocks_s);
+    if (!masks || !counts || !offs) {
+        set_error("semijoin: workspace too small");
+        return DBT_ERR_WORKSPACE;
+    }
+    const size_t smem = sizeof(uint32_t) * kBlockWords * kTpStages + 8 * kTpStages + 128;
+    static int per_sm[3] = {0, 0, 0};
+    const int f = field == '0' ? 0 : 1;
+    auto occupancy = [&](const void *fn, int idx) -> int {
+        if (!per_sm[idx]) {
+            DBT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int occ = 0;
+            DBT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kTpThreads, smem));
+            per_sm[idx] = std::max(occ, 1);
+        }
+        return 0;
+    };
+    DBT_TRY(occupancy(f == 0 ? (const void *)semijoin_count_kernel<0> : (const void *)semijoin_count_kernel<1>, f));
+    DBT_TRY(occupancy((const void *)semijoin_copy_kernel, 2));
+    {
+        StageScope sc(ST_HASH_PROBE, st);
+        const int grid = (int)std::min<uint64_t>(nblocks_s, (uint64_t)148 * per_sm[f]);
+        if (f == 0)
+            semijoin_count_kernel<0><<<grid, kTpThreads, smem, st>>>((const uint32_t *)d_s_img, nblocks_s, d_bitmap, base, span, masks, counts);
+        else
+            semijoin_count_kernel<1><<<grid, kTpThreads, smem, st>>>((const uint32_t *)d_s_img, nblocks_s, d_bitmap, base, span, masks, counts);
+        count_launch();
+        DBT_KERNEL_CHECK();
+    }
+    {
+        StageScope sc(ST_COMPACT, st);
+        DBT_TRY(exclusive_offsets(counts, nblocks_s, offs, d_total, ws, st));
+    }
+    DBT_CUDA(cudaMemcpyAsync(h_total, d_total, 8, cudaMemcpyDeviceToHost, st));
+    DBT_CUDA(cudaStreamSynchronize(st));
+    if (*h_total > cap_rows || *h_total == 0) { // nothing to move, or it would not fit: the caller reports the size
+        ws.release(m0);
+        return 0;
+    }
+    {
+        StageScope sc(ST_GATHER, st);
+        const int grid = (int)std::min<uint64_t>(nblocks_s, (uint64_t)148 * per_sm[2]);
+        semijoin_copy_kernel<<<grid, kTpThreads, smem, st>>>((const uint32_t *)d_s_img, nblocks_s, masks, counts, offs, (uint32_t *)d_out);
+        semijoin_finish_kernel<<<1, 256, 0, st>>>((uint32_t *)d_out, (const unsigned long long *)d_total, cap_rows);
+        count_launch(2);
+        DBT_KERNEL_CHECK();
+    }
+    ws.release(m0);
+    return 0;
+}
+
 } // namespace dbt

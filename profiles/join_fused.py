@@ -28,7 +28,7 @@ peak = 6539.9
 for kind, label in ((1, "uniform"), (4, "zipf1.1")):
     dbt.check(L.dbt_gen_syn(9, ns, D, kind, 0, ns, 0, d_s.data_ptr(), sp))
     ref = None
-    for fused in ("1", "0"):
+    for fused in ("2", "1", "0"):
         os.environ["DBT_JOIN_FUSED"] = fused
         L.dbt_stage_timing_enable(1)
         times = []
@@ -48,8 +48,8 @@ for kind, label in ((1, "uniform"), (4, "zipf1.1")):
         chk = int(d_o[: nbo * BB].view(torch.int32)[:: 997].to(torch.int64).sum().item())  # sampled checksum of the output image
         if ref is None:
             ref = (k, chk)
-        probe_ms = rep["hash_probe"][0]
-        alg = (140.0 * ns + 140.0 * k) if fused == "1" else None
+        probe_ms = rep["hash_probe"][0] + (rep.get("record_gather", (0, 0))[0] + rep.get("compact", (0, 0))[0] if fused == "2" else 0)
+        alg = (140.0 * ns + 140.0 * k) if fused != "0" else None
         print(json.dumps({"S_rows": ns, "dist": label, "fused": fused, "ms": round(ms, 3), "nres": k, "same_as_fused": (k, chk) == ref,
                           "stage_ms": {a: round(b[0], 3) for a, b in rep.items()},
                           "stream_pass_hbm_frac": round(alg / (probe_ms * 1e-3) / 1e9 / peak, 4) if alg else None}), flush=True)

@@ -176,8 +176,10 @@ def test_hashjoin_wide_key_range_and_table_fallback(dbt, orc, monkeypatch):
         e["num"] = pool[rng.integers(0, len(pool), size=e["num"].shape)]
     want = orc.hashjoin(r, s, "1")
     assert 0 < orc.count_rows(want) < orc.count_rows(s)
+    got, n = H.dev_hashjoin(dbt, orc, r, s, "1")          # two streaming passes over S against the full-range bitmap (default)
+    assert H.same_image(got, want), H.first_diff(got, want)
     monkeypatch.setenv("DBT_JOIN_FUSED", "1")
-    got, n = H.dev_hashjoin(dbt, orc, r, s, "1")          # fused streaming semi-join over the full-range bitmap
+    got, n = H.dev_hashjoin(dbt, orc, r, s, "1")          # one chained streaming pass
     assert H.same_image(got, want), H.first_diff(got, want)
     monkeypatch.setenv("DBT_JOIN_FUSED", "0")              # the column-based paths:
     got, n = H.dev_hashjoin(dbt, orc, r, s, "1")          # sliced bitmap
@@ -381,21 +383,23 @@ def test_zipf_generator_is_zipf_and_reproducible_on_any_subrange(dbt, orc):
 
 
 def test_fused_semijoin_edge_cases(dbt, orc, monkeypatch):
-    """DBT_JOIN_FUSED=1: fields '0'/'1' run HashJoin's probe as one streaming pass over S: ragged S blocks (the pass reads
-    nreserved from the block it streams), results that end exactly on a block boundary, empty results, capacity errors
-    carrying the needed size, and agreement with the column-based path."""
-    monkeypatch.setenv("DBT_JOIN_FUSED", "1")
+    """Fields '0'/'1' run HashJoin's probe as streaming passes over S (DBT_JOIN_FUSED=2, the default: count pass + copy
+    pass; 1: one chained pass): ragged S blocks (the passes read nreserved from the block they stream), results that end
+    exactly on a block boundary, empty results, capacity errors carrying the needed size, agreement with the column path."""
     r, s = orc.gen_ref(77, 240, num_mod=4000)
     rng = np.random.default_rng(3)
     rag = s.copy()
     rag["nreserved"] = rng.integers(0, 101, size=len(rag)).astype(np.uint32)
     rag["nreserved"][::7] = 0
     rag["nreserved"][5] = 100
-    for field in "01":
-        for src in (s, rag):
-            want = orc.hashjoin(r, src, field)
-            got, n = H.dev_hashjoin(dbt, orc, r, src, field)
-            assert n == orc.count_rows(want) and H.same_image(got, want), (field, H.first_diff(got, want))
+    for mode in ("2", "1"):
+        monkeypatch.setenv("DBT_JOIN_FUSED", mode)
+        for field in "01":
+            for src in (s, rag):
+                want = orc.hashjoin(r, src, field)
+                got, n = H.dev_hashjoin(dbt, orc, r, src, field)
+                assert n == orc.count_rows(want) and H.same_image(got, want), (mode, field, H.first_diff(got, want))
+    monkeypatch.delenv("DBT_JOIN_FUSED")
     # exactly k * 100 matches: no partial last block to fix up
     want = orc.hashjoin(r, s, "1")
     k = orc.count_rows(want)
