@@ -26,13 +26,10 @@ OP_SORT, OP_DEDUP, OP_MERGEJOIN, OP_HASHJOIN = 0, 1, 2, 3
 C_ABI_SYMBOLS = [
     "dbt_last_error", "dbt_abi_version", "dbt_device_count",
     "dbt_sort_counters", "dbt_dedup_nios", "dbt_hashjoin_nios", "dbt_mergejoin_nios",
-    "dbt_sort_pairs_ws_bytes", "dbt_sort_pairs_u32", "dbt_gather_records", "dbt_gather_records_limited",
+    "dbt_sort_pairs_ws_bytes", "dbt_sort_pairs_u32", "dbt_gather_records",
     "dbt_dev_extract_keys_u32", "dbt_dev_partition_rows", "dbt_dev_partition_ws_bytes",
     "dbt_dev_ws_bytes", "dbt_dev_ws_bytes_kw", "dbt_dev_hashjoin_ws_bytes", "dbt_dev_mergesort", "dbt_dev_dedup", "dbt_dev_mergejoin", "dbt_dev_hashjoin", "dbt_dev_innerjoin_pairs", "dbt_dev_semijoin_keys",
     "dbt_host_mergesort", "dbt_host_dedup", "dbt_host_mergejoin", "dbt_host_hashjoin",
-    "dbt_dev_extract_key_recid_u32", "dbt_dev_take_u32", "dbt_dev_order_columns", "dbt_dev_order_columns_ws_bytes",
-    "dbt_gather_records_multi", "dbt_ipc_export",
-    "dbt_ipc_alloc", "dbt_ipc_open", "dbt_ipc_close", "dbt_ipc_free",
     "dbt_host_mergesort_begin", "dbt_host_dedup_begin", "dbt_host_mergejoin_begin", "dbt_host_hashjoin_begin",
     "dbt_host_job_wait", "dbt_host_job_slots", "dbt_host_trim", "dbt_host_set_chunk_blocks", "dbt_host_ooc_stats",
     "dbt_host_alloc", "dbt_host_free", "dbt_gen_syn",
@@ -85,7 +82,6 @@ def lib() -> C.CDLL:
     L.dbt_sort_pairs_ws_bytes.argtypes = [u64]
     L.dbt_sort_pairs_u32.argtypes = [vp, vp, vp, vp, u64, ci, ci, vp, sz, vp, C.POINTER(ci)]
     L.dbt_gather_records.argtypes = [vp, vp, vp, u64, vp, vp]
-    L.dbt_gather_records_limited.argtypes = [vp, vp, vp, u64, vp, vp, ci]
     L.dbt_dev_ws_bytes.restype = sz
     L.dbt_dev_ws_bytes.argtypes = [ci, u64, u64, ci]
     L.dbt_dev_ws_bytes_kw.restype = sz
@@ -106,17 +102,6 @@ def lib() -> C.CDLL:
     L.dbt_host_dedup.argtypes = [vp, u64, ci, vp, ci, pu64, pu64]
     L.dbt_host_mergejoin.argtypes = [vp, u64, vp, u64, ci, vp, vp, vp, ci, pu64]
     L.dbt_host_hashjoin.argtypes = [vp, u64, vp, u64, ci, vp, u64, ci, pu64]
-    L.dbt_dev_extract_key_recid_u32.argtypes = [vp, u64, ci, vp, vp, vp, sz, vp, pu64, C.POINTER(ci)]
-    L.dbt_dev_take_u32.argtypes = [vp, vp, u64, vp, vp]
-    L.dbt_dev_order_columns.argtypes = [vp, vp, u64, ci, vp, pu64, vp, sz, vp]
-    L.dbt_dev_order_columns_ws_bytes.restype = sz
-    L.dbt_dev_order_columns_ws_bytes.argtypes = [u64]
-    L.dbt_gather_records_multi.argtypes = [C.POINTER(vp), u32, pu64, vp, vp, u64, vp, vp]
-    L.dbt_ipc_export.argtypes = [vp, C.c_char_p, pu64]
-    L.dbt_ipc_alloc.argtypes = [sz, C.POINTER(vp), C.c_char_p]
-    L.dbt_ipc_open.argtypes = [C.c_char_p, C.POINTER(vp)]
-    L.dbt_ipc_close.argtypes = [vp]
-    L.dbt_ipc_free.argtypes = [vp]
     L.dbt_host_mergesort_begin.argtypes = [ci, vp, u64, ci, vp, ci]
     L.dbt_host_dedup_begin.argtypes = [ci, vp, u64, ci, vp, ci]
     L.dbt_host_mergejoin_begin.argtypes = [ci, vp, u64, vp, u64, ci, vp, vp, vp, ci]

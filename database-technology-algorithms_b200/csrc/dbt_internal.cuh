@@ -68,6 +68,9 @@ struct StageScope { // records events around a stage when timing is enabled
     int slot;
 };
 int device_setup();   // one-time per-process device limits
+// true exactly once per (current device, key): function attributes such as the dynamic shared-memory limit are per
+// device, and one process may drive several GPUs (host_multi.cu), so "set once per process" is not enough
+bool first_use_on_device(const void *key);
 void stage_resolve(); // call after a stream sync: folds pending event pairs into the totals
 
 // ---- workspace bump allocator (no hidden device allocation on the device-scope path) -------

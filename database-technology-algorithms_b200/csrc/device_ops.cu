@@ -461,101 +461,6 @@ extern "C" int dbt_dev_extract_keys_u32(const void *d_in, uint64_t nblocks, int 
     return finish(st);
 }
 
-extern "C" int dbt_dev_extract_key_recid_u32(const void *d_in, uint64_t nblocks, int field, uint32_t *d_keys,
-                                             uint32_t *d_recids, void *d_ws, size_t ws_bytes, void *stream,
-                                             uint64_t *nrows, int *block_dense) {
-    if (field != '0' && field != '1') {
-        set_error("dbt_dev_extract_key_recid_u32: only fields '0' and '1' have u32 keys");
-        return DBT_ERR_UNSUPPORTED;
-    }
-    cudaStream_t st = (cudaStream_t)stream;
-    Arena ws(d_ws, ws_bytes);
-    Prepared p;
-    DBT_TRY(prepare(d_in, nblocks, field, ws, st, &p));
-    if (p.info.nrows) {
-        DBT_CUDA(cudaMemcpyAsync(d_keys, p.keys.w0, 4 * p.info.nrows, cudaMemcpyDeviceToDevice, st));
-        DBT_CUDA(cudaMemcpyAsync(d_recids, p.keys.recid, 4 * p.info.nrows, cudaMemcpyDeviceToDevice, st));
-    }
-    if (nrows) *nrows = p.info.nrows;
-    if (block_dense) *block_dense = p.row_slot ? 0 : 1;
-    return finish(st);
-}
-
-namespace dbt {
-__global__ void __launch_bounds__(256)
-column_stats_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ recids, uint64_t n, uint32_t *out) {
-    // out: or_key, and_key, or_recid, and_recid, recid_unsorted
-    uint32_t ok = 0, ak = 0xFFFFFFFFu, oi = 0, ai = 0xFFFFFFFFu, un = 0;
-    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        uint32_t k = keys[i], r = recids[i];
-        ok |= k; ak &= k; oi |= r; ai &= r;
-        if (i > 0 && r < recids[i - 1]) un = 1;
-    }
-    ok = __reduce_or_sync(0xFFFFFFFFu, ok); ak = __reduce_and_sync(0xFFFFFFFFu, ak);
-    oi = __reduce_or_sync(0xFFFFFFFFu, oi); ai = __reduce_and_sync(0xFFFFFFFFu, ai);
-    un = __reduce_or_sync(0xFFFFFFFFu, un);
-    if ((threadIdx.x & 31) == 0) {
-        atomicOr(&out[0], ok); atomicAnd(&out[1], ak); atomicOr(&out[2], oi); atomicAnd(&out[3], ai);
-        if (un) atomicOr(&out[4], 1u);
-    }
-}
-} // namespace dbt
-
-extern "C" size_t dbt_dev_order_columns_ws_bytes(uint64_t m) { return 5 * pad256(4 * m) + sort_ws_bytes(m) + (1 << 20); }
-
-extern "C" int dbt_dev_order_columns(uint32_t *d_keys, const uint32_t *d_recids, uint64_t m, int dedup, uint32_t *d_order,
-                                     uint64_t *count, void *d_ws, size_t ws_bytes, void *stream) {
-    if (!is_aligned16(d_keys) || !is_aligned16(d_recids) || !is_aligned16(d_order) || !is_aligned16(d_ws)) {
-        set_error("dbt_dev_order_columns: buffers must be 16-byte aligned");
-        return DBT_ERR_ARG;
-    }
-    cudaStream_t st = (cudaStream_t)stream;
-    Arena ws(d_ws, ws_bytes);
-    if (count) *count = 0;
-    if (m == 0) return 0;
-    uint32_t *d_stats = ws.take<uint32_t>(64);
-    if (!d_stats) {
-        set_error("dbt_dev_order_columns: workspace too small");
-        return DBT_ERR_WORKSPACE;
-    }
-    uint32_t h[5] = {0, 0xFFFFFFFFu, 0, 0xFFFFFFFFu, 0};
-    {
-        StageScope sc(ST_MISC, st);
-        DBT_CUDA(cudaMemcpyAsync(d_stats, h, sizeof h, cudaMemcpyHostToDevice, st));
-        int grid = (int)std::min<uint64_t>((m + 255) / 256, 148 * 8);
-        column_stats_kernel<<<grid, 256, 0, st>>>(d_keys, d_recids, m, d_stats);
-        count_launch();
-        DBT_CUDA(cudaMemcpyAsync(h, d_stats, sizeof h, cudaMemcpyDeviceToHost, st));
-        DBT_CUDA(cudaStreamSynchronize(st));
-    }
-    KeyCols k;
-    memset(&k, 0, sizeof k);
-    k.w0 = d_keys;
-    k.recid = const_cast<uint32_t *>(d_recids);
-    k.n = m;
-    k.kw = 8;
-    k.vary_w0 = h[0] ^ h[1];
-    k.vary_recid = h[2] ^ h[3];
-    k.recid_unsorted = (int)h[4];
-    uint32_t *perm, *sorted;
-    DBT_TRY(sort_rows_by_key(k, '1', ws, st, &perm, &sorted)); // '1': a one-word key in w0, recid as the tie-break word
-    uint64_t out_n = m;
-    if (dedup) {
-        uint64_t *d_cnt = ws.take<uint64_t>(8);
-        if (!d_cnt) {
-            set_error("dbt_dev_order_columns: workspace too small");
-            return DBT_ERR_WORKSPACE;
-        }
-        DBT_TRY(unique_rows(k, '1', perm, sorted, m, d_order, nullptr, d_cnt, ws, st));
-        DBT_TRY(read_u64(d_cnt, &out_n, 1, st));
-    } else {
-        DBT_CUDA(cudaMemcpyAsync(d_order, perm, 4 * m, cudaMemcpyDeviceToDevice, st));
-    }
-    if (count) *count = out_n;
-    return finish(st);
-}
-
 extern "C" int dbt_dev_partition_rows(const uint32_t *d_keys, uint64_t n, int mode, const uint32_t *h_splitters,
                                       uint32_t nparts, uint32_t *d_rows_grouped, uint64_t *h_counts, void *d_ws,
                                       size_t ws_bytes, void *stream) {

@@ -181,11 +181,15 @@ template <class F> static int on_all_ranks(F fn) {
             if (rc[r]) msg[r] = dbt_last_error();
         });
     for (auto &t : th) t.join();
+    // report the rank that failed first-hand (the others only learn "a peer rank failed" from the control block)
+    int first = -1;
     for (size_t r = 0; r < P; ++r)
-        if (rc[r]) {
-            set_error("rank " + std::to_string(r) + ": " + msg[r]);
-            return rc[r];
-        }
+        if (rc[r] && (first < 0 || (msg[first].find("a peer rank failed") != std::string::npos && msg[r].find("a peer rank failed") == std::string::npos)))
+            first = (int)r;
+    if (first >= 0) {
+        set_error("rank " + std::to_string(first) + ": " + msg[first]);
+        return rc[first];
+    }
     return 0;
 }
 

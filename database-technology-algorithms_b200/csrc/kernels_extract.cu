@@ -408,8 +408,8 @@ static int launch_extract_stream(const uint32_t *img, uint64_t nblocks, uint64_t
     size_t smem = sizeof(uint32_t) * kBlockWords * kExStages + 8 * kExStages + 128;
     auto kfn = extract_stream_kernel<FIELD>;
     static int per_sm = 0; // resident CTAs per SM: the grid is exactly one wave of them
+    if (first_use_on_device((const void *)kfn)) DBT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (!per_sm) {
-        DBT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
         DBT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, kExThreads, smem));
         if (const char *e = getenv("DBT_EXTRACT_CTAS")) occ = std::min(occ, atoi(e));

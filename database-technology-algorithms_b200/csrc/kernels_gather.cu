@@ -188,11 +188,8 @@ static int run_scan_emit(uint64_t n, CountFn cnt, EmitFn emit, uint64_t *d_total
     DBT_CUDA(cudaMemsetAsync(sw.ctr, 0, 4, st));
     const size_t smem = (size_t)kScanTile * 4 * (EmitFn::kTwo ? 2 : 1);
     auto kfn = scan_emit_kernel<CountFn, EmitFn>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (first_use_on_device((const void *)kfn))
         DBT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
     kfn<<<(unsigned)ntiles, kScanThreads, smem, st>>>(n, cnt, emit, sw, (unsigned long long *)d_total);
     count_launch();
     DBT_KERNEL_CHECK();
@@ -516,85 +513,6 @@ gather_kernel(const uint32_t *__restrict__ in, const uint32_t *__restrict__ rows
     }
 }
 
-// ---- gather from several images (multi-GPU final gather: peers' images are read over NVLink) ----
-struct MultiSrc {
-    const uint32_t *base[16];
-    unsigned long long seg_start[17]; // received-column index range of every source
-    uint32_t nsrc;
-};
-__global__ void __launch_bounds__(kGatherThreads)
-gather_multi_kernel(MultiSrc ms, const uint32_t *__restrict__ order, const uint32_t *__restrict__ rrow, uint64_t nrows_out,
-                    uint4 *__restrict__ out, uint64_t nblocks_out) {
-    __shared__ __align__(16) uint32_t stage[kBlockWords];
-    __shared__ const uint32_t *src[kRpb];
-    const int tid = threadIdx.x;
-    for (uint64_t ob = blockIdx.x; ob < nblocks_out; ob += gridDim.x) {
-        const uint64_t r0 = ob * kRpb;
-        const uint32_t cnt = (uint32_t)min((uint64_t)kRpb, nrows_out - r0);
-        if (tid < (int)cnt) {
-            const uint32_t idx = order[r0 + tid];
-            uint32_t s = 0;
-            while (s + 1 < ms.nsrc && (unsigned long long)idx >= ms.seg_start[s + 1]) ++s;
-            const uint64_t row = rrow ? (uint64_t)rrow[idx] : (uint64_t)idx - ms.seg_start[s]; // null: k-th tuple <-> k-th row
-            src[tid] = ms.base[s] + slot_word(row);
-        }
-        if (tid == 0) {
-            stage[0] = (uint32_t)ob;
-            stage[1] = cnt;
-            stage[kTrailerWord] = 1;
-            stage[kTrailerWord + 1] = cnt;
-        }
-        __syncthreads();
-        // 16-byte aligned window loads: a 140-byte record at 4-byte alignment lies inside 10 aligned uint4 (160 B).
-        // One LDG.128 instead of four LDG.32 -- what matters for the peer (NVLink) reads, whose cost is per request.
-        constexpr int kVecPerRec = 10;
-        constexpr int kVecPerThread = (kRpb * kVecPerRec + kGatherThreads - 1) / kGatherThreads; // 4
-        uint4 v[kVecPerThread];
-        int rec_of[kVecPerThread], w0_of[kVecPerThread];
-#pragma unroll
-        for (int k = 0; k < kVecPerThread; ++k) {
-            const uint32_t idx = tid + k * kGatherThreads;
-            const uint32_t rec = idx / kVecPerRec, q = idx - rec * kVecPerRec;
-            rec_of[k] = -1;
-            v[k] = make_uint4(0, 0, 0, 0);
-            if (rec < cnt) {
-                const uintptr_t a = (uintptr_t)src[rec];
-                const uint4 *win = reinterpret_cast<const uint4 *>(a & ~(uintptr_t)15);
-                const int shift = (int)((a & 15) >> 2);          // words to skip in the first vector
-                if ((int)q * 4 - shift < (int)kRecWords) {        // this vector still overlaps the record
-                    v[k] = win[q];
-                    rec_of[k] = (int)rec;
-                    w0_of[k] = (int)q * 4 - shift;               // record word index of v[k].x
-                }
-            }
-        }
-        // zero the unused tail of a partial block
-        for (uint32_t i = cnt * kRecWords + tid; i < kRpb * kRecWords; i += kGatherThreads) stage[kEntriesWord + i] = 0u;
-#pragma unroll
-        for (int k = 0; k < kVecPerThread; ++k) {
-            if (rec_of[k] >= 0) {
-                uint32_t *d = stage + kEntriesWord + rec_of[k] * kRecWords;
-                const int w = w0_of[k];
-                if (w >= 0 && w < (int)kRecWords) d[w] = v[k].x;
-                if (w + 1 >= 0 && w + 1 < (int)kRecWords) d[w + 1] = v[k].y;
-                if (w + 2 >= 0 && w + 2 < (int)kRecWords) d[w + 2] = v[k].z;
-                if (w + 3 >= 0 && w + 3 < (int)kRecWords) d[w + 3] = v[k].w;
-            }
-        }
-        __syncthreads();
-        const uint4 *sv = reinterpret_cast<const uint4 *>(stage);
-        uint4 *dst = out + ob * kBlockVec4;
-        for (uint32_t i = tid; i < kBlockVec4; i += kGatherThreads) dst[i] = sv[i];
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(256)
-take_kernel(const uint32_t *__restrict__ src, const uint32_t *__restrict__ idx, uint64_t n, uint32_t *__restrict__ out) {
-    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = src[idx[i]];
-}
-
 int gather_records(const void *d_in, const uint32_t *d_rows, const uint32_t *d_row_slot, uint64_t nrows_out, void *d_out,
                    cudaStream_t st, int max_ctas, uint32_t blockid0) {
     StageScope sc(ST_GATHER, st);
@@ -615,38 +533,6 @@ int gather_records(const void *d_in, const uint32_t *d_rows, const uint32_t *d_r
 
 } // namespace dbt
 
-extern "C" int dbt_dev_take_u32(const uint32_t *d_src, const uint32_t *d_idx, uint64_t n, uint32_t *d_out, void *stream) {
-    if (!n) return 0;
-    int grid = (int)std::min<uint64_t>((n + 255) / 256, 148 * 16);
-    dbt::take_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_src, d_idx, n, d_out);
-    dbt::count_launch();
-    DBT_KERNEL_CHECK();
-    return 0;
-}
-
-extern "C" int dbt_gather_records_multi(const void *const *h_bases, uint32_t nsrc, const uint64_t *h_seg_start,
-                                        const uint32_t *d_order, const uint32_t *d_row, uint64_t count, void *d_out,
-                                        void *stream) {
-    if (nsrc == 0 || nsrc > 16 || !h_bases || !h_seg_start) {
-        dbt::set_error("dbt_gather_records_multi: 1 <= nsrc <= 16");
-        return DBT_ERR_ARG;
-    }
-    if (!count) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    dbt::StageScope sc(dbt::ST_GATHER, st);
-    dbt::MultiSrc ms;
-    memset(&ms, 0, sizeof ms);
-    ms.nsrc = nsrc;
-    for (uint32_t i = 0; i < nsrc; ++i) ms.base[i] = (const uint32_t *)h_bases[i];
-    for (uint32_t i = 0; i <= nsrc; ++i) ms.seg_start[i] = h_seg_start[i];
-    uint64_t nb = (count + dbt::kRpb - 1) / dbt::kRpb;
-    int grid = (int)std::min<uint64_t>(nb, 148 * 8 * 4);
-    dbt::gather_multi_kernel<<<grid, dbt::kGatherThreads, 0, st>>>(ms, d_order, d_row, count, (uint4 *)d_out, nb);
-    dbt::count_launch();
-    DBT_KERNEL_CHECK();
-    return 0;
-}
-
 extern "C" int dbt_gather_records(const void *d_in_image, const uint32_t *d_rows, const uint32_t *d_row_slot,
                                   uint64_t nrows_out, void *d_out_image, void *stream) {
     if (!d_in_image || !d_out_image) {
@@ -658,13 +544,4 @@ extern "C" int dbt_gather_records(const void *d_in_image, const uint32_t *d_rows
         return DBT_ERR_ARG;
     }
     return dbt::gather_records(d_in_image, d_rows, d_row_slot, nrows_out, d_out_image, (cudaStream_t)stream, 0);
-}
-
-extern "C" int dbt_gather_records_limited(const void *d_in_image, const uint32_t *d_rows, const uint32_t *d_row_slot,
-                                          uint64_t nrows_out, void *d_out_image, void *stream, int max_ctas) {
-    if (!d_in_image || !d_out_image || ((uintptr_t)d_out_image & 15)) {
-        dbt::set_error("dbt_gather_records_limited: NULL or misaligned image (output must be 16-byte aligned)");
-        return DBT_ERR_ARG;
-    }
-    return dbt::gather_records(d_in_image, d_rows, d_row_slot, nrows_out, d_out_image, (cudaStream_t)stream, max_ctas);
 }

@@ -589,11 +589,8 @@ int intersect_sorted(const KeyCols &r, const uint32_t *d_ur, const uint32_t *d_u
         const size_t smem = (size_t)(kMpTile + 1) * kwt * 4;
         if (ok && a_start && smem <= 200 * 1024) {
             mp_partition_kernel<<<(unsigned)((ntiles + 1 + 255) / 256), 256, 0, st>>>(A, nur, B, nus, kwt, ntiles, a_start);
-            static bool attr_done = false;
-            if (!attr_done) {
+            if (first_use_on_device((const void *)mp_intersect_kernel))
                 DBT_CUDA(cudaFuncSetAttribute(mp_intersect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                attr_done = true;
-            }
             mp_intersect_kernel<<<(unsigned)ntiles, kMpThreads, smem, st>>>(A, nur, B, nus, kwt, a_start, d_flags);
             count_launch(2);
         } else { // not enough workspace for the contiguous copies: binary search through the row lists

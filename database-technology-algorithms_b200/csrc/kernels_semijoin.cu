@@ -431,8 +431,8 @@ int semijoin_two_pass(const void *d_s_img, uint64_t nblocks_s, int field, const 
     static int per_sm[3] = {0, 0, 0};
     const int f = field == '0' ? 0 : 1;
     auto occupancy = [&](const void *fn, int idx) -> int {
+        if (first_use_on_device(fn)) DBT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (!per_sm[idx]) {
-            DBT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int occ = 0;
             DBT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kTpThreads, smem));
             per_sm[idx] = std::max(occ, 1);

@@ -638,11 +638,8 @@ static int launch_onesweep_t(const uint32_t *kin, uint32_t *kout, const uint32_t
 #define DBT_LAUNCH_OS(HV, IO)                                                                                     \
     do {                                                                                                          \
         auto kfn = onesweep_kernel<THREADS, ITEMS, HV, IO>;                                                       \
-        static bool attr_done = false;                                                                            \
-        if (!attr_done) {                                                                                         \
+        if (first_use_on_device((const void *)kfn))                                                               \
             DBT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
-            attr_done = true;                                                                                     \
-        }                                                                                                         \
         kfn<<<ntiles, THREADS, smem, st>>>(kin, kout, vin, vout, n, shift, digit_base, state, ctr);               \
     } while (0)
     if (!has_vals) DBT_LAUNCH_OS(false, false);
@@ -681,11 +678,8 @@ static int launch_onesweep2_t(const uint32_t *kin, uint32_t *kout, const uint32_
 #define DBT_LAUNCH_OS2(IO, RK)                                                                                   \
     do {                                                                                                         \
         auto kfn = onesweep2_kernel<THREADS, ITEMS, true, IO, RK>;                                               \
-        static bool attr_done = false;                                                                           \
-        if (!attr_done) {                                                                                        \
+        if (first_use_on_device((const void *)kfn))                                                              \
             DBT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-            attr_done = true;                                                                                    \
-        }                                                                                                        \
         kfn<<<grid, THREADS, smem, st>>>(kin, kout, vin, vout, n, shift, digit_base, state, ctr);                \
     } while (0)
     if (iota) {

@@ -85,6 +85,18 @@ void stage_resolve() {
 // for the 140-byte random reads and has no effect on B200, profiles/micro/l2gran.cu).
 int device_setup() { return 0; }
 
+bool first_use_on_device(const void *key) {
+    static std::mutex mu;
+    static std::vector<std::pair<int, const void *>> seen;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    for (const auto &e : seen)
+        if (e.first == dev && e.second == key) return false;
+    seen.emplace_back(dev, key);
+    return true;
+}
+
 } // namespace dbt
 
 using namespace dbt;
@@ -152,56 +164,6 @@ uint64_t dbt_mergejoin_nios(uint64_t BR, uint64_t BS, uint32_t M, const uint64_t
     // both dedups + the 2 first block reads + later reads of the two-pointer walk + output blocks
     // (reference: DatabaseProject.cpp:395,405,441,465,475,491)
     return dbt_dedup_nios(BR, M, res[1]) + dbt_dedup_nios(BS, M, res[2]) + 2 + res[3] + (res[0] + kRpb - 1) / kRpb;
-}
-
-// ---- peer memory (CUDA IPC) for the fused gather + exchange --------------------------------------
-int dbt_ipc_alloc(size_t bytes, void **d_ptr, unsigned char handle[64]) {
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    DBT_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 256));
-    cudaIpcMemHandle_t h;
-    DBT_CUDA(cudaIpcGetMemHandle(&h, *d_ptr));
-    memcpy(handle, &h, 64);
-    return 0;
-}
-int dbt_ipc_export(const void *d_ptr, unsigned char handle[64], uint64_t *offset) {
-    // cudaIpcGetMemHandle wants the allocation's base pointer: ask the driver for the address range
-    typedef int (*range_fn)(unsigned long long *, size_t *, unsigned long long);
-    static range_fn fn = nullptr;
-    if (!fn) {
-        void *sym = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        DBT_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &sym, cudaEnableDefault, &q));
-        fn = (range_fn)sym;
-        if (!fn) {
-            set_error("cuMemGetAddressRange unavailable");
-            return DBT_ERR_CUDA;
-        }
-    }
-    unsigned long long base = 0;
-    size_t size = 0;
-    if (fn(&base, &size, (unsigned long long)(uintptr_t)d_ptr) != 0) {
-        set_error("dbt_ipc_export: pointer is not inside a device allocation");
-        return DBT_ERR_ARG;
-    }
-    cudaIpcMemHandle_t h;
-    DBT_CUDA(cudaIpcGetMemHandle(&h, (void *)(uintptr_t)base));
-    memcpy(handle, &h, 64);
-    *offset = (uint64_t)((uintptr_t)d_ptr - base);
-    return 0;
-}
-int dbt_ipc_open(const unsigned char handle[64], void **d_ptr) {
-    cudaIpcMemHandle_t h;
-    memcpy(&h, handle, 64);
-    DBT_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
-    return 0;
-}
-int dbt_ipc_close(void *d_ptr) {
-    DBT_CUDA(cudaIpcCloseMemHandle(d_ptr));
-    return 0;
-}
-int dbt_ipc_free(void *d_ptr) {
-    DBT_CUDA(cudaFree(d_ptr));
-    return 0;
 }
 
 int dbt_host_alloc(void **p, size_t bytes) {

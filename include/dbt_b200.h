@@ -85,11 +85,6 @@ int dbt_sort_pairs_u32(uint32_t *d_keys, uint32_t *d_keys_alt, uint32_t *d_vals,
  * d_row_slot may be NULL when every input block except the last is full (slot == row). */
 int dbt_gather_records(const void *d_in_image, const uint32_t *d_rows, const uint32_t *d_row_slot, uint64_t nrows_out,
                        void *d_out_image, void *stream);
-/* same, with the grid capped at max_ctas CTAs (0 = no cap): for link-bound gathers (output in peer memory) that
- * should leave SMs to kernels running concurrently on other streams */
-int dbt_gather_records_limited(const void *d_in_image, const uint32_t *d_rows, const uint32_t *d_row_slot,
-                               uint64_t nrows_out, void *d_out_image, void *stream, int max_ctas);
-
 /* ----------------------------------------------------------------------------------------------
  * Device-scope operators: image in HBM -> image in HBM.  `d_out` must hold
  * ceil(rows/100) blocks where rows is the worst case for the operator (input rows for sort /
@@ -150,13 +145,9 @@ int dbt_dev_innerjoin_pairs(const void *d_in_r, uint64_t nblocks_r, const void *
                             uint64_t *npairs);
 
 /* ----------------------------------------------------------------------------------------------
- * Multi-GPU building blocks.  The operators shard by KEY: sort / dedup by key range
- * (sample-sort splitters, so equal keys meet on one GPU and the concatenation of the ranks' outputs
- * is globally ordered), joins by key hash.  Each rank: extract keys -> choose a destination per row ->
- * group its rows by destination -> gather each group into its own block image -> ONE all-to-all of
- * images (NCCL, issued by the caller) -> the ordinary device-scope operator on what it received.
- * Routing uses the key's most significant word (recid, num, or the first four str bytes): equal keys share it, so
- * every field shards; the columns-only strategies of dist.py ("keys", "overlap") are for the u32 fields '0'/'1'.
+ * Multi-GPU building blocks, used by the C++ layer below and usable on their own: the routing word of
+ * every row (the key's most significant word: recid, num, or the first four str bytes -- equal keys share it, so
+ * every field shards on it) and the rows grouped by destination.
  * ---------------------------------------------------------------------------------------------- */
 /* routing word of every live row in file order (recid | num | first 4 bytes of str, NUL-normalised, big-endian);
  * *nrows receives the count */
@@ -169,37 +160,6 @@ int dbt_dev_extract_keys_u32(const void *d_in, uint64_t nblocks, int field, uint
 int dbt_dev_partition_rows(const uint32_t *d_keys, uint64_t n, int mode, const uint32_t *h_splitters, uint32_t nparts,
                            uint32_t *d_rows_grouped, uint64_t *h_counts, void *d_ws, size_t ws_bytes, void *stream);
 size_t dbt_dev_partition_ws_bytes(uint64_t nblocks);
-
-/* Peer memory for the fused gather+exchange: a rank's receive buffer is allocated with dbt_ipc_alloc,
- * its 64-byte handle is handed to the other ranks (any transport), and they map it with dbt_ipc_open.
- * dbt_gather_records then takes the mapped pointer as its output image: the gather kernel's 16-byte
- * stores travel over NVLink straight into the owner's HBM -- no send buffer, no separate collective. */
-/* Multi-GPU sort / dedup without moving records twice ("rows stay put"): only (key, recid, row) columns
- * are exchanged; the owner of a key range orders what it received with dbt_dev_order_columns and then
- * pulls the winning records straight out of the peers' input images (mapped with dbt_ipc_export /
- * dbt_ipc_open) into their final positions with dbt_gather_records_multi.  u32 keys. */
-int dbt_dev_extract_key_recid_u32(const void *d_in, uint64_t nblocks, int field, uint32_t *d_keys, uint32_t *d_recids,
-                                  void *d_ws, size_t ws_bytes, void *stream, uint64_t *nrows, int *block_dense);
-/* out[i] = src[idx[i]] */
-int dbt_dev_take_u32(const uint32_t *d_src, const uint32_t *d_idx, uint64_t n, uint32_t *d_out, void *stream);
-/* Order m (key, recid) tuples by (key, recid) (stable beyond that) and optionally keep the first of every key:
- * d_order receives indices into the input columns, *count their number.  d_keys is clobbered. */
-int dbt_dev_order_columns(uint32_t *d_keys, const uint32_t *d_recids, uint64_t m, int dedup, uint32_t *d_order,
-                          uint64_t *count, void *d_ws, size_t ws_bytes, void *stream);
-size_t dbt_dev_order_columns_ws_bytes(uint64_t m);
-/* Record gather from several (block-dense) images: output row j is row d_row[d_order[j]] of image s, where s is
- * the segment of the received columns that index d_order[j] falls into (h_seg_start[nsrc+1], host memory);
- * h_bases[nsrc] are device pointers (local or peer-mapped).  d_row == NULL means the k-th index of segment s is
- * row k of image s (the images were filled in the same order as the columns). */
-int dbt_gather_records_multi(const void *const *h_bases, uint32_t nsrc, const uint64_t *h_seg_start,
-                             const uint32_t *d_order, const uint32_t *d_row, uint64_t count, void *d_out, void *stream);
-
-/* handle + byte offset of any device pointer inside a cudaMalloc allocation (for mapping on the peers) */
-int dbt_ipc_export(const void *d_ptr, unsigned char handle[64], uint64_t *offset);
-int dbt_ipc_alloc(size_t bytes, void **d_ptr, unsigned char handle[64]);
-int dbt_ipc_open(const unsigned char handle[64], void **d_ptr);
-int dbt_ipc_close(void *d_ptr);
-int dbt_ipc_free(void *d_ptr);
 
 /* ----------------------------------------------------------------------------------------------
  * Multi-GPU operators (C++ host layer, csrc/dist.cu).  One RANK per GPU of one box.  Ranks are
