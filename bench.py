@@ -363,6 +363,15 @@ def main():
         "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "gpu_launches": launches,
         "stage_ms_per_step": stage_ms, "stage_hbm_frac": per_stage_frac, "extra": extra,
     }
+    summary = {"cfg1_dedup_100M": {"ms": round(ms_step, 2), "Grec_s": round(value / 1e9, 2), "e2e_ms": round(e2e["ms_per_step"], 1) if e2e else None}}
+    for k, v in extra.items():  # compact: the driver keeps the last 1500 characters of stdout
+        if isinstance(v, dict):
+            e = v.get("dbt_b200_entry_point", v)
+            summary[k] = {a: (round(b, 2) if isinstance(b, float) else b) for a, b in e.items()
+                          if a in ("ms", "nres", "error", "nunique", "hbm_frac_of_measured_at_68B_per_record", "s_passes_hbm_frac_of_measured")}
+            if "reference" in v and v["reference"]:
+                summary[k]["ref_cpu_ms"] = round(v["reference"]["ms"], 1)
+    line["summary"] = summary
     print(json.dumps(line))
     return 0
 
@@ -836,7 +845,7 @@ def extra_measurements(dbt, torch, dev, peak):
         out["cfg0_mergesort_1M_record_file"] = {"error": str(e)[:200]}
     # HashJoin field=num, R=100M x S=400M rows (BASELINE configs[3] asks for S=1B: 140 GB of S records do not
     # fit beside R and the output on one 180 GB GPU, so the single-GPU figure uses the largest S that does)
-    for kind, label in ((1, "uniform"), (2, "skewed")):
+    for kind, label in ((1, "uniform"), (4, "zipf1.1")):
         try:
             nr, ns, D = 100_000_000, 400_000_000, 100_000_000
             nbr, nbs = nr // RPB, ns // RPB
@@ -862,15 +871,18 @@ def extra_measurements(dbt, torch, dev, peak):
             rep = dbt.stage_report()
             L.dbt_stage_timing_enable(0)
             ms = sum(times) / len(times)
-            probe_ms = rep["hash_probe"][0]
+            probe_ms = rep["hash_probe"][0] + rep.get("record_gather", (0.0, 0))[0]  # the two streaming passes over S
             sel = k / ns
             out[f"hashjoin_R100M_S400M_{label}"] = {
                 "probe_tuples_per_s": ns / (ms * 1e-3), "ms": ms, "nres": k, "selectivity": sel,
                 "stage_ms": {a: round(b[0], 3) for a, b in rep.items()},
-                "probe_kernel_hbm_frac_of_measured": (8 + 4 * sel) * ns / (probe_ms * 1e-3) / 1e9 / peak,
-                "note": "semi-join (reference semantics): S rows in S order whose key is in keys(R); probe kernel = "
-                        "L2-resident bitmap test because keys(R) span < 2^29; whole operator includes extraction of "
-                        "both images and the gather of the matching S records"}
+                "s_passes_hbm_frac_of_measured": (140 + 140 * sel) * ns / (probe_ms * 1e-3) / 1e9 / peak,
+                "s_passes_actual_bytes_frac_of_measured": (280 + 140 * sel) * ns / (probe_ms * 1e-3) / 1e9 / peak,
+                "note": "semi-join (reference semantics): S rows in S order whose key is in keys(R).  R: extraction + "
+                        "direct-address bitmap (L2-resident: keys(R) span < 2^29).  S: two streaming passes over the image "
+                        "(count per block, scan, copy the matching records to their final place): algorithmic 140 B read + "
+                        "140 B written per match; actual 280 B read (S is read twice, sequentially, instead of once "
+                        "sequentially + once as a random gather at 267 B per match)"}
             del d_r, d_s, d_o, ws
             torch.cuda.empty_cache()
         except Exception as e:  # noqa: BLE001
@@ -918,7 +930,7 @@ def extra_measurements(dbt, torch, dev, peak):
     # BASELINE configs[3] at ONE GPU: HashJoin field=num, R = 100M x S = 1B records.  S (140 GB) cannot be resident beside
     # R and the output, so it streams through HBM in 10 chunks of 100M records (generated in place between the timed
     # probes, the way a chunk would arrive from storage); R's key column is extracted once and stays resident.
-    for kind, label in ((1, "uniform"), (2, "skewed")):
+    for kind, label in ((1, "uniform"), (4, "zipf1.1")):
         try:
             nr, ns, D, nchunk = 100_000_000, 1_000_000_000, 100_000_000, 10
             rows_c = ns // nchunk
@@ -960,9 +972,9 @@ def extra_measurements(dbt, torch, dev, peak):
                 "probe_tuples_per_s": ns / (ms * 1e-3), "ms": ms, "ms_extract_R_keys": ms_r, "ms_probe_chunks": ms_s,
                 "chunks": nchunk, "nres": total, "selectivity": total / ns,
                 "note": "BASELINE configs[3] at 1 GPU, device scope: S streams through HBM in 10 chunks of 100M records "
-                        "(dbt_dev_semijoin_keys per chunk: extraction, bitmap build + probe, compaction, gather of the "
-                        "matching S records), R's keys resident; same generator and seeds as the 8-GPU run of "
-                        "profiles/dist_configs.py, so nres must equal that run's"}
+                        "(dbt_dev_semijoin_keys per chunk: bitmap of R's keys, two streaming passes over the chunk), R's keys "
+                        "resident; same generator and seeds as the multi-GPU configs[3] leg, so nres must equal that run's "
+                        "(632,100,452 uniform / 711,420,513 Zipf(1.1))"}
             del d_s, d_o, ws, rkeys
             torch.cuda.empty_cache()
         except Exception as e:  # noqa: BLE001

@@ -187,6 +187,9 @@ int unique_sorted(const KeyCols &k, const KeyCols &compact, int field, const uin
 
 // joins (kernels_join.cu)
 size_t hash_table_slots(uint64_t nr);
+// radix-partitioned build / probe with per-partition shared-memory tables on exact 64-bit keys (hi may be null)
+int radix_join_counts(const uint32_t *r_hi, const uint32_t *r_lo, uint64_t nr, const uint32_t *s_hi, const uint32_t *s_lo, uint64_t ns,
+                      bool multi, uint32_t *d_counts, bool *overflowed, Arena &ws, cudaStream_t st);
 int build_key_bitmap(const uint32_t *d_keys, uint64_t n, Arena &ws, cudaStream_t st, uint32_t **bm, uint32_t *base,
                      uint32_t *span);
 // one streaming pass over the S image (kernels_semijoin.cu): matching records go straight to the packed output image;

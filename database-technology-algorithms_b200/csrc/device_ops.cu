@@ -359,6 +359,7 @@ extern "C" size_t dbt_dev_ws_bytes_kw(int op, uint64_t nbr, uint64_t nbs, int fi
         b += rel_bytes(nbr, field, kw, false) + rel_bytes(nbs, field, kw, false) + 2 * pad256(4 * hash_table_slots(nr)) +
              2 * pad256(4 * ns) + scan + 4096;
         if (field != '3') b += (1ull << 29) + 4096 + pad256(4 * nr) + pad256(4 * ns); // the full-range key bitmap (512 MB); compact str keys
+        if (field >= '2') b += 6 * pad256(4 * nr) + 10 * pad256(4 * ns) + 2 * sort_ws_bytes(std::max(nr, ns)) + (16u << 20); // radix partitioning: key words, mixed keys (ping/pong), rows, partition starts
         break;
     default: return 0;
     }
@@ -800,11 +801,16 @@ extern "C" int dbt_dev_hashjoin(const void *d_in_r, uint64_t nbr, const void *d_
         // u32 paths (direct-address bitmap, sliced bitmap, u32 table) replace the 32-byte-key hash table
         KeyCols rk = pr.keys, sk = ps.keys;
         int jf = field;
-        if (field == '2') {
+        bool have_counts = false;
+        if (field >= '2') {
+            // Keys whose varying bits (over R and S together) fit 64 bits are joined as those bits -- an exact key of one
+            // or two words.  One word and set semantics (field '2'): the u32 paths (direct-address bitmap).  Otherwise:
+            // radix-partitioned build / probe with per-partition tables in shared memory (field '3' carries a multiplicity
+            // counter per key).  Wider keys, or a partition that overflows its table, use the linear-probing table in HBM.
             KeyCols j;
             CompactPlan plan;
             const int bits = joint_compaction(pr.keys, ps.keys, field, &plan, &j);
-            if (bits && bits <= 32) {
+            if (field == '2' && bits && bits <= 32) {
                 uint32_t *lo_r = ws.take<uint32_t>(pr.info.nrows), *lo_s = ws.take<uint32_t>(ns);
                 if (lo_r && lo_s) {
                     DBT_TRY(launch_compaction(pr.keys, field, plan, lo_r, nullptr, st));
@@ -813,9 +819,23 @@ extern "C" int dbt_dev_hashjoin(const void *d_in_r, uint64_t nbr, const void *d_
                     sk.w0 = lo_s;
                     jf = '1';
                 }
+            } else if (bits && bits <= 64 && getenv("DBT_JOIN_NO_RADIX") == nullptr) {
+                const size_t m1 = ws.mark();
+                const uint64_t nr = pr.info.nrows;
+                uint32_t *lo_r = ws.take<uint32_t>(nr), *lo_s = ws.take<uint32_t>(ns);
+                uint32_t *hi_r = bits > 32 ? ws.take<uint32_t>(nr) : nullptr, *hi_s = bits > 32 ? ws.take<uint32_t>(ns) : nullptr;
+                if (lo_r && lo_s && (bits <= 32 || (hi_r && hi_s))) {
+                    DBT_TRY(launch_compaction(pr.keys, field, plan, lo_r, hi_r, st));
+                    DBT_TRY(launch_compaction(ps.keys, field, plan, lo_s, hi_s, st));
+                    bool over = false;
+                    int rc = radix_join_counts(hi_r, lo_r, nr, hi_s, lo_s, ns, field == '3', counts, &over, ws, st);
+                    if (rc == 0 && !over) have_counts = true;
+                    else if (rc != DBT_ERR_WORKSPACE && rc != 0) return rc;
+                }
+                ws.release(m1);
             }
         }
-        DBT_TRY(hash_join_counts(rk, sk, jf, counts, ws, st));
+        if (!have_counts) DBT_TRY(hash_join_counts(rk, sk, jf, counts, ws, st));
         DBT_TRY(compact_select(counts, nullptr, ns, rows, rows_cap, d_total, ws, st));
         uint64_t total = 0;
         DBT_TRY(read_u64(d_total, &total, 1, st));

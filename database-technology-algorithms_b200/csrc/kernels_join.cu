@@ -378,6 +378,224 @@ int hash_join_counts(const KeyCols &r, const KeyCols &s, int field, uint32_t *d_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Radix-partitioned build / probe with per-partition open-addressing tables in SHARED memory
+// (north_star; the table's shape -- linear probing, duplicate-rejecting insert -- is the reference's
+// HashTable.cpp:32-91, its use DatabaseProject.cpp:537-544 (build) and :604-629 (probe, multiplicity for field '3')).
+//
+// For keys that are exact 64-bit values (str / num+str keys whose varying bits over R and S together fit 64 bits; the
+// order-preserving compaction of device_ops.cu makes them): both sides are grouped by the top B bits of a mixing hash
+// of the key -- one or two onesweep passes over (partition id, row) pairs, the same scatter the sort uses -- with B
+// chosen so that a partition of R holds ~2,000 rows.  One CTA per partition then builds the partition's table in
+// shared memory (key + multiplicity counter, atomicCAS on the 64-bit key), streams the partition's S rows through it
+// and writes, per S row, how often the reference would emit it.  Every access that can miss is a 4-byte column read
+// through the grouped row list (one sector); the table itself never leaves the SM.  The linear-probing table in HBM
+// above stays as the fallback: keys wider than 64 varying bits, or a partition with more distinct keys than a table holds.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kPartSlots = 8192;             // 64 KB of keys + 32 KB of counters: two CTAs per SM
+constexpr uint32_t kPartTargetRows = 2048;        // R rows per partition the partition count aims at
+constexpr unsigned long long kPartEmpty = ~0ull;  // (the all-ones key itself is counted on the side)
+
+// A BIJECTION of the 64-bit key (the finalizer of MurmurHash3: xor-shifts and odd multiplications, each invertible):
+// equal mixed keys <=> equal keys, so the mixed key can stand in for the key everywhere, and its top bits are the
+// partition id.  That is what lets the key travel THROUGH the partition passes as the (key, value) pair the onesweep
+// kernel moves anyway -- the join kernel then reads a partition's keys sequentially instead of fetching them through
+// a row list (one random 128-byte DRAM access per 4-byte word: the first version spent 5.8 of its 8.7 ms there).
+__device__ __forceinline__ uint64_t mix_key64(uint32_t hi, uint32_t lo) {
+    uint64_t x = ((uint64_t)hi << 32) | lo;
+    x ^= x >> 33;
+    x *= 0xFF51AFD7ED558CCDull;
+    x ^= x >> 33;
+    x *= 0xC4CEB9FE1A85EC53ull;
+    x ^= x >> 33;
+    return x;
+}
+__global__ void __launch_bounds__(256)
+mix_keys_kernel(const uint32_t *__restrict__ hi, const uint32_t *__restrict__ lo, uint64_t n, uint32_t *__restrict__ mhi,
+                uint32_t *__restrict__ mlo, uint32_t *__restrict__ mhi2 /*second copy of mhi (or null)*/) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t m = mix_key64(hi ? hi[i] : 0u, lo[i]);
+        mhi[i] = (uint32_t)(m >> 32);
+        mlo[i] = (uint32_t)m;
+        if (mhi2) mhi2[i] = (uint32_t)(m >> 32);
+    }
+}
+// start[p] = first position of partition p (= top `bits` bits of the grouped mixed-hi column); n for trailing empty ones
+__global__ void __launch_bounds__(256)
+part_bounds_kernel(const uint32_t *__restrict__ grouped_mhi, uint64_t n, uint32_t bits, uint32_t *__restrict__ start /*[2^bits + 1], preset to 0xFFFFFFFF*/) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t p = bits ? (grouped_mhi[i] >> (32 - bits)) : 0u;
+        if (i == 0 || (bits ? (grouped_mhi[i - 1] >> (32 - bits)) : 0u) != p) start[p] = (uint32_t)i;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) start[1u << bits] = (uint32_t)n;
+}
+__global__ void __launch_bounds__(256) part_fill_kernel(uint32_t *start, uint32_t nparts) {
+    // empty partitions start where the next non-empty one does: every thread looks ahead from its own entry (runs of empty
+    // partitions are short: the partition ids are hash bits)
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nparts || start[p] != 0xFFFFFFFFu) return;
+    uint32_t q = p + 1;
+    while (start[q] == 0xFFFFFFFFu) ++q; // start[nparts] = n is always set
+    __syncwarp(__activemask());
+    start[p] = start[q];
+}
+
+template <bool MULTI>
+__global__ void __launch_bounds__(256, 2)
+smem_join_kernel(const uint32_t *__restrict__ r_mhi, const uint32_t *__restrict__ r_mlo, const uint32_t *__restrict__ r_start,
+                 const uint32_t *__restrict__ s_mhi, const uint32_t *__restrict__ s_mlo, const uint32_t *__restrict__ s_rows,
+                 const uint32_t *__restrict__ s_start, uint32_t nparts, uint32_t *__restrict__ counts /*[ns] by S row*/,
+                 uint32_t *__restrict__ overflow) {
+    extern __shared__ __align__(16) unsigned char pj_raw[];
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(pj_raw);
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(pj_raw + sizeof(unsigned long long) * kPartSlots);
+    __shared__ uint32_t s_ones, s_over;
+    const int tid = threadIdx.x;
+    for (uint32_t p = blockIdx.x; p < nparts; p += gridDim.x) {
+        const uint32_t rs = r_start[p], re = r_start[p + 1], ss = s_start[p], se = s_start[p + 1];
+        if (ss == se) continue; // nobody probes this partition
+        for (uint32_t i = tid; i < kPartSlots; i += blockDim.x) {
+            keys[i] = kPartEmpty;
+            cnt[i] = 0;
+        }
+        if (tid == 0) s_ones = s_over = 0;
+        __syncthreads();
+        for (uint32_t i = rs + tid; i < re; i += blockDim.x) { // build: duplicate keys share a slot and bump its counter
+            const unsigned long long k = ((unsigned long long)r_mhi[i] << 32) | r_mlo[i];
+            if (k == kPartEmpty) {
+                atomicAdd(&s_ones, 1u);
+                continue;
+            }
+            uint32_t h = (uint32_t)(k >> 7) & (kPartSlots - 1); // (the top bits are the partition id: use middle ones)
+            uint32_t steps = 0;
+            while (true) {
+                const unsigned long long cur = atomicCAS(&keys[h], kPartEmpty, k);
+                if (cur == kPartEmpty || cur == k) {
+                    atomicAdd(&cnt[h], 1u);
+                    break;
+                }
+                h = (h + 1) & (kPartSlots - 1);
+                if (++steps >= kPartSlots) { // more distinct keys than slots: the caller reruns with the table in HBM
+                    s_over = 1;
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        if (s_over) {
+            if (tid == 0) atomicExch(overflow, 1u);
+            __syncthreads();
+            continue;
+        }
+        const uint32_t ones = s_ones;
+        for (uint32_t j = ss + tid; j < se; j += blockDim.x) { // probe
+            const unsigned long long k = ((unsigned long long)s_mhi[j] << 32) | s_mlo[j];
+            uint32_t c = 0;
+            if (k == kPartEmpty) {
+                c = ones;
+            } else {
+                uint32_t h = (uint32_t)(k >> 7) & (kPartSlots - 1);
+                for (uint32_t steps = 0; steps < kPartSlots; ++steps) {
+                    const unsigned long long cur = keys[h];
+                    if (cur == k) {
+                        c = cnt[h];
+                        break;
+                    }
+                    if (cur == kPartEmpty) break;
+                    h = (h + 1) & (kPartSlots - 1);
+                }
+            }
+            counts[s_rows[j]] = MULTI ? c : (c ? 1u : 0u);
+        }
+        __syncthreads(); // the table is rebuilt for the next partition
+    }
+}
+
+// per S row: how often the reference emits it (multi: once per equal R row, else 0/1); keys = exact (hi, lo) words of both
+// sides (hi may be null).  *overflowed is set when some partition had more distinct keys than a shared-memory table holds
+// (d_counts is then incomplete and the caller falls back).
+int radix_join_counts(const uint32_t *r_hi, const uint32_t *r_lo, uint64_t nr, const uint32_t *s_hi, const uint32_t *s_lo, uint64_t ns,
+                      bool multi, uint32_t *d_counts, bool *overflowed, Arena &ws, cudaStream_t st) {
+    *overflowed = false;
+    if (!ns) return 0;
+    if (nr >= (1ull << 32) || ns >= (1ull << 32)) {
+        set_error("hash join: fewer than 2^32 rows per side");
+        return DBT_ERR_UNSUPPORTED;
+    }
+    const size_t m0 = ws.mark();
+    uint32_t bits = 0;
+    while (bits < 20 && (nr >> bits) > kPartTargetRows) ++bits;
+    const uint32_t nparts = 1u << bits;
+    const uint32_t mask = bits ? (0xFFFFFFFFu << (32 - bits)) : 0u; // the partition id = the top bits of the mixed key
+    const uint64_t nrr = std::max<uint64_t>(nr, 1);
+    uint32_t *r_a = ws.take<uint32_t>(nrr), *r_b = ws.take<uint32_t>(nrr), *r_c = ws.take<uint32_t>(nrr), *r_d = ws.take<uint32_t>(nrr);
+    uint32_t *s_a = ws.take<uint32_t>(ns), *s_b = ws.take<uint32_t>(ns), *s_c = ws.take<uint32_t>(ns), *s_d = ws.take<uint32_t>(ns);
+    uint32_t *s_e = ws.take<uint32_t>(ns), *s_f = ws.take<uint32_t>(ns), *s_g = ws.take<uint32_t>(ns), *s_h = ws.take<uint32_t>(ns);
+    uint32_t *r_start = ws.take<uint32_t>(nparts + 1), *s_start = ws.take<uint32_t>(nparts + 1), *d_over = ws.take<uint32_t>(64);
+    if (!r_a || !r_b || !r_c || !r_d || !s_a || !s_b || !s_c || !s_d || !s_e || !s_f || !s_g || !s_h || !r_start || !s_start || !d_over) {
+        set_error("hash join: workspace too small");
+        return DBT_ERR_WORKSPACE;
+    }
+    {
+        StageScope sc(ST_HASH_BUILD, st);
+        if (nr) {
+            const int g = (int)std::min<uint64_t>((nr + 255) / 256, 148 * 16);
+            mix_keys_kernel<<<g, 256, 0, st>>>(r_hi, r_lo, nr, r_a, r_c, nullptr);
+            count_launch();
+        }
+        const int g = (int)std::min<uint64_t>((ns + 255) / 256, 148 * 16);
+        mix_keys_kernel<<<g, 256, 0, st>>>(s_hi, s_lo, ns, s_a, s_c, s_e);
+        count_launch();
+        DBT_KERNEL_CHECK();
+    }
+    // the partition passes: stable LSD over the partition bits; the pair that moves is (mixed hi, mixed lo) = the key itself.
+    // S needs its row as well: a second sort of (mixed hi, row) with the same digits gives the same (stable) order.
+    uint32_t *rk = r_a, *rka = r_b, *rv = r_c, *rva = r_d;
+    if (nr) DBT_TRY(sort_pairs_masked(rk, rka, rv, rva, nr, mask, false, ws, st));
+    uint32_t *sk = s_a, *ska = s_b, *sv = s_c, *sva = s_d;
+    DBT_TRY(sort_pairs_masked(sk, ska, sv, sva, ns, mask, false, ws, st));
+    uint32_t *sk2 = s_e, *sk2a = s_f, *srow = s_g, *srowa = s_h;
+    DBT_TRY(sort_pairs_masked(sk2, sk2a, srow, srowa, ns, mask, true, ws, st));
+    if (!mask) DBT_TRY(iota_u32(srow, ns, st)); // (a single partition: nothing was sorted, the row list is the identity)
+    {
+        StageScope sc(ST_HASH_BUILD, st);
+        DBT_CUDA(cudaMemsetAsync(r_start, 0xFF, (size_t)(nparts + 1) * 4, st));
+        DBT_CUDA(cudaMemsetAsync(s_start, 0xFF, (size_t)(nparts + 1) * 4, st));
+        const int gr = (int)std::min<uint64_t>((nrr + 255) / 256, 148 * 16), gs = (int)std::min<uint64_t>((ns + 255) / 256, 148 * 16);
+        part_bounds_kernel<<<gr, 256, 0, st>>>(rk, nr, bits, r_start);
+        part_bounds_kernel<<<gs, 256, 0, st>>>(sk, ns, bits, s_start);
+        part_fill_kernel<<<(nparts + 255) / 256, 256, 0, st>>>(r_start, nparts);
+        part_fill_kernel<<<(nparts + 255) / 256, 256, 0, st>>>(s_start, nparts);
+        count_launch(4);
+        DBT_KERNEL_CHECK();
+    }
+    const size_t smem = (size_t)kPartSlots * 12;
+    {
+        StageScope sc(ST_HASH_PROBE, st);
+        DBT_CUDA(cudaMemsetAsync(d_over, 0, 4, st));
+        const int grid = (int)std::min<uint32_t>(nparts, 148u * 2u * 8u);
+        if (multi) {
+            if (first_use_on_device((const void *)smem_join_kernel<true>))
+                DBT_CUDA(cudaFuncSetAttribute(smem_join_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            smem_join_kernel<true><<<grid, 256, smem, st>>>(rk, rv, r_start, sk, sv, srow, s_start, nparts, d_counts, d_over);
+        } else {
+            if (first_use_on_device((const void *)smem_join_kernel<false>))
+                DBT_CUDA(cudaFuncSetAttribute(smem_join_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            smem_join_kernel<false><<<grid, 256, smem, st>>>(rk, rv, r_start, sk, sv, srow, s_start, nparts, d_counts, d_over);
+        }
+        count_launch();
+        DBT_KERNEL_CHECK();
+    }
+    uint32_t h_over = 0;
+    DBT_CUDA(cudaMemcpyAsync(&h_over, d_over, 4, cudaMemcpyDeviceToHost, st));
+    DBT_CUDA(cudaStreamSynchronize(st));
+    *overflowed = h_over != 0;
+    ws.release(m0);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Intersection of two sorted unique lists.
 // ---------------------------------------------------------------------------------------------
 struct SortedList { // i-th smallest key of a relation: either a sorted u32 column or rows + key columns

@@ -438,3 +438,43 @@ def test_fused_semijoin_edge_cases(dbt, orc, monkeypatch):
     monkeypatch.setenv("DBT_JOIN_FUSED", "0")
     got, n = H.dev_hashjoin(dbt, orc, r, rag, "0")
     assert H.same_image(got, orc.hashjoin(r, rag, "0"))
+
+
+def test_radix_partitioned_join_agrees_with_the_hbm_table(dbt, orc, monkeypatch):
+    """Fields '2' (more than 32 varying key bits) and '3' take the radix-partitioned build / probe with per-partition tables
+    in shared memory when the keys' varying bits fit 64; DBT_JOIN_NO_RADIX=1 forces the linear-probing table in HBM.
+    Both must give the oracle's image: set semantics for '2', one emission per matching R row for '3'."""
+    r, s = orc.gen_ref(91, 400, num_mod=900)           # 40,000 rows per side, ~44 rows per num: real multiplicities for '3'
+    rng = np.random.default_rng(4)
+    for img in (r, s):                                  # 7-letter strings from 'a'..'p': 28 varying str bits (+10 of num for '3')
+        e = img["entries"].reshape(-1).copy()
+        st = np.zeros((len(e), 120), dtype=np.uint8)
+        st[:, :7] = rng.integers(ord("a"), ord("q"), size=(len(e), 7), dtype=np.uint8)
+        st[::3, 2:] = 0                                 # many short strings: plenty of equal (num, str) pairs
+        e["str"] = st.view("V120").reshape(-1)
+        img["entries"][:] = e.reshape(img["entries"].shape)
+    s["nreserved"][7] = 13                              # a ragged S block
+    for field in "23":
+        want = orc.hashjoin(r, s, field)
+        nres = orc.count_rows(want)
+        assert nres > 500
+        for no_radix in (False, True):
+            if no_radix:
+                monkeypatch.setenv("DBT_JOIN_NO_RADIX", "1")
+            else:
+                monkeypatch.delenv("DBT_JOIN_NO_RADIX", raising=False)
+            got, n = H.dev_hashjoin(dbt, orc, r, s, field, cap_blocks=H.nb(nres) + 1)
+            assert n == nres and H.same_image(got, want), (field, no_radix, H.first_diff(got, want))
+    # 9-letter strings: 36+ varying bits => two key words (hi and lo)
+    for img in (r, s):
+        e = img["entries"].reshape(-1).copy()
+        st = np.zeros((len(e), 120), dtype=np.uint8)
+        st[:, :9] = rng.integers(ord("a"), ord("q"), size=(len(e), 9), dtype=np.uint8)
+        st[::2, 1:] = 0
+        e["str"] = st.view("V120").reshape(-1)
+        img["entries"][:] = e.reshape(img["entries"].shape)
+    monkeypatch.delenv("DBT_JOIN_NO_RADIX", raising=False)
+    for field in "23":
+        want = orc.hashjoin(r, s, field)
+        got, n = H.dev_hashjoin(dbt, orc, r, s, field, cap_blocks=H.nb(orc.count_rows(want)) + 1)
+        assert n == orc.count_rows(want) and H.same_image(got, want), (field, H.first_diff(got, want))
