@@ -94,8 +94,6 @@ struct dbt_dist {
     cudaStream_t work = nullptr; // owner-side operators on what has landed (highest priority)
     cudaEvent_t ev_c = nullptr, ev_q[kMaxSub] = {};
     Buf send[2]; // per-owner block images waiting for the copy engines
-    cudaStream_t cp[kMaxRanks] = {}; // one copy stream per destination: the P-1 transfers of a sub-range run side by side
-    cudaEvent_t ev_cp[kMaxRanks] = {};
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     SharedBuf stag[2], keys, flags;
     Buf ws, lists;
@@ -191,7 +189,6 @@ static int ensure_shared(dbt_dist *d, SharedBuf &b, size_t need_bytes, cudaStrea
     DBT_CUDA(cudaStreamSynchronize(main));
     DBT_CUDA(cudaStreamSynchronize(d->work));
     DBT_CUDA(cudaStreamSynchronize(d->side));
-    for (int k = 0; k + 1 < d->world; ++k) DBT_CUDA(cudaStreamSynchronize(d->cp[k]));
     DBT_TRY(host_barrier(d)); // nobody stores into the old buffers any more
     for (int r = 0; r < d->world; ++r) {
         if (r != d->rank && b.peer[r] && !d->local) cudaIpcCloseMemHandle(b.peer[r]);
@@ -384,32 +381,18 @@ static int exchange_push(dbt_dist *d, int slot, const void *d_in, Routed &r, int
             DIST_CUDA(cudaStreamWaitEvent(d->side, d->ev_q[q], 0));
             DIST_TRY(launch_signal(fp, P, flag_idx, d->epoch, d->side));
         } else {
-            // my own segment is in place as soon as the gather is done; every other owner gets its segment through its own
-            // copy stream (the P-1 transfers of a sub-range run concurrently: uniform all-to-all flows, no owner is the
-            // target of two full-rate copies at once) and its flag right behind the copy
-            FlagPtrs self;
-            memset(&self, 0, sizeof self);
-            self.p[0] = fp.p[d->rank];
+            // the copy engines carry this sub-range's images, one owner after the other on ONE stream, then one flag to
+            // everybody.  Tried and measured slower (profiles/r02_notes.md): one copy stream per destination -- the
+            // engines drain the streams unevenly, so the LAST segment of the first sub-range arrived near the end of the
+            // whole transfer (first sub-range complete at 30 ms instead of 15 at P = 8; 42.8 vs 36.8 ms per step).
             DIST_CUDA(cudaStreamWaitEvent(d->side, d->ev_q[q], 0));
             if (first_copy && first_exchange) DIST_CUDA(cudaEventRecord(d->ev_a, d->side));
-            DIST_TRY(launch_signal(self, 1, flag_idx, d->epoch, d->side));
-            for (uint32_t c = 0; c < ncopies; ++c) {
-                cudaStream_t cs = d->cp[c];
-                DIST_CUDA(cudaStreamWaitEvent(cs, d->ev_q[q], 0));
-                if (copies[c].bytes) DIST_CUDA(cudaMemcpyAsync(copies[c].dst, copies[c].src, copies[c].bytes, cudaMemcpyDeviceToDevice, cs));
-                FlagPtrs one;
-                memset(&one, 0, sizeof one);
-                one.p[0] = fp.p[copies[c].owner];
-                DIST_TRY(launch_signal(one, 1, flag_idx, d->epoch, cs));
-            }
+            for (uint32_t c = 0; c < ncopies; ++c)
+                if (copies[c].bytes) DIST_CUDA(cudaMemcpyAsync(copies[c].dst, copies[c].src, copies[c].bytes, cudaMemcpyDeviceToDevice, d->side));
+            DIST_TRY(launch_signal(fp, P, flag_idx, d->epoch, d->side));
         }
         first_copy = false;
     }
-    if (Q > 1) // the NVLink phase ends when the last copy stream is done
-        for (uint32_t c = 0; c + 1 < P; ++c) {
-            DIST_CUDA(cudaEventRecord(d->ev_cp[c], d->cp[c]));
-            DIST_CUDA(cudaStreamWaitEvent(d->side, d->ev_cp[c], 0));
-        }
     DIST_CUDA(cudaEventRecord(d->ev_b, d->side));
     d->stats[1] += (double)remote;
     d->stats[2] += (double)total;
@@ -427,7 +410,6 @@ static int finish_op(dbt_dist *d, cudaStream_t main) {
     DIST_CUDA(cudaStreamSynchronize(main));
     DIST_CUDA(cudaStreamSynchronize(d->work));
     DIST_CUDA(cudaStreamSynchronize(d->side));
-    for (int k = 0; k + 1 < d->world; ++k) DIST_CUDA(cudaStreamSynchronize(d->cp[k]));
     stage_resolve();
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, d->ev_a, d->ev_b) == cudaSuccess) d->stats[0] = ms;
@@ -472,9 +454,8 @@ static uint32_t pick_sub_ranges(dbt_dist *d, uint64_t max_blocks) {
     uint32_t Q = d->nsub; // 0 = automatic
     if (!Q)
         if (const char *e = getenv("DBT_DIST_SUBRANGES")) Q = (uint32_t)atoi(e);
-    // small shards: the pipeline's per-sub-range launches would dominate; many ranks: the tail after the last transfer
-    // (the operator on the last sub-range) is what remains exposed, so cut finer
-    if (!Q) Q = (max_blocks < 20000) ? 1 : (d->world <= 2 ? 4 : 8);
+    // small shards: the pipeline's per-sub-range launches would dominate (8 sub-ranges measured slower than 4 at P = 2, 4, 8)
+    if (!Q) Q = (max_blocks < 20000) ? 1 : 4;
     Q = std::max<uint32_t>(1, std::min<uint32_t>(Q, std::min<uint32_t>(kMaxSub, 64u / (uint32_t)d->world)));
     return Q;
 }
@@ -548,10 +529,6 @@ int dbt_dist_init(const char *session, int rank, int world, int device, dbt_dist
     if (!rc && cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) lo = hi = 0;
     if (!rc && cudaStreamCreateWithPriority(&d->side, cudaStreamNonBlocking, lo) != cudaSuccess) rc = DBT_ERR_CUDA;
     if (!rc && cudaStreamCreateWithPriority(&d->work, cudaStreamNonBlocking, hi) != cudaSuccess) rc = DBT_ERR_CUDA;
-    for (int k = 0; k + 1 < world && !rc; ++k)
-        if (cudaStreamCreateWithFlags(&d->cp[k], cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&d->ev_cp[k], cudaEventDisableTiming) != cudaSuccess)
-            rc = DBT_ERR_CUDA;
     if (!rc && (cudaEventCreate(&d->ev_a) != cudaSuccess || cudaEventCreate(&d->ev_b) != cudaSuccess ||
                 cudaEventCreateWithFlags(&d->ev_c, cudaEventDisableTiming) != cudaSuccess))
         rc = DBT_ERR_CUDA;
@@ -590,10 +567,6 @@ int dbt_dist_init_local(int world, const int *devices, dbt_dist **out) {
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         DBT_CUDA(cudaStreamCreateWithPriority(&d->side, cudaStreamNonBlocking, lo));
         DBT_CUDA(cudaStreamCreateWithPriority(&d->work, cudaStreamNonBlocking, hi));
-        for (int k = 0; k + 1 < world; ++k) {
-            DBT_CUDA(cudaStreamCreateWithFlags(&d->cp[k], cudaStreamNonBlocking));
-            DBT_CUDA(cudaEventCreateWithFlags(&d->ev_cp[k], cudaEventDisableTiming));
-        }
         DBT_CUDA(cudaEventCreateWithFlags(&d->ev_c, cudaEventDisableTiming));
         for (uint32_t q = 0; q < kMaxSub; ++q) DBT_CUDA(cudaEventCreateWithFlags(&d->ev_q[q], cudaEventDisableTiming));
         DBT_CUDA(cudaEventCreate(&d->ev_a));
@@ -622,10 +595,6 @@ int dbt_dist_destroy(dbt_dist *d) {
     if (d->d_err) cudaFree(d->d_err);
     if (d->side) cudaStreamDestroy(d->side);
     if (d->work) cudaStreamDestroy(d->work);
-    for (cudaStream_t c : d->cp)
-        if (c) cudaStreamDestroy(c);
-    for (cudaEvent_t e : d->ev_cp)
-        if (e) cudaEventDestroy(e);
     if (d->ev_c) cudaEventDestroy(d->ev_c);
     for (cudaEvent_t e : d->ev_q)
         if (e) cudaEventDestroy(e);
@@ -716,7 +685,9 @@ int dbt_dist_sort(dbt_dist *d, const void *d_in, uint64_t nblocks, int field, in
     d->stats[3] = Q;
 
     // ---- owner side: sub-range q is processed as soon as its P segments have landed (the copy engines keep moving the
-    // later sub-ranges meanwhile; the SMs are all ours) ------------------------------------------------------------
+    // later sub-ranges meanwhile; the SMs are all ours).  Tried and measured slower: ordering the sub-ranges as they land
+    // but deferring the HBM-heavy record gather to ONE gather after the last transfer (to keep HBM free for the copy
+    // engines): they only went from ~480 to ~510 GB/s and the 6 ms gather is exposed (P=4: 34.5 vs 30 ms, P=2: 28.3 vs 25.0).
     d->stats[6] = ms_since(t_begin);
     uint64_t carry = 0, out_blk = 0, n_in_total = 0;
     const uint64_t cap_rows = out_capacity_blocks * kRpb;

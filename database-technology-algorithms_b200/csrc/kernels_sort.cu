@@ -606,6 +606,9 @@ onesweep2_kernel(const uint32_t *__restrict__ kin, uint32_t *__restrict__ kout, 
         else
             os2_process_tile<THREADS, ITEMS, HAS_VALS, IOTA_VALS, RANK, false>(sm, stg, tile, kin, kout, vin, vout, n, shift,
                                                                                digit_base, state);
+        // every thread has written this stage through the generic proxy (the in-place digit staging); the next bulk copy
+        // into it goes through the async proxy: the writers fence before the barrier, then thread 0 may issue the copy
+        fence_proxy_async();
         __syncthreads(); // the stage buffers are free again; next_tile[stg^1] was written long ago
         tile = sm.next_tile[stg ^ 1];
         stg ^= 1;
