@@ -22,6 +22,7 @@
 #include "dist_internal.cuh"
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <fcntl.h>
 #include <string>
@@ -57,19 +58,36 @@ struct SharedBuf { // a device buffer every rank can store into
 struct Layout {
     uint32_t P = 0, Q = 0;
     uint64_t cnt[kMaxRanks][64]; // cnt[src][bucket], bucket = owner * Q + sub-range
+    // capacity mode (streaming scatter): the regions of an owner start at offsets fixed BEFORE the rows were counted
+    // (sums of the senders' capacities), and the owner's own segment comes first in every region -- the sender wrote it
+    // in place while it scattered; the other segments follow packed, in rank order
+    bool by_capacity = false;
+    uint64_t cap_blocks[kMaxRanks][64]; // cap_blocks[src][bucket]
     uint64_t seg_blocks(uint32_t src, uint32_t owner, uint32_t q) const { return (cnt[src][owner * Q + q] + kRpb - 1) / kRpb; }
     uint64_t region_blocks(uint32_t owner, uint32_t q) const {
         uint64_t b = 0;
         for (uint32_t s = 0; s < P; ++s) b += seg_blocks(s, owner, q);
         return b;
     }
+    uint64_t region_cap(uint32_t owner, uint32_t q) const {
+        uint64_t b = 0;
+        for (uint32_t s = 0; s < P; ++s) b += cap_blocks[s][owner * Q + q];
+        return b;
+    }
     uint64_t region_blk0(uint32_t owner, uint32_t q) const {
         uint64_t b = 0;
-        for (uint32_t k = 0; k < q; ++k) b += region_blocks(owner, k);
+        for (uint32_t k = 0; k < q; ++k) b += by_capacity ? region_cap(owner, k) : region_blocks(owner, k);
         return b;
     }
     uint64_t seg_blk0(uint32_t src, uint32_t owner, uint32_t q) const {
         uint64_t b = region_blk0(owner, q);
+        if (by_capacity) {
+            if (src == owner) return b;
+            b += seg_blocks(owner, owner, q);
+            for (uint32_t s = 0; s < src; ++s)
+                if (s != owner) b += seg_blocks(s, owner, q);
+            return b;
+        }
         for (uint32_t s = 0; s < src; ++s) b += seg_blocks(s, owner, q);
         return b;
     }
@@ -96,7 +114,7 @@ struct dbt_dist {
     Buf send[2]; // per-owner block images waiting for the copy engines
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     SharedBuf stag[2], keys, flags;
-    Buf ws, lists;
+    Buf ws, lists, carry;
     uint32_t *d_err = nullptr;
     uint32_t epoch = 0;
     uint32_t nsub = 0; // key sub-ranges per owner; 0 = automatic
@@ -399,6 +417,134 @@ static int exchange_push(dbt_dist *d, int slot, const void *d_in, Routed &r, int
     return 0;
 }
 
+
+// The same exchange for a routing key that is a record word (fields '0', '1', '3'), without key columns, row lists or
+// gathers on the sender (kernels_dist.cu: route_scatter_kernel): sample the image, agree on splitters and on CAPACITIES
+// (estimated bucket sizes plus slack: the exact counts are only known after the pass), scatter in one streaming pass --
+// own rows straight into the own staging buffer, the others into per-bucket images of the send buffer -- then agree on
+// the exact counts, write the block headers and let the copy engines carry the images, sub-range by sub-range.
+// *fell_back = true: a bucket outgrew its capacity on some rank (every rank sees it) and nothing was sent.
+static int exchange_stream(dbt_dist *d, const void *d_in, uint64_t nblocks, int field, uint32_t Q, cudaStream_t main, Layout *lay,
+                           bool *fell_back) {
+    const uint32_t P = (uint32_t)d->world, nb = P * Q;
+    const uint32_t word = field == '0' ? 0u : 1u;
+    constexpr uint32_t kEst = 32768; // samples for the capacity estimate (a few hundred per bucket)
+    *fell_back = false;
+    // ---- samples -> splitters and local bucket estimates
+    DIST_TRY(d->lists.ensure((size_t)kEst * 8 + 64 * 8 + 4096));
+    Arena A(d->lists.p, d->lists.cap);
+    uint32_t *d_samp = A.take<uint32_t>(kEst), *d_ok = A.take<uint32_t>(kEst);
+    unsigned long long *d_cursor = A.take<unsigned long long>(64);
+    uint32_t *d_over = A.take<uint32_t>(64);
+    const uint32_t nsamp = nblocks ? kEst : 0;
+    std::vector<uint32_t> hs(nsamp), hok(nsamp), samp;
+    if (nsamp) {
+        DIST_TRY(launch_sample_image(d_in, nblocks, word, nsamp, d_samp, d_ok, main));
+        DIST_CUDA(cudaMemcpyAsync(hs.data(), d_samp, 4 * (size_t)nsamp, cudaMemcpyDeviceToHost, main));
+        DIST_CUDA(cudaMemcpyAsync(hok.data(), d_ok, 4 * (size_t)nsamp, cudaMemcpyDeviceToHost, main));
+    }
+    DIST_CUDA(cudaMemsetAsync(d_cursor, 0, 64 * 8, main));
+    DIST_CUDA(cudaMemsetAsync(d_over, 0, 4, main));
+    DIST_CUDA(cudaStreamSynchronize(main));
+    for (uint32_t i = 0; i < nsamp; ++i)
+        if (hok[i]) samp.push_back(hs[i]);
+    std::vector<uint32_t> few; // the all-gathered message holds 2 * kSamplesPerRank keys
+    const size_t lim = std::max<uint32_t>(1024u, 2 * kSamplesPerRank / P);
+    for (size_t i = 0; i < lim && !samp.empty(); ++i) few.push_back(samp[i * samp.size() / lim]);
+    uint32_t splitters[64];
+    DIST_TRY(choose_splitters(d, few, nb, splitters));
+    uint64_t est[64] = {0};
+    for (uint32_t k : samp) {
+        uint32_t b = 0;
+        for (uint32_t j = 0; j + 1 < nb; ++j) b += splitters[j] <= k ? 1u : 0u;
+        ++est[b];
+    }
+    lay->P = P;
+    lay->Q = Q;
+    lay->by_capacity = true;
+    uint64_t mycap[64], everycap[kMaxRanks][64];
+    for (uint32_t b = 0; b < 64; ++b) {
+        // rows of this shard expected in bucket b, + 25 % + 3 sigma of the sampling error + a few blocks
+        const double frac = samp.empty() ? 0.0 : (double)est[b] / (double)samp.size();
+        const double rows = frac * (double)nblocks * kRpb;
+        const double sigma = samp.empty() ? 0.0 : std::sqrt(frac * (1.0 - frac) / (double)samp.size()) * (double)nblocks * kRpb;
+        mycap[b] = b < nb && nblocks ? (uint64_t)((rows * 1.25 + 3.0 * sigma) / kRpb) + 8 : 0;
+    }
+    DIST_TRY(host_allgather(d, mycap, sizeof mycap, everycap));
+    for (uint32_t s = 0; s < P; ++s)
+        for (uint32_t b = 0; b < 64; ++b) {
+            lay->cap_blocks[s][b] = everycap[s][b];
+            lay->cnt[s][b] = 0;
+        }
+    DIST_TRY(ensure_shared(d, d->stag[0], (size_t)lay->total_blocks(d->rank) * DBT_BLOCK_BYTES + 256, main));
+    uint64_t send_blocks = 0;
+    for (uint32_t b = 0; b < nb; ++b)
+        if ((int)(b / Q) != d->rank) send_blocks += mycap[b];
+    DIST_TRY(d->send[0].ensure((size_t)send_blocks * DBT_BLOCK_BYTES + 256));
+    // ---- scatter
+    RoutePlan plan;
+    memset(&plan, 0, sizeof plan);
+    plan.nb = nb;
+    plan.word = word;
+    for (uint32_t j = 0; j + 1 < nb; ++j) plan.split[j] = splitters[j];
+    uint64_t send_off[64], off = 0;
+    for (uint32_t b = 0; b < nb; ++b) {
+        const uint32_t owner = b / Q, q = b % Q;
+        if ((int)owner == d->rank) {
+            plan.dst[b] = (uint32_t *)((char *)d->stag[0].own + lay->region_blk0(owner, q) * DBT_BLOCK_BYTES);
+            send_off[b] = 0;
+        } else {
+            plan.dst[b] = (uint32_t *)((char *)d->send[0].p + off * DBT_BLOCK_BYTES);
+            send_off[b] = off;
+            off += mycap[b];
+        }
+        plan.cap[b] = (uint32_t)std::min<uint64_t>(mycap[b] * kRpb, 0xFFFFFFFFull);
+    }
+    DIST_TRY(launch_route_scatter(d_in, nblocks, plan, d_cursor, d_over, main));
+    struct Counts {
+        uint64_t c[64];
+        uint64_t overflow;
+    } mine, every[kMaxRanks];
+    uint32_t over = 0;
+    DIST_CUDA(cudaMemcpyAsync(mine.c, d_cursor, 64 * 8, cudaMemcpyDeviceToHost, main));
+    DIST_CUDA(cudaMemcpyAsync(&over, d_over, 4, cudaMemcpyDeviceToHost, main));
+    DIST_CUDA(cudaStreamSynchronize(main));
+    mine.overflow = over;
+    DIST_TRY(host_allgather(d, &mine, sizeof mine, every));
+    for (uint32_t s = 0; s < P; ++s)
+        if (every[s].overflow) *fell_back = true;
+    if (*fell_back) return 0;
+    for (uint32_t s = 0; s < P; ++s)
+        for (uint32_t b = 0; b < 64; ++b) lay->cnt[s][b] = every[s].c[b];
+    // ---- headers of everything I filled, then the copies, sub-range by sub-range, one flag to every owner behind each
+    SegFillPlan fill;
+    memset(&fill, 0, sizeof fill);
+    for (uint32_t b = 0; b < nb; ++b)
+        if (mine.c[b]) fill.seg[fill.nseg++] = SegFill{plan.dst[b], mine.c[b]};
+    DIST_TRY(launch_seg_headers(fill, main));
+    DIST_CUDA(cudaEventRecord(d->ev_q[0], main));
+    DIST_CUDA(cudaStreamWaitEvent(d->side, d->ev_q[0], 0));
+    DIST_CUDA(cudaEventRecord(d->ev_a, d->side));
+    const FlagPtrs fp = flag_ptrs(d);
+    uint64_t remote = 0, total = 0;
+    for (uint32_t q = 0; q < Q; ++q) {
+        for (uint32_t k = 0; k < P; ++k) {
+            const uint32_t owner = (d->rank + 1 + k) % P;
+            const size_t bytes = (size_t)lay->seg_blocks(d->rank, owner, q) * DBT_BLOCK_BYTES;
+            total += bytes;
+            if ((int)owner == d->rank || !bytes) continue;
+            char *at_owner = (char *)d->stag[0].peer[owner] + lay->seg_blk0(d->rank, owner, q) * DBT_BLOCK_BYTES;
+            DIST_CUDA(cudaMemcpyAsync(at_owner, (char *)d->send[0].p + send_off[owner * Q + q] * DBT_BLOCK_BYTES, bytes, cudaMemcpyDeviceToDevice, d->side));
+            remote += bytes;
+        }
+        DIST_TRY(launch_signal(fp, P, q * kMaxRanks + d->rank, d->epoch, d->side));
+    }
+    DIST_CUDA(cudaEventRecord(d->ev_b, d->side));
+    d->stats[1] += (double)remote;
+    d->stats[2] += (double)total;
+    return 0;
+}
+
 static int wait_region(dbt_dist *d, int slot, uint32_t q, cudaStream_t main) {
     return launch_wait((const uint32_t *)d->flags.own, (uint32_t)d->world, (slot ? kFlagSlot1 : 0) + q * kMaxRanks, 1, d->epoch,
                        kDevTimeoutS, d->d_err, main);
@@ -527,6 +673,7 @@ int dbt_dist_init(const char *session, int rank, int world, int device, dbt_dist
     if (rank == 0) shm_unlink(name.c_str()); // every rank has it mapped: the name can go (nothing is left behind)
     int lo = 0, hi = 0;
     if (!rc && cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) lo = hi = 0;
+    if (const char *e = getenv("DBT_DIST_SIDE_PRIO")) lo = atoi(e) > 0 ? hi : 0; // experiment hook: 1 = highest, 0 = default
     if (!rc && cudaStreamCreateWithPriority(&d->side, cudaStreamNonBlocking, lo) != cudaSuccess) rc = DBT_ERR_CUDA;
     if (!rc && cudaStreamCreateWithPriority(&d->work, cudaStreamNonBlocking, hi) != cudaSuccess) rc = DBT_ERR_CUDA;
     if (!rc && (cudaEventCreate(&d->ev_a) != cudaSuccess || cudaEventCreate(&d->ev_b) != cudaSuccess ||
@@ -642,6 +789,7 @@ int dbt_dist_trim(dbt_dist *d) {
     d->send[1].release();
     d->ws.release();
     d->lists.release();
+    d->carry.release();
     return host_barrier(d);
 }
 int dbt_dist_stats(const dbt_dist *d, double out[16]) {
@@ -669,19 +817,37 @@ int dbt_dist_sort(dbt_dist *d, const void *d_in, uint64_t nblocks, int field, in
     DIST_TRY(host_allgather(d, &nblocks, 8, nbs));
     for (uint32_t r = 0; r < P; ++r) mxb = std::max(mxb, nbs[r]);
     const uint32_t Q = pick_sub_ranges(d, mxb);
-    DIST_TRY(d->lists.ensure(route_bytes(nblocks, field) + (64 << 10)));
-    Arena A(d->lists.p, d->lists.cap);
-    uint32_t *d_carry = A.take<uint32_t>(256);
-    Routed r;
-    DIST_TRY(route_prepare(d, A, d_in, nblocks, field, main, &r));
-    d->stats[4] = ms_since(t_begin);
-    std::vector<uint32_t> samp;
-    DIST_TRY(take_samples(d, A, r, (uint32_t)std::min<uint64_t>(std::max<uint32_t>(1024u, 2 * kSamplesPerRank / P), r.n), main, &samp));
-    uint32_t splitters[64];
-    DIST_TRY(choose_splitters(d, samp, P * Q, splitters));
-    d->stats[5] = ms_since(t_begin);
     Layout lay;
-    DIST_TRY(exchange_push(d, 0, d_in, r, 0, Q, splitters, main, &lay));
+    // The streaming scatter (DBT_DIST_STREAM=1; needs a record word as the routing key and shards large enough for the
+    // pipeline) is exact (tests/dist_check.py passes with it) but opt-in: it halves the sender's HBM traffic (28 instead
+    // of 58 GB per 14 GB shard) yet the rows of a bucket arrive in arbitrary block order, so the owner has to sort the
+    // recid word as well (4 more onesweep passes per sub-range) -- measured 27.1 vs 24.8 ms per step at P = 2
+    // (profiles/r02_notes.md).
+    static const bool stream_ok = [] { const char *e = getenv("DBT_DIST_STREAM"); return e && atoi(e) != 0; }();
+    bool streamed = false;
+    if (stream_ok && field != '2' && Q > 1 && P > 1) {
+        bool fell_back = false;
+        DIST_TRY(exchange_stream(d, d_in, nblocks, field, Q, main, &lay, &fell_back));
+        streamed = !fell_back;
+        d->stats[9] = streamed ? 1 : -1;
+        d->stats[4] = d->stats[5] = ms_since(t_begin);
+    }
+    if (!streamed) {
+        lay = Layout();
+        DIST_TRY(d->lists.ensure(route_bytes(nblocks, field) + (64 << 10)));
+        Arena A(d->lists.p, d->lists.cap);
+        Routed r;
+        DIST_TRY(route_prepare(d, A, d_in, nblocks, field, main, &r));
+        d->stats[4] = ms_since(t_begin);
+        std::vector<uint32_t> samp;
+        DIST_TRY(take_samples(d, A, r, (uint32_t)std::min<uint64_t>(std::max<uint32_t>(1024u, 2 * kSamplesPerRank / P), r.n), main, &samp));
+        uint32_t splitters[64];
+        DIST_TRY(choose_splitters(d, samp, P * Q, splitters));
+        d->stats[5] = ms_since(t_begin);
+        DIST_TRY(exchange_push(d, 0, d_in, r, 0, Q, splitters, main, &lay));
+    }
+    DIST_TRY(d->carry.ensure(1024));
+    uint32_t *d_carry = (uint32_t *)d->carry.p;
     d->stats[3] = Q;
 
     // ---- owner side: sub-range q is processed as soon as its P segments have landed (the copy engines keep moving the

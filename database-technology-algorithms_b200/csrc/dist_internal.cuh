@@ -26,6 +26,32 @@ struct KeyDst {
     uint32_t *p[kMaxRanks];
 };
 
+// ---- streaming scatter (the sender side of the pipelined sort when the routing key is a record word) ----------
+struct RoutePlan {
+    uint32_t nb;         // buckets (owner * Q + sub-range)
+    uint32_t word;       // record word holding the routing key: 0 recid, 1 num
+    uint32_t split[63];  // bucket of a key = number of splitters <= key (as dest_kernel, device_ops.cu)
+    uint32_t pad_;
+    uint32_t *dst[64];   // block image of bucket b (send buffer, or the own staging buffer)
+    uint32_t cap[64];    // its capacity in rows
+};
+struct SegFill { // one block image whose headers are written once its row count is known
+    uint32_t *img;
+    uint64_t nrows;
+};
+struct SegFillPlan {
+    SegFill seg[64];
+    uint32_t nseg;
+};
+// one streaming pass over the image: every live row goes to the next free slot of its bucket's image
+// (d_cursor[b]: rows handed out so far, may exceed cap[b] -- then *d_overflow is set and the surplus rows are dropped)
+int launch_route_scatter(const void *d_in, uint64_t nblocks, const RoutePlan &plan, unsigned long long *d_cursor /*[64], zeroed*/,
+                         uint32_t *d_overflow /*zeroed*/, cudaStream_t st);
+int launch_seg_headers(const SegFillPlan &plan, cudaStream_t st);
+// nsamp routing keys from evenly spaced live rows of the image (d_ok[i] = 0 where the probed block was empty)
+int launch_sample_image(const void *d_in, uint64_t nblocks, uint32_t word, uint32_t nsamp, uint32_t *d_keys, uint32_t *d_ok,
+                        cudaStream_t st);
+
 int launch_gather_push(const void *d_in, const uint32_t *d_row_slot, const PushPlan &plan, cudaStream_t st);
 int launch_signal(const FlagPtrs &peers, uint32_t nranks, uint32_t idx, uint32_t epoch, cudaStream_t st);
 int launch_wait(const uint32_t *flags, uint32_t nranks, uint32_t idx0, uint32_t stride, uint32_t epoch, double timeout_s,

@@ -80,6 +80,172 @@ int launch_gather_push(const void *d_in, const uint32_t *d_row_slot, const PushP
     return 0;
 }
 
+
+// ---- streaming scatter ---------------------------------------------------------------------------------
+// The sender side of the pipelined sort used to be: key extraction (one full read of the image for 8 bytes per row),
+// a partition pass over the row ids, and one random 140-byte gather per row into per-owner block images (267 bytes
+// read per row, kernels_gather.cu) -- 58 GB of HBM traffic for a 14 GB shard.  When the routing key is a record
+// word (recid / num), ONE streaming pass does it: blocks arrive in shared memory by cp.async.bulk (as in the
+// streaming semi-join), every live row finds its bucket among the splitters, takes the next free slot of the bucket's
+// image (shared-memory ranks inside the block, one global atomic per block and bucket) and is copied there by one warp.
+// Rows of a block that share a bucket are contiguous in the destination; the order inside a bucket is arbitrary (the
+// owner sorts).  28 GB instead of 58, and no list space.
+constexpr int kRtThreads = 128;
+constexpr int kRtStages = 3;
+
+__device__ __forceinline__ uint32_t rt_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(kRtThreads)
+route_scatter_kernel(const uint32_t *__restrict__ img, uint64_t nblocks, const __grid_constant__ RoutePlan plan,
+                     unsigned long long *__restrict__ cursor, uint32_t *__restrict__ overflow) {
+    extern __shared__ __align__(128) unsigned char rt_raw[];
+    uint32_t(*stage)[kBlockWords] = reinterpret_cast<uint32_t(*)[kBlockWords]>(rt_raw);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(rt_raw + sizeof(uint32_t) * kBlockWords * kRtStages);
+    __shared__ uint32_t s_split[64], s_cnt[64];
+    __shared__ unsigned long long s_base[64];
+    __shared__ uint32_t *s_dst[kRpb];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t first = blockIdx.x, step = gridDim.x;
+    const uint64_t mine = first < nblocks ? (nblocks - first + step - 1) / step : 0;
+    auto issue = [&](uint64_t block, int sidx) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rt_smem_u32(&mbar[sidx])), "r"((uint32_t)DBT_BLOCK_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(rt_smem_u32(stage[sidx])),
+                     "l"(img + block * kBlockWords), "r"((uint32_t)DBT_BLOCK_BYTES), "r"(rt_smem_u32(&mbar[sidx]))
+                     : "memory");
+    };
+    if (tid == 0) {
+        for (int i = 0; i < kRtStages; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rt_smem_u32(&mbar[i])), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (uint64_t k = 0; k < (uint64_t)(kRtStages - 1) && k < mine; ++k) issue(first + k * step, (int)k);
+    }
+    if (tid < 64) {
+        s_split[tid] = tid + 1 < (int)plan.nb ? plan.split[tid] : 0xFFFFFFFFu;
+        s_cnt[tid] = 0;
+    }
+    __syncthreads();
+    const uint32_t nsplit = plan.nb - 1;
+    for (uint64_t k = 0; k < mine; ++k) {
+        if (tid == 0 && k + kRtStages - 1 < mine) issue(first + (k + kRtStages - 1) * step, (int)((k + kRtStages - 1) % kRtStages));
+        const int sidx = (int)(k % kRtStages);
+        {
+            const uint32_t parity = (uint32_t)((k / kRtStages) & 1);
+            uint32_t ok = 0;
+            while (!ok)
+                asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                             : "=r"(ok)
+                             : "r"(rt_smem_u32(&mbar[sidx])), "r"(parity)
+                             : "memory");
+        }
+        const uint32_t *blk = stage[sidx];
+        const uint32_t nres = min(blk[1], kRpb);
+        uint32_t b = 0, r = 0;
+        if (tid < (int)nres) {
+            const uint32_t key = blk[kEntriesWord + tid * kRecWords + plan.word];
+            for (uint32_t j = 0; j < nsplit; ++j) b += (s_split[j] <= key) ? 1u : 0u;
+            r = atomicAdd(&s_cnt[b], 1u);
+        }
+        __syncthreads();
+        if (tid < (int)plan.nb) {
+            const uint32_t c = s_cnt[tid];
+            unsigned long long base = 0;
+            if (c) {
+                base = atomicAdd(&cursor[tid], (unsigned long long)c);
+                if (base + c > plan.cap[tid]) atomicExch(overflow, 1u);
+            }
+            s_base[tid] = base;
+            s_cnt[tid] = 0;
+        }
+        __syncthreads();
+        if (tid < (int)nres) {
+            const unsigned long long slot = s_base[b] + r;
+            s_dst[tid] = slot < plan.cap[b] ? plan.dst[b] + slot_word(slot) : nullptr;
+        }
+        __syncthreads();
+        for (uint32_t e = warp; e < nres; e += kRtThreads / 32) { // one warp per record: 32 + 3 consecutive words
+            const uint32_t *src = blk + kEntriesWord + e * kRecWords;
+            uint32_t *dst = s_dst[e];
+            if (dst) {
+                dst[lane] = src[lane];
+                if (lane < 3) dst[32 + lane] = src[32 + lane];
+            }
+        }
+        __syncthreads(); // the stage and the lists are free again
+    }
+}
+
+int launch_route_scatter(const void *d_in, uint64_t nblocks, const RoutePlan &plan, unsigned long long *d_cursor, uint32_t *d_overflow,
+                         cudaStream_t st) {
+    if (!nblocks) return 0;
+    const size_t smem = sizeof(uint32_t) * kBlockWords * kRtStages + 8 * kRtStages + 128;
+    static int per_sm = 0;
+    if (first_use_on_device((const void *)route_scatter_kernel))
+        DBT_CUDA(cudaFuncSetAttribute(route_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!per_sm) {
+        int occ = 0;
+        DBT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, route_scatter_kernel, kRtThreads, smem));
+        per_sm = std::max(occ, 1);
+    }
+    StageScope sc(ST_GATHER, st);
+    const int grid = (int)std::min<uint64_t>(nblocks, (uint64_t)148 * per_sm);
+    route_scatter_kernel<<<grid, kRtThreads, smem, st>>>((const uint32_t *)d_in, nblocks, plan, d_cursor, d_overflow);
+    count_launch();
+    DBT_KERNEL_CHECK();
+    return 0;
+}
+
+// headers (and the unused tail of the last block) of the images the scatter filled: blockid = block number inside the
+// image, nreserved = live rows, valid = 1, dummy = nreserved -- what gather_push_kernel writes
+__global__ void __launch_bounds__(256) seg_headers_kernel(const __grid_constant__ SegFillPlan plan) {
+    const SegFill sg = plan.seg[blockIdx.y];
+    const uint64_t nb = (sg.nrows + kRpb - 1) / kRpb;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t cnt = (uint32_t)min((uint64_t)kRpb, sg.nrows - b * kRpb);
+        uint32_t *o = sg.img + b * kBlockWords;
+        o[0] = (uint32_t)b;
+        o[1] = cnt;
+        o[kTrailerWord] = 1;
+        o[kTrailerWord + 1] = cnt;
+        for (uint32_t w = kEntriesWord + cnt * kRecWords; w < kTrailerWord; ++w) o[w] = 0; // only the last block has a tail
+    }
+}
+int launch_seg_headers(const SegFillPlan &plan, cudaStream_t st) {
+    if (!plan.nseg) return 0;
+    uint64_t mx = 0;
+    for (uint32_t i = 0; i < plan.nseg; ++i) mx = std::max<uint64_t>(mx, (plan.seg[i].nrows + kRpb - 1) / kRpb);
+    if (!mx) return 0;
+    const dim3 grid((unsigned)std::min<uint64_t>((mx + 255) / 256, 148 * 4), plan.nseg);
+    seg_headers_kernel<<<grid, 256, 0, st>>>(plan);
+    count_launch();
+    DBT_KERNEL_CHECK();
+    return 0;
+}
+
+__global__ void sample_image_kernel(const uint32_t *__restrict__ img, uint64_t nblocks, uint32_t word, uint32_t nsamp,
+                                    uint32_t *__restrict__ keys, uint32_t *__restrict__ ok) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsamp) return;
+    const uint64_t b = (uint64_t)i * nblocks / nsamp;
+    const uint32_t *blk = img + b * kBlockWords;
+    const uint32_t nres = min(blk[1], kRpb);
+    if (!nres) {
+        ok[i] = 0;
+        keys[i] = 0;
+        return;
+    }
+    const uint32_t e = (i * 37u) % nres;
+    keys[i] = blk[kEntriesWord + e * kRecWords + word];
+    ok[i] = 1;
+}
+int launch_sample_image(const void *d_in, uint64_t nblocks, uint32_t word, uint32_t nsamp, uint32_t *d_keys, uint32_t *d_ok,
+                        cudaStream_t st) {
+    if (!nsamp || !nblocks) return 0;
+    sample_image_kernel<<<(nsamp + 255) / 256, 256, 0, st>>>((const uint32_t *)d_in, nblocks, word, nsamp, d_keys, d_ok);
+    count_launch();
+    DBT_KERNEL_CHECK();
+    return 0;
+}
+
 // ---- flags ------------------------------------------------------------------------------------------
 __global__ void signal_kernel(FlagPtrs peers, uint32_t nranks, uint32_t idx, uint32_t epoch) {
     const uint32_t d = threadIdx.x;

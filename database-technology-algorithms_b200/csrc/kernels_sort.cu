@@ -9,32 +9,13 @@
 // tile sorted-by-digit in shared memory and writes digit runs coalesced.  Per pass the DRAM
 // traffic is 8 B read + 8 B written per pair (keys+rows) -- the kernel is HBM-bound.
 #include "dbt_internal.cuh"
+#include "sort_common.cuh"
 #include <cstdlib>
 #include <cstring>
 #include <vector>
 
 namespace dbt {
 
-constexpr int kRadix = 256;
-constexpr uint32_t kFlagAgg = 0x40000000u; // tile aggregate available
-constexpr uint32_t kFlagInc = 0x80000000u; // inclusive prefix available
-constexpr uint32_t kValMask = 0x3FFFFFFFu;
-
-__device__ __forceinline__ uint32_t lanemask_lt() {
-    uint32_t m;
-    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
-    return m;
-}
-// tile-state words carry flag and value together, so relaxed gpu-scope accesses are enough
-// (ld.volatile would be system scope: LDG.E.STRONG.SYS, measurably slower in the look-back loop)
-__device__ __forceinline__ uint32_t ld_volatile(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_volatile(uint32_t *p, uint32_t v) {
-    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 // Decoupled look-back for one digit column: sum the aggregates of the predecessor tiles until one
 // with an inclusive prefix is met.  Four predecessors are fetched per round trip (speculatively).
 __device__ __forceinline__ uint32_t lookback_exclusive(const uint32_t *state, uint32_t tile, uint32_t col) {
@@ -364,28 +345,6 @@ onesweep_kernel(const uint32_t *__restrict__ kin, uint32_t *__restrict__ kout, c
 // shared memory, ranks with warp ballots (ALU pipe), optionally mixing in match.any (ADU pipe) so
 // both pipes work, and reuses the stage buffer for the digit-ordered staging of the scatter.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok)
-                 : "r"(smem_u32(bar)), "r"(parity)
-                 : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 template <int THREADS, int ITEMS>
 struct Os2Smem {
     static constexpr int WARPS = THREADS / 32;
@@ -706,16 +665,20 @@ static int launch_onesweep2_t(const uint32_t *kin, uint32_t *kout, const uint32_
     return 0;
 }
 
-static int tile_items() {
+static int tile_items() { // the smallest tile any kernel this build may pick uses (sizes the tile-state array)
     OnesweepCfg c = current_cfg();
-    return c.threads * c.items;
+    int t = c.threads * c.items;
+    if (os2_cfg().impl == 3) t = std::min(t, onesweep3_tile_items());
+    return t;
 }
 
 static int launch_onesweep(const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, uint32_t n,
                            int shift, const uint32_t *digit_base, uint32_t *state, uint32_t *ctr, bool has_vals,
-                           bool iota, cudaStream_t st) {
+                           bool iota, bool two_nibbles, cudaStream_t st) {
     OnesweepCfg c = current_cfg();
     const bool aligned = (((uintptr_t)kin | (uintptr_t)vin) & 15) == 0; // cp.async.bulk needs 16-byte aligned sources
+    if (os2_cfg().impl == 3 && has_vals && aligned)
+        return launch_onesweep3(kin, kout, vin, vout, n, shift, digit_base, state, ctr, iota, two_nibbles, st);
     if (os2_cfg().impl == 2 && has_vals && aligned) {
         int rk = os2_cfg().rank;
         if (c.threads == 256 && c.items == 16)
@@ -809,8 +772,9 @@ int sort_pairs_masked(uint32_t *&keys, uint32_t *&keys_alt, uint32_t *&vals, uin
         StageScope sc(ST_ONESWEEP, st);
         DBT_CUDA(cudaMemsetAsync(state, 0, (size_t)ntiles * kRadix * 4, st));
         DBT_CUDA(cudaMemsetAsync(ctr, 0, 4, st));
+        const bool two_nibbles = ((varying_mask >> plan.shift[p]) & 0xF0u) != 0; // else the window's high nibble is constant
         DBT_TRY(launch_onesweep(keys, keys_alt, vals, vals_alt, (uint32_t)n, plan.shift[p], ghist + p * kRadix, state,
-                                ctr, true, iota_vals && p == 0, st));
+                                ctr, true, iota_vals && p == 0, two_nibbles, st));
         std::swap(keys, keys_alt);
         std::swap(vals, vals_alt);
     }

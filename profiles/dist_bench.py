@@ -35,6 +35,9 @@ dbt.check(L.dbt_gen_syn(42, n_total, U, 0, rank * n, n, 0, d_in.data_ptr(), sp))
 cap = int(nb * 1.25) + 64
 d_out = torch.empty(cap * BB, dtype=torch.uint8, device=dev)
 torch.cuda.synchronize()
+STAGES = os.environ.get("DIST_BENCH_STAGES") == "1"
+if STAGES:
+    L.dbt_stage_timing_enable(1)
 for q in qs:
     d.set_sub_ranges(q)
     times = []
@@ -42,6 +45,8 @@ for q in qs:
         dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if STAGES and it == 4:
+            L.dbt_stage_timing_reset()
         e0.record()
         rows, recv = d.sort(d_in.data_ptr(), nb, field, dedup, d_out.data_ptr(), cap, sp)
         e1.record()
@@ -59,6 +64,8 @@ for q in qs:
                           "records_per_s": n_total / (float(ms.item()) * 1e-3), "out_rows_total": int(tot.item()), "expected": U if dedup else n_total,
                           "push_ms_rank0": round(st["nvlink_ms"], 3), "nvlink_gbs_per_direction_rank0": gbs,
                           "timeline_ms_rank0": st["timeline_ms"]}), flush=True)
+        if STAGES:
+            print(json.dumps({"stages_last_iteration_rank0": dbt.stage_report()}), flush=True)
 d.barrier()
 d.close()
 dist.barrier()
