@@ -18,21 +18,23 @@ namespace dbt {
 
 // Decoupled look-back for one digit column: sum the aggregates of the predecessor tiles until one
 // with an inclusive prefix is met.  Four predecessors are fetched per round trip (speculatively).
-__device__ __forceinline__ uint32_t lookback_exclusive(const uint32_t *state, uint32_t tile, uint32_t col) {
-    uint32_t excl = 0;
+template <typename S>
+__device__ __forceinline__ uint32_t lookback_exclusive(const S *state, uint32_t tile, uint32_t col) {
+    using TS = TileState<S>;
+    uint32_t excl = 0; // positions are < 2^32 whatever the width of the state words
     int p = (int)tile - 1;
     while (p >= 0) {
-        uint32_t s[4];
+        S s[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-            s[q] = (p - q >= 0) ? ld_volatile(&state[(size_t)(p - q) * kRadix + col]) : kFlagInc;
+            s[q] = (p - q >= 0) ? TS::ld(&state[(size_t)(p - q) * kRadix + col]) : TS::kInc;
         int q = 0;
         bool done = false;
 #pragma unroll
         for (; q < 4; ++q) {
-            if ((s[q] >> 30) == 0) break; // not published yet: poll again from here
-            excl += s[q] & kValMask;
-            if (s[q] & kFlagInc) {
+            if ((s[q] >> TS::kFlagShift) == 0) break; // not published yet: poll again from here
+            excl += (uint32_t)(s[q] & TS::kMask);
+            if (s[q] & TS::kInc) {
                 done = true;
                 break;
             }
@@ -203,11 +205,12 @@ struct OnesweepSmem {
     uint32_t vals[TILE];
 };
 
-template <int THREADS, int ITEMS, bool HAS_VALS, bool IOTA_VALS>
+template <int THREADS, int ITEMS, bool HAS_VALS, bool IOTA_VALS, typename S>
 __global__ void __launch_bounds__(THREADS)
 onesweep_kernel(const uint32_t *__restrict__ kin, uint32_t *__restrict__ kout, const uint32_t *__restrict__ vin,
                 uint32_t *__restrict__ vout, uint32_t n, int shift, const uint32_t *__restrict__ digit_base,
-                uint32_t *state /*[ntiles][256], zeroed*/, uint32_t *tile_ctr /*zeroed*/) {
+                S *state /*[ntiles][256], zeroed*/, uint32_t *tile_ctr /*zeroed*/) {
+    using TS = TileState<S>;
     using Smem = OnesweepSmem<THREADS, ITEMS>;
     constexpr int WARPS = Smem::WARPS;
     constexpr int TILE = Smem::TILE;
@@ -276,7 +279,7 @@ onesweep_kernel(const uint32_t *__restrict__ kin, uint32_t *__restrict__ kout, c
             acc += t;
         }
         count_d = acc;
-        st_volatile(&state[(size_t)tile * kRadix + tid], (tile == 0 ? kFlagInc : kFlagAgg) | count_d);
+        TS::st(&state[(size_t)tile * kRadix + tid], (tile == 0 ? TS::kInc : TS::kAgg) | count_d);
         // exclusive scan of the 256 counts (8 warps)
         incl = count_d;
 #pragma unroll
@@ -315,7 +318,7 @@ onesweep_kernel(const uint32_t *__restrict__ kin, uint32_t *__restrict__ kout, c
         uint32_t excl_prefix = 0;
         if (tile > 0) {
             excl_prefix = lookback_exclusive(state, tile, tid);
-            st_volatile(&state[(size_t)tile * kRadix + tid], kFlagInc | (excl_prefix + count_d));
+            TS::st(&state[(size_t)tile * kRadix + tid], TS::kInc | (S)(excl_prefix + count_d));
         }
         sm.goff[tid] = digit_base[tid] + excl_prefix - sm.excl[tid];
     }
@@ -358,12 +361,13 @@ struct Os2Smem {
     uint32_t next_tile[2];
 };
 
-template <int THREADS, int ITEMS, bool HAS_VALS, bool IOTA_VALS, int RANK, bool FULL>
+template <int THREADS, int ITEMS, bool HAS_VALS, bool IOTA_VALS, int RANK, bool FULL, typename S>
 __device__ __forceinline__ void os2_process_tile(Os2Smem<THREADS, ITEMS> &sm, int stg, uint32_t tile,
                                              const uint32_t *__restrict__ kin, uint32_t *__restrict__ kout,
                                              const uint32_t *__restrict__ vin, uint32_t *__restrict__ vout,
                                              uint32_t n, int shift, const uint32_t *__restrict__ digit_base,
-                                             uint32_t *state) {
+                                             S *state) {
+    using TS = TileState<S>;
     using Smem = Os2Smem<THREADS, ITEMS>;
     constexpr int WARPS = Smem::WARPS;
     constexpr int TILE = Smem::TILE;
@@ -449,7 +453,7 @@ __device__ __forceinline__ void os2_process_tile(Os2Smem<THREADS, ITEMS> &sm, in
     if (tid < kRadix) {
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) count_d += sm.hist[w][tid];
-        st_volatile(&state[(size_t)tile * kRadix + tid], (tile == 0 ? kFlagInc : kFlagAgg) | count_d);
+        TS::st(&state[(size_t)tile * kRadix + tid], (tile == 0 ? TS::kInc : TS::kAgg) | count_d);
         incl = count_d;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -488,7 +492,7 @@ __device__ __forceinline__ void os2_process_tile(Os2Smem<THREADS, ITEMS> &sm, in
         uint32_t excl_prefix = 0;
         if (tile > 0) {
             excl_prefix = lookback_exclusive(state, tile, tid);
-            st_volatile(&state[(size_t)tile * kRadix + tid], kFlagInc | (excl_prefix + count_d));
+            TS::st(&state[(size_t)tile * kRadix + tid], TS::kInc | (S)(excl_prefix + count_d));
         }
         sm.goff[tid] = digit_base[tid] + excl_prefix - excl_d;
     }
@@ -509,11 +513,11 @@ __device__ __forceinline__ void os2_process_tile(Os2Smem<THREADS, ITEMS> &sm, in
 
 // RANK: 0 = match.any, 1 = 8 ballots, 2 = alternating (even items ballots, odd items match.any),
 //       10+K = match.any on the K low digit bits + (8-K) ballots (13 is the tuned default)
-template <int THREADS, int ITEMS, bool HAS_VALS, bool IOTA_VALS, int RANK>
+template <int THREADS, int ITEMS, bool HAS_VALS, bool IOTA_VALS, int RANK, typename S>
 __global__ void __launch_bounds__(THREADS, (THREADS * ITEMS <= 4096) ? 3 : ((THREADS * ITEMS <= 6144) ? 2 : 1))
 onesweep2_kernel(const uint32_t *__restrict__ kin, uint32_t *__restrict__ kout, const uint32_t *__restrict__ vin,
                  uint32_t *__restrict__ vout, uint32_t n, int shift, const uint32_t *__restrict__ digit_base,
-                 uint32_t *state /*[ntiles][256], zeroed*/, uint32_t *tile_ctr /*zeroed*/) {
+                 S *state /*[ntiles][256], zeroed*/, uint32_t *tile_ctr /*zeroed*/) {
     using Smem = Os2Smem<THREADS, ITEMS>;
     constexpr int WARPS = Smem::WARPS;
     constexpr int TILE = Smem::TILE;
@@ -560,10 +564,10 @@ onesweep2_kernel(const uint32_t *__restrict__ kin, uint32_t *__restrict__ kout, 
         parity ^= 1u << stg;
         __syncthreads();
         if (tile * (uint32_t)TILE + (uint32_t)TILE <= n)
-            os2_process_tile<THREADS, ITEMS, HAS_VALS, IOTA_VALS, RANK, true>(sm, stg, tile, kin, kout, vin, vout, n, shift,
+            os2_process_tile<THREADS, ITEMS, HAS_VALS, IOTA_VALS, RANK, true, S>(sm, stg, tile, kin, kout, vin, vout, n, shift,
                                                                               digit_base, state);
         else
-            os2_process_tile<THREADS, ITEMS, HAS_VALS, IOTA_VALS, RANK, false>(sm, stg, tile, kin, kout, vin, vout, n, shift,
+            os2_process_tile<THREADS, ITEMS, HAS_VALS, IOTA_VALS, RANK, false, S>(sm, stg, tile, kin, kout, vin, vout, n, shift,
                                                                                digit_base, state);
         // every thread has written this stage through the generic proxy (the in-place digit staging); the next bulk copy
         // into it goes through the async proxy: the writers fence before the barrier, then thread 0 may issue the copy
@@ -590,16 +594,17 @@ static OnesweepCfg current_cfg() {
     return cfg;
 }
 
-template <int THREADS, int ITEMS>
+template <int THREADS, int ITEMS, typename S = uint32_t>
 static int launch_onesweep_t(const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, uint32_t n,
-                             int shift, const uint32_t *digit_base, uint32_t *state, uint32_t *ctr, bool has_vals,
+                             int shift, const uint32_t *digit_base, void *state_v, uint32_t *ctr, bool has_vals,
                              bool iota, cudaStream_t st) {
+    S *state = (S *)state_v;
     using Smem = OnesweepSmem<THREADS, ITEMS>;
     size_t smem = sizeof(Smem);
     uint32_t ntiles = (n + Smem::TILE - 1) / Smem::TILE;
 #define DBT_LAUNCH_OS(HV, IO)                                                                                     \
     do {                                                                                                          \
-        auto kfn = onesweep_kernel<THREADS, ITEMS, HV, IO>;                                                       \
+        auto kfn = onesweep_kernel<THREADS, ITEMS, HV, IO, S>;                                                       \
         if (first_use_on_device((const void *)kfn))                                                               \
             DBT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
         kfn<<<ntiles, THREADS, smem, st>>>(kin, kout, vin, vout, n, shift, digit_base, state, ctr);               \
@@ -631,15 +636,16 @@ static Os2Cfg os2_cfg() {
 
 template <int THREADS, int ITEMS>
 static int launch_onesweep2_t(const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, uint32_t n,
-                              int shift, const uint32_t *digit_base, uint32_t *state, uint32_t *ctr, bool iota, int rank,
+                              int shift, const uint32_t *digit_base, void *state_v, uint32_t *ctr, bool iota, int rank,
                               cudaStream_t st) {
+    uint32_t *state = (uint32_t *)state_v;
     using Smem = Os2Smem<THREADS, ITEMS>;
     size_t smem = sizeof(Smem) + 128;
     uint32_t ntiles = (n + Smem::TILE - 1) / Smem::TILE;
     int grid = (int)std::min<uint32_t>(ntiles, 148u * (uint32_t)os2_cfg().ctas_per_sm);
 #define DBT_LAUNCH_OS2(IO, RK)                                                                                   \
     do {                                                                                                         \
-        auto kfn = onesweep2_kernel<THREADS, ITEMS, true, IO, RK>;                                               \
+        auto kfn = onesweep2_kernel<THREADS, ITEMS, true, IO, RK, uint32_t>;                                               \
         if (first_use_on_device((const void *)kfn))                                                              \
             DBT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
         kfn<<<grid, THREADS, smem, st>>>(kin, kout, vin, vout, n, shift, digit_base, state, ctr);                \
@@ -670,6 +676,30 @@ static int tile_items() { // the smallest tile any kernel this build may pick us
     int t = c.threads * c.items;
     if (os2_cfg().impl == 3) t = std::min(t, onesweep3_tile_items());
     return t;
+}
+
+// n >= 2^30: 64-bit tile states, one configuration (the tuned default) per kernel version
+static int launch_onesweep_wide(const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, uint32_t n, int shift,
+                                const uint32_t *digit_base, uint64_t *state, uint32_t *ctr, bool has_vals, bool iota, cudaStream_t st) {
+    const bool aligned = (((uintptr_t)kin | (uintptr_t)vin) & 15) == 0;
+    if (!(has_vals && aligned)) return launch_onesweep_t<256, 24, uint64_t>(kin, kout, vin, vout, n, shift, digit_base, state, ctr, has_vals, iota, st);
+    using Smem = Os2Smem<256, 24>;
+    const size_t smem = sizeof(Smem) + 128;
+    const uint32_t ntiles = (uint32_t)(((uint64_t)n + Smem::TILE - 1) / Smem::TILE);
+    const int grid = (int)std::min<uint32_t>(ntiles, 148u * 2u);
+#define DBT_LAUNCH_OS2W(IO)                                                                                      \
+    do {                                                                                                         \
+        auto kfn = onesweep2_kernel<256, 24, true, IO, 13, uint64_t>;                                            \
+        if (first_use_on_device((const void *)kfn))                                                              \
+            DBT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+        kfn<<<grid, 256, smem, st>>>(kin, kout, vin, vout, n, shift, digit_base, state, ctr);                    \
+    } while (0)
+    if (iota) DBT_LAUNCH_OS2W(true);
+    else DBT_LAUNCH_OS2W(false);
+#undef DBT_LAUNCH_OS2W
+    count_launch();
+    DBT_KERNEL_CHECK();
+    return 0;
 }
 
 static int launch_onesweep(const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, uint32_t n,
@@ -709,8 +739,11 @@ static int launch_onesweep(const uint32_t *kin, uint32_t *kout, const uint32_t *
     return DBT_ERR_ARG;
 }
 
+constexpr uint64_t kMaxSortElems = (1ull << 32) - (1ull << 16); // u32 row ids, and tile arithmetic that stays inside 32 bits
+
 size_t sort_ws_bytes(uint64_t n) {
     uint64_t ntiles = (n + 2048 - 1) / 2048 + 1; // bound for the smallest tile any config uses (256x12 = 3072)
+    if (n >= (1ull << 30)) return pad256(((n + 6143) / 6144 + 1) * kRadix * 8) + pad256(4 * kRadix * 4) + 4 * 256 + 4096; // 64-bit states
     return pad256(ntiles * kRadix * 4) + pad256(4 * kRadix * 4) + 4 * 256 + 4096;
 }
 
@@ -732,8 +765,8 @@ static DigitPlan plan_digits(uint32_t varying) {
 // On return keys/vals point at the buffers holding the result (swapped as needed).
 int sort_pairs_masked(uint32_t *&keys, uint32_t *&keys_alt, uint32_t *&vals, uint32_t *&vals_alt, uint64_t n,
                       uint32_t varying_mask, bool iota_vals, Arena &ws, cudaStream_t st, const uint32_t *byte_hist) {
-    if (n >= (1ull << 30)) {
-        set_error("sort_pairs: n must be < 2^30 per call");
+    if (n > kMaxSortElems) {
+        set_error("sort_pairs: n must be at most 2^32 - 2^16 per call (row ids are 32 bits)");
         return DBT_ERR_UNSUPPORTED;
     }
     DigitPlan plan = plan_digits(varying_mask);
@@ -741,11 +774,14 @@ int sort_pairs_masked(uint32_t *&keys, uint32_t *&keys_alt, uint32_t *&vals, uin
         if (iota_vals && n) DBT_TRY(iota_u32(vals, n, st)); // nothing to sort but the caller expects a row list
         return 0;
     }
+    const bool wide = n >= (1ull << 30); // the 30-bit values of the 32-bit tile states no longer hold a position
     size_t m0 = ws.mark();
-    uint32_t ntiles = (uint32_t)((n + tile_items() - 1) / tile_items());
+    const uint32_t tile = wide ? 256u * 24u : (uint32_t)tile_items();
+    uint32_t ntiles = (uint32_t)((n + tile - 1) / tile);
     uint32_t *ghist = ws.take<uint32_t>(4 * kRadix);
     uint32_t *ctr = ws.take<uint32_t>(64);
-    uint32_t *state = ws.take<uint32_t>((size_t)ntiles * kRadix);
+    const size_t state_bytes = (size_t)ntiles * kRadix * (wide ? 8 : 4);
+    void *state = ws.take<unsigned char>(state_bytes);
     if (!ghist || !ctr || !state) {
         set_error("sort_pairs: workspace too small");
         return DBT_ERR_WORKSPACE;
@@ -770,11 +806,15 @@ int sort_pairs_masked(uint32_t *&keys, uint32_t *&keys_alt, uint32_t *&vals, uin
     }
     for (int p = 0; p < plan.npass; ++p) {
         StageScope sc(ST_ONESWEEP, st);
-        DBT_CUDA(cudaMemsetAsync(state, 0, (size_t)ntiles * kRadix * 4, st));
+        DBT_CUDA(cudaMemsetAsync(state, 0, state_bytes, st));
         DBT_CUDA(cudaMemsetAsync(ctr, 0, 4, st));
         const bool two_nibbles = ((varying_mask >> plan.shift[p]) & 0xF0u) != 0; // else the window's high nibble is constant
-        DBT_TRY(launch_onesweep(keys, keys_alt, vals, vals_alt, (uint32_t)n, plan.shift[p], ghist + p * kRadix, state,
-                                ctr, true, iota_vals && p == 0, two_nibbles, st));
+        if (wide)
+            DBT_TRY(launch_onesweep_wide(keys, keys_alt, vals, vals_alt, (uint32_t)n, plan.shift[p], ghist + p * kRadix,
+                                         (uint64_t *)state, ctr, true, iota_vals && p == 0, st));
+        else
+            DBT_TRY(launch_onesweep(keys, keys_alt, vals, vals_alt, (uint32_t)n, plan.shift[p], ghist + p * kRadix,
+                                    (uint32_t *)state, ctr, true, iota_vals && p == 0, two_nibbles, st));
         std::swap(keys, keys_alt);
         std::swap(vals, vals_alt);
     }

@@ -73,7 +73,8 @@ uint64_t dbt_mergejoin_nios(uint64_t nblocks_r, uint64_t nblocks_s, uint32_t nme
  * Replaces qsort run generation + priority_queue k-way merge (DatabaseProject.cpp:207-214,
  * 255-343) at the pair level.  keys/vals are double buffers of n elements each; on return
  * *result_in_alt is 1 when the sorted data sits in the *_alt buffers.  Stable.
- * Digit positions where all keys agree are skipped.  n < 2^30. */
+ * Digit positions where all keys agree are skipped.  n <= 2^32 - 2^16 (32-bit row ids); from 2^30 elements on the
+ * look-back chain runs on 64-bit tile states. */
 size_t dbt_sort_pairs_ws_bytes(uint64_t n);
 int dbt_sort_pairs_u32(uint32_t *d_keys, uint32_t *d_keys_alt, uint32_t *d_vals, uint32_t *d_vals_alt, uint64_t n,
                        int begin_bit, int end_bit, void *d_ws, size_t ws_bytes, void *stream, int *result_in_alt);

@@ -164,6 +164,38 @@ def test_sort_pairs_u32_full_range(dbt):
     assert torch.equal(vo.to(torch.int64), ref_i)
 
 
+def test_sort_pairs_beyond_2_30_elements_uses_wide_tile_states(dbt):
+    """n >= 2^30: the tile states of the look-back chain switch to 64-bit words (32-bit words hold 30-bit positions).
+    Checked by properties, in chunks: (key, value) strictly ascending, so the values are distinct, i.e. a permutation,
+    ties in input order (stable); and every output key is the input key of its value."""
+    import ctypes as C
+    import torch
+
+    if torch.cuda.mem_get_info()[1] < 60 * 2**30:
+        pytest.skip("needs a 60 GB device")
+    n = 2**30 + 77_777
+    g = torch.Generator(device="cuda").manual_seed(9)
+    keys = torch.randint(-2**31, 2**31, (n,), dtype=torch.int32, device="cuda", generator=g)
+    k1 = keys.clone()
+    v1 = torch.arange(n, dtype=torch.int32, device="cuda")
+    k2, v2 = torch.empty_like(k1), torch.empty_like(v1)
+    wsb = dbt.lib().dbt_sort_pairs_ws_bytes(n)
+    ws = H.dev_alloc(wsb)
+    alt = C.c_int()
+    dbt.check(dbt.lib().dbt_sort_pairs_u32(k1.data_ptr(), k2.data_ptr(), v1.data_ptr(), v2.data_ptr(), n, 0, 32,
+                                           ws.data_ptr(), wsb, H.stream(), C.byref(alt)))
+    ko, vo = (k2, v2) if alt.value else (k1, v1)
+    step = 2**27
+    for a in range(0, n, step):
+        b = min(n, a + step + 1)  # one element of overlap: the pair across the chunk boundary is checked too
+        kk = ko[a:b].to(torch.int64) & 0xFFFFFFFF
+        vv = vo[a:b].to(torch.int64)
+        assert bool(((vv >= 0) & (vv < n)).all())
+        asc = (kk[1:] > kk[:-1]) | ((kk[1:] == kk[:-1]) & (vv[1:] > vv[:-1]))
+        assert bool(asc.all()), f"order broken in chunk at {a}"
+        assert bool((keys[vv] == ko[a:b]).all()), f"pairs broken in chunk at {a}"
+
+
 def test_hashjoin_wide_key_range_and_table_fallback(dbt, orc, monkeypatch):
     """u32 semi-join paths: L2-resident bitmap (narrow key range, the other tests), sliced full-range bitmap
     (keys spread over 32 bits), and the linear-probing hash table (forced)."""
