@@ -400,6 +400,23 @@ __device__ __forceinline__ void os2_process_tile(Os2Smem<THREADS, ITEMS> &sm, in
         if (RANK == 0 || (RANK == 2 && (j & 1))) {
             if (!FULL) valid = li0 + j * 32 < nvalid;
             peers = __match_any_sync(0xFFFFFFFFu, valid ? d : 0x100u);
+        } else if (RANK >= 23 && RANK <= 25) {
+            // the hybrid below with the ballots written so that ptxas sets the bit predicates with one R2P and spends
+            // VOTE + predicated NOT + OR per bit (3 instructions instead of the 6 it makes of `bit ? m : ~m`):
+            // differing lanes are collected per bit and removed from the match mask at the end
+            constexpr int K = (RANK >= 23 && RANK <= 25) ? RANK - 20 : 3;
+            if (!FULL) valid = li0 + j * 32 < nvalid;
+            peers = __match_any_sync(0xFFFFFFFFu, valid ? (d & ((1u << K) - 1u)) : (1u << K));
+            uint32_t diff = 0;
+#pragma unroll
+            for (int b = K; b < 8; ++b) {
+                uint32_t m, x;
+                asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tvote.sync.ballot.b32 %0, p, 0xffffffff;\n\tselp.u32 %1, 0xffffffff, 0, p;\n\t}"
+                    : "=r"(m), "=r"(x)
+                    : "r"(d & (1u << b)));
+                diff |= m ^ x;
+            }
+            peers &= ~diff;
         } else if (RANK >= 13 && RANK <= 15) {
             // hybrid: match.any on the low K bits (cost ~ number of distinct values: <= 2^K groups, ADU pipe)
             // and one ballot per remaining bit (ALU pipe): every item loads both pipes lightly
@@ -426,14 +443,23 @@ __device__ __forceinline__ void os2_process_tile(Os2Smem<THREADS, ITEMS> &sm, in
                 peers &= valid ? vm : ~vm;
             }
         }
-        const int leader = __ffs(peers) - 1;
-        uint32_t old = 0;
-        if (lane == leader && valid) {
-            old = sm.hist[warp][d];
-            sm.hist[warp][d] = old + __popc(peers);
+        if (RANK >= 23 && RANK <= 25) {
+            // every lane reads the group's counter itself (one broadcast LDS) before the group's first lane bumps it: no
+            // leader election (BREV + FLO), no shuffle
+            const uint32_t before = peers & lt;
+            const uint32_t old = sm.hist[warp][d];
+            if (before == 0 && valid) sm.hist[warp][d] = old + __popc(peers);
+            rank2[j >> 1] |= (old + __popc(before)) << ((j & 1) * 16);
+        } else {
+            const int leader = __ffs(peers) - 1;
+            uint32_t old = 0;
+            if (lane == leader && valid) {
+                old = sm.hist[warp][d];
+                sm.hist[warp][d] = old + __popc(peers);
+            }
+            old = __shfl_sync(0xFFFFFFFFu, old, leader);
+            rank2[j >> 1] |= (old + __popc(peers & lt)) << ((j & 1) * 16);
         }
-        old = __shfl_sync(0xFFFFFFFFu, old, leader);
-        rank2[j >> 1] |= (old + __popc(peers & lt)) << ((j & 1) * 16);
         __syncwarp();
     }
     uint32_t val[HAS_VALS ? ITEMS : 1];
@@ -625,7 +651,7 @@ struct Os2Cfg {
 };
 static Os2Cfg os2_cfg() {
     static Os2Cfg cfg = [] {
-        Os2Cfg c{2, 13, 2}; // persistent pipelined kernel, match(3 low bits)+5 ballots, 2 CTAs/SM
+        Os2Cfg c{2, 23, 2}; // persistent pipelined kernel, match(3 low bits)+5 ballots (hand-scheduled, 23), 2 CTAs/SM
         if (const char *e = getenv("DBT_ONESWEEP_IMPL")) c.impl = atoi(e);
         if (const char *e = getenv("DBT_ONESWEEP_RANK")) c.rank = atoi(e);
         if (const char *e = getenv("DBT_ONESWEEP_CTAS")) c.ctas_per_sm = atoi(e);
@@ -654,6 +680,7 @@ static int launch_onesweep2_t(const uint32_t *kin, uint32_t *kout, const uint32_
         if (rank == 0) DBT_LAUNCH_OS2(true, 0);
         else if (rank == 2) DBT_LAUNCH_OS2(true, 2);
         else if (rank == 13) DBT_LAUNCH_OS2(true, 13);
+        else if (rank == 23) DBT_LAUNCH_OS2(true, 23);
         else if (rank == 14) DBT_LAUNCH_OS2(true, 14);
         else if (rank == 15) DBT_LAUNCH_OS2(true, 15);
         else DBT_LAUNCH_OS2(true, 1);
@@ -661,6 +688,7 @@ static int launch_onesweep2_t(const uint32_t *kin, uint32_t *kout, const uint32_
         if (rank == 0) DBT_LAUNCH_OS2(false, 0);
         else if (rank == 2) DBT_LAUNCH_OS2(false, 2);
         else if (rank == 13) DBT_LAUNCH_OS2(false, 13);
+        else if (rank == 23) DBT_LAUNCH_OS2(false, 23);
         else if (rank == 14) DBT_LAUNCH_OS2(false, 14);
         else if (rank == 15) DBT_LAUNCH_OS2(false, 15);
         else DBT_LAUNCH_OS2(false, 1);
@@ -689,7 +717,7 @@ static int launch_onesweep_wide(const uint32_t *kin, uint32_t *kout, const uint3
     const int grid = (int)std::min<uint32_t>(ntiles, 148u * 2u);
 #define DBT_LAUNCH_OS2W(IO)                                                                                      \
     do {                                                                                                         \
-        auto kfn = onesweep2_kernel<256, 24, true, IO, 13, uint64_t>;                                            \
+        auto kfn = onesweep2_kernel<256, 24, true, IO, 23, uint64_t>;                                            \
         if (first_use_on_device((const void *)kfn))                                                              \
             DBT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
         kfn<<<grid, 256, smem, st>>>(kin, kout, vin, vout, n, shift, digit_base, state, ctr);                    \
