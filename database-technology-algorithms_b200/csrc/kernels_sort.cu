@@ -400,22 +400,26 @@ __device__ __forceinline__ void os2_process_tile(Os2Smem<THREADS, ITEMS> &sm, in
         if (RANK == 0 || (RANK == 2 && (j & 1))) {
             if (!FULL) valid = li0 + j * 32 < nvalid;
             peers = __match_any_sync(0xFFFFFFFFu, valid ? d : 0x100u);
-        } else if (RANK >= 23 && RANK <= 25) {
+        } else if (RANK >= 22 && RANK <= 25) {
             // the hybrid below with the ballots written so that ptxas sets the bit predicates with one R2P and spends
             // VOTE + predicated NOT + OR per bit (3 instructions instead of the 6 it makes of `bit ? m : ~m`):
             // differing lanes are collected per bit and removed from the match mask at the end
-            constexpr int K = (RANK >= 23 && RANK <= 25) ? RANK - 20 : 3;
+            constexpr int K = (RANK >= 22 && RANK <= 25) ? RANK - 20 : 3;
             if (!FULL) valid = li0 + j * 32 < nvalid;
             peers = __match_any_sync(0xFFFFFFFFu, valid ? (d & ((1u << K) - 1u)) : (1u << K));
-            uint32_t diff = 0;
+            uint32_t mm[8 - K]; // lanes whose bit b differs from mine
 #pragma unroll
             for (int b = K; b < 8; ++b) {
                 uint32_t m, x;
                 asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tvote.sync.ballot.b32 %0, p, 0xffffffff;\n\tselp.u32 %1, 0xffffffff, 0, p;\n\t}"
                     : "=r"(m), "=r"(x)
                     : "r"(d & (1u << b)));
-                diff |= m ^ x;
+                mm[b - K] = m ^ x;
             }
+            uint32_t diff = mm[0]; // three-input ORs
+#pragma unroll
+            for (int t = 1; t + 1 < 8 - K; t += 2) diff = diff | mm[t] | mm[t + 1];
+            if ((8 - K) % 2 == 0) diff |= mm[8 - K - 1];
             peers &= ~diff;
         } else if (RANK >= 13 && RANK <= 15) {
             // hybrid: match.any on the low K bits (cost ~ number of distinct values: <= 2^K groups, ADU pipe)
@@ -443,7 +447,7 @@ __device__ __forceinline__ void os2_process_tile(Os2Smem<THREADS, ITEMS> &sm, in
                 peers &= valid ? vm : ~vm;
             }
         }
-        if (RANK >= 23 && RANK <= 25) {
+        if (RANK >= 22 && RANK <= 25) {
             // every lane reads the group's counter itself (one broadcast LDS) before the group's first lane bumps it: no
             // leader election (BREV + FLO), no shuffle
             const uint32_t before = peers & lt;
@@ -681,6 +685,8 @@ static int launch_onesweep2_t(const uint32_t *kin, uint32_t *kout, const uint32_
         else if (rank == 2) DBT_LAUNCH_OS2(true, 2);
         else if (rank == 13) DBT_LAUNCH_OS2(true, 13);
         else if (rank == 23) DBT_LAUNCH_OS2(true, 23);
+        else if (rank == 22) DBT_LAUNCH_OS2(true, 22);
+        else if (rank == 24) DBT_LAUNCH_OS2(true, 24);
         else if (rank == 14) DBT_LAUNCH_OS2(true, 14);
         else if (rank == 15) DBT_LAUNCH_OS2(true, 15);
         else DBT_LAUNCH_OS2(true, 1);
@@ -689,6 +695,8 @@ static int launch_onesweep2_t(const uint32_t *kin, uint32_t *kout, const uint32_
         else if (rank == 2) DBT_LAUNCH_OS2(false, 2);
         else if (rank == 13) DBT_LAUNCH_OS2(false, 13);
         else if (rank == 23) DBT_LAUNCH_OS2(false, 23);
+        else if (rank == 22) DBT_LAUNCH_OS2(false, 22);
+        else if (rank == 24) DBT_LAUNCH_OS2(false, 24);
         else if (rank == 14) DBT_LAUNCH_OS2(false, 14);
         else if (rank == 15) DBT_LAUNCH_OS2(false, 15);
         else DBT_LAUNCH_OS2(false, 1);
