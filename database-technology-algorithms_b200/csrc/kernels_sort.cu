@@ -416,11 +416,12 @@ __device__ __forceinline__ void os2_process_tile(Os2Smem<THREADS, ITEMS> &sm, in
                     : "r"(d & (1u << b)));
                 mm[b - K] = m ^ x;
             }
-            uint32_t diff = mm[0]; // three-input ORs
+            // peers = match & ~(mm[0] | ... ): three-input LOP3s (ptxas keeps two-input ORs otherwise)
+            uint32_t diff = mm[0];
 #pragma unroll
-            for (int t = 1; t + 1 < 8 - K; t += 2) diff = diff | mm[t] | mm[t + 1];
-            if ((8 - K) % 2 == 0) diff |= mm[8 - K - 1];
-            peers &= ~diff;
+            for (int t = 1; t + 1 < 8 - K; t += 2) asm("lop3.b32 %0, %0, %1, %2, 0xFE;" : "+r"(diff) : "r"(mm[t]), "r"(mm[t + 1]));
+            if ((8 - K) % 2 == 0) asm("lop3.b32 %0, %0, %1, %2, 0x10;" : "+r"(peers) : "r"(diff), "r"(mm[8 - K - 1])); // a & ~(b | c)
+            else peers &= ~diff;
         } else if (RANK >= 13 && RANK <= 15) {
             // hybrid: match.any on the low K bits (cost ~ number of distinct values: <= 2^K groups, ADU pipe)
             // and one ballot per remaining bit (ALU pipe): every item loads both pipes lightly
@@ -451,9 +452,11 @@ __device__ __forceinline__ void os2_process_tile(Os2Smem<THREADS, ITEMS> &sm, in
             // every lane reads the group's counter itself (one broadcast LDS) before the group's first lane bumps it: no
             // leader election (BREV + FLO), no shuffle
             const uint32_t before = peers & lt;
-            const uint32_t old = sm.hist[warp][d];
-            if (before == 0 && valid) sm.hist[warp][d] = old + __popc(peers);
-            rank2[j >> 1] |= (old + __popc(before)) << ((j & 1) * 16);
+            uint32_t *cnt = &sm.hist[warp][0] + d;
+            const uint32_t old = *cnt;
+            const uint32_t ahead = __popc(before);
+            if (ahead == 0 && valid) *cnt = old + __popc(peers);
+            rank2[j >> 1] += (old + ahead) << ((j & 1) * 16); // (disjoint fields: + is |, and folds into one IMAD)
         } else {
             const int leader = __ffs(peers) - 1;
             uint32_t old = 0;
