@@ -19,6 +19,26 @@ constexpr uint32_t kTrailerWord = 3502;  // valid/misc/pad word, then dummy at 3
 constexpr uint32_t kBlockVec4 = 876;     // 14016 / 16
 
 // word offset of slot s (slot = block*100 + entry) inside an image
+// Read-only 4-byte load for RANDOM accesses (record gathers, words fetched through a permutation, table probes).  By default
+// an L2 miss fills a whole 128-byte line from DRAM; the .L2::64B qualifier makes it a 64-byte fill: ncu dram__bytes_read for
+// 50M random 140-byte records drops from 267 to 202 bytes per record, for random 8-byte reads from 132 to 68
+// (profiles/micro/l2gran2.cu, profiles/r02_notes.md; cudaLimitMaxL2FetchGranularity changes nothing).  DBT_SPARSE_LD=0 at
+// build time restores the plain load for A/B runs.
+#ifndef DBT_SPARSE_LD
+#define DBT_SPARSE_LD 1
+#endif
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t ld_sparse(const uint32_t *p) {
+#if DBT_SPARSE_LD
+    uint32_t v;
+    asm("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+#endif
+
 __host__ __device__ __forceinline__ uint64_t slot_word(uint64_t slot) {
     uint64_t b = slot / kRpb;
     uint32_t e = (uint32_t)(slot - b * kRpb);

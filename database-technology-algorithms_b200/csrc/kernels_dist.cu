@@ -51,7 +51,7 @@ gather_push_kernel(const uint32_t *__restrict__ in, const uint32_t *__restrict__
         const uint32_t idx = tid + k * kPushThreads;
         const uint32_t rec = idx / kRecWords;
         const uint32_t w = idx - rec * kRecWords;
-        v[k] = (idx < nwords) ? __ldg(in + src[rec] + w) : 0u;
+        v[k] = (idx < nwords) ? ld_sparse(in + src[rec] + w) : 0u;
     }
 #pragma unroll
     for (int k = 0; k < kPerThread; ++k) {

@@ -400,6 +400,101 @@ extract_stream_kernel(const uint32_t *__restrict__ img, uint64_t nblocks, uint64
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Sparse extraction for fields '0' / '1' (round 2).  The key of those fields is the record's first 8 bytes (recid, num).
+// ld.global.nc.L2::64B makes an L2 miss fill 64 bytes instead of a 128-byte line (dbt_internal.cuh: ld_sparse), so a
+// strided read of 8 bytes per 140-byte row costs ~68 bytes of DRAM traffic per row instead of the whole image (140):
+// the streaming kernel above reads 14.0 GB per 100M rows, this one ~6.9 GB.  Persistent CTAs, 4 rows (8 independent
+// loads) per thread per step, OR/AND in registers, byte histograms of the key in shared memory as in the streaming kernel.
+// Serves dense and ragged images alike (row_slot).
+// ---------------------------------------------------------------------------------------------
+constexpr int kSpThreads = 256;
+constexpr int kSpRows = 4;
+
+template <int FIELD>
+__global__ void __launch_bounds__(kSpThreads)
+extract_sparse_kernel(const uint32_t *__restrict__ img, uint64_t nrows, const uint32_t *__restrict__ row_slot,
+                      uint32_t *__restrict__ out_w0, uint32_t *__restrict__ out_recid, ExtractStats *stats,
+                      uint32_t *__restrict__ byte_hist /*[4][256] or null*/) {
+    static_assert(FIELD == 0 || FIELD == 1, "numeric fields only");
+    __shared__ uint32_t s_hist[4][256];
+    __shared__ uint32_t s_or[2], s_and[2], s_flag;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const bool HIST = byte_hist != nullptr;
+    if (HIST)
+        for (int i = tid; i < 4 * 256; i += kSpThreads) (&s_hist[0][0])[i] = 0;
+    if (tid < 2) {
+        s_or[tid] = 0;
+        s_and[tid] = 0xFFFFFFFFu;
+    }
+    if (tid == 0) s_flag = 0;
+    __syncthreads();
+    uint32_t o_w0 = 0, a_w0 = 0xFFFFFFFFu, o_id = 0, a_id = 0xFFFFFFFFu, unsorted = 0;
+    constexpr uint64_t kTile = (uint64_t)kSpThreads * kSpRows;
+    for (uint64_t t0 = (uint64_t)blockIdx.x * kTile; t0 < nrows; t0 += (uint64_t)gridDim.x * kTile) {
+        uint32_t recid[kSpRows], w0[kSpRows], prev0[kSpRows];
+#pragma unroll
+        for (int u = 0; u < kSpRows; ++u) { // every load of the step is issued before the first use
+            const uint64_t r = t0 + (uint64_t)u * kSpThreads + tid;
+            recid[u] = w0[u] = prev0[u] = 0;
+            if (r < nrows) {
+                const uint64_t base = slot_word(row_slot ? row_slot[r] : r);
+                recid[u] = ld_sparse(img + base);
+                w0[u] = (FIELD == 0) ? recid[u] : ld_sparse(img + base + 1);
+                if (lane == 0 && r > 0) prev0[u] = ld_sparse(img + slot_word(row_slot ? row_slot[r - 1] : r - 1));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kSpRows; ++u) {
+            const uint64_t r = t0 + (uint64_t)u * kSpThreads + tid;
+            const bool live = r < nrows;
+            uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, recid[u], 1);
+            if (lane == 0) prev = prev0[u];
+            if (live) {
+                out_recid[r] = recid[u];
+                out_w0[r] = w0[u];
+                if (HIST) {
+                    atomicAdd(&s_hist[0][w0[u] & 0xFF], 1u);
+                    atomicAdd(&s_hist[1][(w0[u] >> 8) & 0xFF], 1u);
+                    atomicAdd(&s_hist[2][(w0[u] >> 16) & 0xFF], 1u);
+                    atomicAdd(&s_hist[3][w0[u] >> 24], 1u);
+                }
+                o_w0 |= w0[u];
+                a_w0 &= w0[u];
+                o_id |= recid[u];
+                a_id &= recid[u];
+                unsorted |= (r > 0 && recid[u] < prev) ? 1u : 0u; // recid monotone in file order? (see extract_kernel)
+            }
+        }
+    }
+    o_w0 = __reduce_or_sync(0xFFFFFFFFu, o_w0);
+    a_w0 = __reduce_and_sync(0xFFFFFFFFu, a_w0);
+    o_id = __reduce_or_sync(0xFFFFFFFFu, o_id);
+    a_id = __reduce_and_sync(0xFFFFFFFFu, a_id);
+    unsorted = __reduce_or_sync(0xFFFFFFFFu, unsorted);
+    if (lane == 0) {
+        atomicOr(&s_or[0], o_w0);
+        atomicAnd(&s_and[0], a_w0);
+        atomicOr(&s_or[1], o_id);
+        atomicAnd(&s_and[1], a_id);
+        if (unsorted) s_flag = 1;
+    }
+    __syncthreads();
+    if ((uint64_t)blockIdx.x * kTile >= nrows) return;
+    if (HIST)
+        for (int i = tid; i < 4 * 256; i += kSpThreads) {
+            const uint32_t c = (&s_hist[0][0])[i];
+            if (c) atomicAdd(&byte_hist[i], c);
+        }
+    if (tid == 0) {
+        atomicOr(&stats->or_w0, s_or[0]);
+        atomicAnd(&stats->and_w0, s_and[0]);
+        atomicOr(&stats->or_recid, s_or[1]);
+        atomicAnd(&stats->and_recid, s_and[1]);
+        if (s_flag) atomicOr(&stats->recid_unsorted, 1u);
+    }
+}
+
 template <int FIELD>
 static int launch_extract_stream(const uint32_t *img, uint64_t nblocks, uint64_t nrows, uint32_t kw,
                                  const uint32_t *blk_nres, const uint32_t *blk_row_off, uint32_t *d_w0,
@@ -431,9 +526,18 @@ int extract_keys(const void *d_image, uint64_t nblocks_img, uint64_t nrows, cons
     const bool ragged = d_row_slot != nullptr;
     const bool stream_ok = (!ragged || (d_blk_nres && d_blk_row_off)) && ((uintptr_t)d_image % 16 == 0) &&
                            getenv("DBT_EXTRACT_STRIDED") == nullptr;
-    if (d_byte_hist && stream_ok && nrows && (field == '0' || field == '1'))
+    static const bool sparse_on = [] { const char *e = getenv("DBT_EXTRACT_SPARSE"); return !e || atoi(e) != 0; }(); // A/B hook
+    const bool sparse = sparse_on && (field == '0' || field == '1');
+    if (d_byte_hist && (stream_ok || sparse) && nrows && (field == '0' || field == '1'))
         DBT_CUDA(cudaMemsetAsync(d_byte_hist, 0, 4 * 256 * 4, st));
-    if (nrows && stream_ok) {
+    if (nrows && sparse) {
+        const uint32_t *img = (const uint32_t *)d_image;
+        const int grid = (int)std::min<uint64_t>((nrows + kSpThreads * kSpRows - 1) / (kSpThreads * kSpRows), 148 * 8);
+        if (field == '0') extract_sparse_kernel<0><<<grid, kSpThreads, 0, st>>>(img, nrows, d_row_slot, d_w0, d_recid, d_stats, d_byte_hist);
+        else extract_sparse_kernel<1><<<grid, kSpThreads, 0, st>>>(img, nrows, d_row_slot, d_w0, d_recid, d_stats, d_byte_hist);
+        count_launch();
+        if (hist_done && d_byte_hist) *hist_done = 1;
+    } else if (nrows && stream_ok) {
         const uint32_t *img = (const uint32_t *)d_image;
         const uint64_t nblocks = ragged ? nblocks_img : (nrows + kRpb - 1) / kRpb;
         const uint32_t *bn = ragged ? d_blk_nres : nullptr, *bo = ragged ? d_blk_row_off : nullptr;

@@ -881,7 +881,7 @@ gather_word_kernel(const uint32_t *__restrict__ src, uint32_t stride, uint32_t w
     uint64_t gstride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gstride) {
         uint64_t r = perm ? perm[i] : i;
-        out[i] = src[r * stride + word];
+        out[i] = perm ? ld_sparse(src + r * stride + word) : src[r * stride + word];
     }
 }
 int gather_word(const uint32_t *d_src, uint32_t stride, uint32_t word, const uint32_t *d_perm, uint32_t *d_out,

@@ -13,8 +13,9 @@ wsb = L.dbt_sort_pairs_ws_bytes(n); ws = torch.empty(wsb, dtype=torch.uint8, dev
 alt = C.c_int(); sp = torch.cuda.current_stream().cuda_stream
 L.dbt_stage_timing_enable(1)
 ts = []
+iota = torch.arange(n, dtype=torch.int32, device="cuda")
 for it in range(iters + 2):
-    k1.copy_(keys); v1.copy_(torch.arange(n, dtype=torch.int32, device="cuda")) if it == 0 else None
+    k1.copy_(keys); v1.copy_(iota)
     torch.cuda.synchronize(); L.dbt_stage_timing_reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -25,5 +26,10 @@ rep = dbt.stage_report()
 ko = k2 if alt.value else k1
 c = ko[: min(n, 50_000_000)].to(torch.int64) & 0xFFFFFFFF
 ok = bool((c[1:] >= c[:-1]).all().item())
+if n <= 200_000_000:  # exact: the row column must be the stable argsort of the keys
+    vo = v2 if alt.value else v1
+    want = torch.sort(keys.to(torch.int64) & 0xFFFFFFFF, stable=True).indices
+    ok = ok and bool((vo.to(torch.int64) == want).all().item())
+    del want
 ms = sum(ts) / len(ts); one = rep["onesweep_pass"][0] / 4
 print(f"n={n} total {ms:.3f} ms  onesweep/pass {one:.3f} ms = {16*n/one/1e6/peak:.3f} of HBM peak  hist {rep['histogram'][0]:.3f} ms  sorted={ok}  env={ {k:v for k,v in os.environ.items() if k.startswith('DBT_')} }")
