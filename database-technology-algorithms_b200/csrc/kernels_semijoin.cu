@@ -353,6 +353,49 @@ semijoin_count_kernel(const uint32_t *__restrict__ img, uint64_t nblocks, const 
     }
 }
 
+// Pass 1 without the image: the key is in the record's first 8 bytes, and ld.global.nc.L2::64B (ld_sparse) fills 64 bytes per L2
+// miss instead of a 128-byte line, so testing the keys costs ~68 bytes of DRAM traffic per S row instead of the 140 the
+// streaming version reads (the nreserved word of the block header shares its 64 bytes with the first record).  Four blocks
+// (4 x 100 independent loads) per CTA step.
+constexpr int kCsBlocks = 4;
+template <int FIELD>
+__global__ void __launch_bounds__(kTpThreads)
+semijoin_count_sparse_kernel(const uint32_t *__restrict__ img, uint64_t nblocks, const uint32_t *__restrict__ bm, uint32_t base,
+                             uint32_t span, uint4 *__restrict__ masks, uint32_t *__restrict__ counts) {
+    __shared__ uint32_t s_mask[kCsBlocks][4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint64_t b0 = (uint64_t)blockIdx.x * kCsBlocks; b0 < nblocks; b0 += (uint64_t)gridDim.x * kCsBlocks) {
+        uint32_t key[kCsBlocks], nres[kCsBlocks];
+#pragma unroll
+        for (int u = 0; u < kCsBlocks; ++u) {
+            const uint64_t b = b0 + u;
+            key[u] = nres[u] = 0;
+            if (b < nblocks) {
+                const uint32_t *blk = img + b * kBlockWords;
+                nres[u] = ld_sparse(blk + 1);
+                if (tid < (int)kRpb) key[u] = ld_sparse(blk + kEntriesWord + tid * kRecWords + (FIELD == 0 ? 0 : 1));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kCsBlocks; ++u) {
+            bool match = false;
+            if (tid < (int)min(nres[u], kRpb)) {
+                const uint32_t v = key[u] - base;
+                match = (v <= span) && ((__ldg(bm + (v >> 5)) >> (v & 31)) & 1u);
+            }
+            const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, match);
+            if (lane == 0) s_mask[u][warp] = ballot;
+        }
+        __syncthreads();
+        if (tid < kCsBlocks && b0 + tid < nblocks) {
+            const uint4 m = make_uint4(s_mask[tid][0], s_mask[tid][1], s_mask[tid][2], s_mask[tid][3]);
+            masks[b0 + tid] = m;
+            counts[b0 + tid] = __popc(m.x) + __popc(m.y) + __popc(m.z) + __popc(m.w);
+        }
+        __syncthreads(); // s_mask is rewritten by the next step
+    }
+}
+
 __global__ void __launch_bounds__(kTpThreads)
 semijoin_copy_kernel(const uint32_t *__restrict__ img, uint64_t nblocks, const uint4 *__restrict__ masks, const uint32_t *__restrict__ counts,
                      const uint32_t *__restrict__ offs /*[nblocks] output row of the block's first match*/, uint32_t *__restrict__ out) {
@@ -443,8 +486,13 @@ int semijoin_two_pass(const void *d_s_img, uint64_t nblocks_s, int field, const 
     DBT_TRY(occupancy((const void *)semijoin_copy_kernel, 2));
     {
         StageScope sc(ST_HASH_PROBE, st);
+        static const bool sparse = [] { const char *e = getenv("DBT_SEMIJOIN_SPARSE"); return !e || atoi(e) != 0; }(); // A/B hook
         const int grid = (int)std::min<uint64_t>(nblocks_s, (uint64_t)148 * per_sm[f]);
-        if (f == 0)
+        if (sparse) {
+            const int g = (int)std::min<uint64_t>((nblocks_s + kCsBlocks - 1) / kCsBlocks, (uint64_t)148 * 16);
+            if (f == 0) semijoin_count_sparse_kernel<0><<<g, kTpThreads, 0, st>>>((const uint32_t *)d_s_img, nblocks_s, d_bitmap, base, span, masks, counts);
+            else semijoin_count_sparse_kernel<1><<<g, kTpThreads, 0, st>>>((const uint32_t *)d_s_img, nblocks_s, d_bitmap, base, span, masks, counts);
+        } else if (f == 0)
             semijoin_count_kernel<0><<<grid, kTpThreads, smem, st>>>((const uint32_t *)d_s_img, nblocks_s, d_bitmap, base, span, masks, counts);
         else
             semijoin_count_kernel<1><<<grid, kTpThreads, smem, st>>>((const uint32_t *)d_s_img, nblocks_s, d_bitmap, base, span, masks, counts);
