@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) header_kernel(const uint32_t *__restrict_
     uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t r = 0, ragged = 0;
     if (b < nblocks) {
-        r = img[b * kBlockWords + 1];
+        r = ld_sparse(img + b * kBlockWords + 1);
         if (r > kRpb) r = kRpb;
         if (b + 1 < nblocks && r != kRpb) ragged = 1;
         if (nres_out) nres_out[b] = r;

@@ -468,59 +468,14 @@ __global__ void __launch_bounds__(256) blockid_add_kernel(uint32_t *__restrict__
     if (b < nblocks) img[b * kBlockWords] += blockid0;
 }
 
-__global__ void __launch_bounds__(kGatherThreads)
-gather_kernel(const uint32_t *__restrict__ in, const uint32_t *__restrict__ rows, const uint32_t *__restrict__ row_slot,
-              uint64_t nrows_out, uint4 *__restrict__ out, uint64_t nblocks_out) {
-    __shared__ __align__(16) uint32_t stage[kBlockWords];
-    __shared__ uint64_t src[kRpb];
-    const int tid = threadIdx.x;
-    for (uint64_t ob = blockIdx.x; ob < nblocks_out; ob += gridDim.x) {
-        const uint64_t r0 = ob * kRpb;
-        const uint32_t cnt = (uint32_t)min((uint64_t)kRpb, nrows_out - r0);
-        if (tid < (int)cnt) {
-            uint32_t row = rows ? rows[r0 + tid] : (uint32_t)(r0 + tid);
-            uint64_t slot = row_slot ? row_slot[row] : row;
-            src[tid] = slot_word(slot);
-        }
-        if (tid == 0) {
-            stage[0] = (uint32_t)ob; // blockid
-            stage[1] = cnt;          // nreserved
-            stage[kTrailerWord] = 1; // valid=1, misc=0, padding 0
-            stage[kTrailerWord + 1] = cnt; // dummy
-        }
-        __syncthreads();
-        const uint32_t nwords = cnt * kRecWords;
-        // all of a thread's loads are issued before the first shared-memory store: ~14 independent
-        // 4-byte loads in flight per thread (the first version had 4 and was latency-bound, ncu r01)
-        constexpr int kPerThread = (kRpb * kRecWords + kGatherThreads - 1) / kGatherThreads;
-        uint32_t v[kPerThread];
-#pragma unroll
-        for (int k = 0; k < kPerThread; ++k) {
-            uint32_t idx = tid + k * kGatherThreads;
-            uint32_t rec = idx / kRecWords;
-            uint32_t w = idx - rec * kRecWords;
-            v[k] = (idx < nwords) ? ld_sparse(in + src[rec] + w) : 0u;
-        }
-#pragma unroll
-        for (int k = 0; k < kPerThread; ++k) {
-            uint32_t idx = tid + k * kGatherThreads;
-            if (idx < kRpb * kRecWords) stage[kEntriesWord + idx] = v[k];
-        }
-        __syncthreads();
-        const uint4 *sv = reinterpret_cast<const uint4 *>(stage);
-        uint4 *dst = out + ob * kBlockVec4;
-        for (uint32_t i = tid; i < kBlockVec4; i += kGatherThreads) dst[i] = sv[i];
-        __syncthreads();
-    }
-}
-
-// Version 2 (default): the same gather, software-pipelined.  Why (ncu, profiles/r02_notes.md): with 64-byte fills version 1 no
-// longer saturates DRAM (65 % busy, long-scoreboard and barrier stalls): a CTA's record loads are in flight for ~40 % of its
-// time -- the rest goes to the rows -> slot -> word-offset chain before them and to the block store after them.  Here the
-// loads of block b+1 are issued BEFORE block b is stored, and the offsets of block b+2 are fetched under them, so every CTA
-// has record loads in flight nearly all the time, with two barriers per block instead of three.
-// (A cp.async / LDGSTS version -- 4-byte copies straight into a second stage buffer, 32 registers, 7 CTAs per SM -- was
-// 35 % SLOWER than version 1: 7.86 vs 5.84 ms per 90M rows.)
+// The loop is software-pipelined (round 2).  With 64-byte fills (ld_sparse: DRAM read 267 -> 202 B per record) the first
+// version -- offsets, loads, barrier, stage, barrier, store, barrier per block -- no longer saturated DRAM (ncu: 65 % busy,
+// long-scoreboard and barrier stalls; a CTA's record loads were in flight ~40 % of its time).  Here the loads of block b+1
+// are issued BEFORE block b is stored and the rows -> slot -> word-offset chain of block b+2 is fetched under them: record
+// loads are in flight nearly all the time, two barriers per block.  6.03 -> 5.84 (64-byte fills) -> 5.63-5.66 ms per 90M rows.
+// Two other designs end at the same 5.6 ms = 5.5 TB/s of actual traffic, which is therefore the memory system's rate for
+// this mix of 64-byte random reads and streaming writes (profiles/r02_notes.md): aligned 16-byte cp.async.cg chunks into
+// 160-byte slots, three blocks deep, no registers under the loads (5.64 ms); 4-byte cp.async.ca copies were 35 % slower (7.86).
 __device__ __forceinline__ uint32_t ld_sparse_pinned(const uint32_t *p) { // stays where it is written (before the block store)
     uint32_t v;
 #if DBT_SPARSE_LD
@@ -531,10 +486,9 @@ __device__ __forceinline__ uint32_t ld_sparse_pinned(const uint32_t *p) { // sta
     return v;
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(kGatherThreads, MINB)
-gather2_kernel(const uint32_t *__restrict__ in, const uint32_t *__restrict__ rows, const uint32_t *__restrict__ row_slot,
-               uint64_t nrows_out, uint4 *__restrict__ out, uint64_t nblocks_out) {
+__global__ void __launch_bounds__(kGatherThreads, 5) // 48 registers, five CTAs per SM (four: 5.69 ms, six: 6.04 ms per 90M rows)
+gather_kernel(const uint32_t *__restrict__ in, const uint32_t *__restrict__ rows, const uint32_t *__restrict__ row_slot,
+              uint64_t nrows_out, uint4 *__restrict__ out, uint64_t nblocks_out) {
     __shared__ __align__(16) uint32_t stage[kBlockWords];
     __shared__ uint64_t src[2][kRpb];
     const int tid = threadIdx.x;
@@ -605,139 +559,15 @@ gather2_kernel(const uint32_t *__restrict__ in, const uint32_t *__restrict__ row
     }
 }
 
-// Version 3: no registers under the record reads at all.  A record (140 bytes, 4-byte aligned) lies inside 9 or 10
-// ALIGNED 16-byte chunks; those are copied global -> shared memory by cp.async.cg (LDGSTS.128, L1 bypassed, .L2::64B fills)
-// into a 160-byte slot per record that keeps the source alignment, three blocks deep per CTA; the output block is then
-// assembled straight from the slots (4 shifted LDS.32 per 16-byte store).  Bytes in flight per SM are bounded by shared
-// memory (4 CTAs x 2 blocks ahead x 100 records x ~200 B), not by registers (version 2: 4 CTAs x 256 threads x 56 B).
-constexpr int kG3Stages = 3;
-constexpr int kG3SlotWords = 40; // 160 bytes
-struct G3Smem {
-    alignas(16) uint32_t slot[kG3Stages][kRpb * kG3SlotWords];
-    uint64_t src[kG3Stages + 1][kRpb]; // aligned BYTE address of each record's first chunk; ring of stages + 1 (see the loop)
-    uint32_t shift[kG3Stages + 1][kRpb]; // (record address - chunk address) / 4
-};
-
-__global__ void __launch_bounds__(kGatherThreads, 4)
-gather3_kernel(const uint32_t *__restrict__ in, const uint32_t *__restrict__ rows, const uint32_t *__restrict__ row_slot,
-               uint64_t nrows_out, uint4 *__restrict__ out, uint64_t nblocks_out) {
-    extern __shared__ __align__(16) unsigned char g3_raw[];
-    G3Smem &sm = *reinterpret_cast<G3Smem *>(g3_raw);
-    const int tid = threadIdx.x;
-    const uint64_t G = gridDim.x;
-    auto count_of = [&](uint64_t ob) { return ob < nblocks_out ? (uint32_t)min((uint64_t)kRpb, nrows_out - ob * kRpb) : 0u; };
-    auto fetch_src = [&](uint64_t ob) -> uint64_t { // byte address of record `tid` of block ob (0: none)
-        if (tid < (int)count_of(ob)) {
-            const uint64_t r = ob * kRpb + tid;
-            const uint32_t row = rows ? rows[r] : (uint32_t)r;
-            const uint64_t slot = row_slot ? row_slot[row] : row;
-            return (uint64_t)(uintptr_t)(in + slot_word(slot));
-        }
-        return 0;
-    };
-    auto publish_src = [&](int ring, uint64_t a) {
-        if (tid < (int)kRpb) {
-            sm.src[ring][tid] = a & ~15ull;
-            sm.shift[ring][tid] = (uint32_t)(a & 15ull) >> 2;
-        }
-    };
-    auto issue = [&](uint64_t ob, int stg, int ring) { // the block's chunk copies (src/shift[ring] are visible); one group
-        const uint32_t cnt = count_of(ob);
-        constexpr int kPerThread = (kRpb * 10 + kGatherThreads - 1) / kGatherThreads;
-#pragma unroll
-        for (int k = 0; k < kPerThread; ++k) {
-            const uint32_t idx = tid + k * kGatherThreads;
-            const uint32_t rec = idx / 10u;
-            const uint32_t c = idx - rec * 10u;
-            if (rec < cnt && (c < 9u || sm.shift[ring][rec] >= 2u)) { // 4*shift + 140 bytes: 9 chunks for shift 0/1, 10 for 2/3
-                const uint32_t d = (uint32_t)__cvta_generic_to_shared(&sm.slot[stg][rec * kG3SlotWords + c * 4u]);
-                const uint64_t g = sm.src[ring][rec] + c * 16u;
-#if DBT_SPARSE_LD
-                asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
-#else
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
-#endif
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    uint64_t ob = blockIdx.x;
-    if (ob >= nblocks_out) return;
-    // prologue: blocks ob, ob+G (stages 0, 1; rings 0, 1) in flight, the address chain of block ob+2G in a register
-#pragma unroll
-    for (int i = 0; i < kG3Stages - 1; ++i) publish_src(i, fetch_src(ob + i * G));
-    uint64_t wnext = fetch_src(ob + (kG3Stages - 1) * G);
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < kG3Stages - 1; ++i) issue(ob + i * G, i, i);
-    int stg = 0, ring = 0; // of block ob
-    for (; ob < nblocks_out; ob += G) {
-        const int nstg = (stg + kG3Stages - 1) % kG3Stages, nring = (ring + kG3Stages - 1) % (kG3Stages + 1);
-        const uint64_t nb = ob + (kG3Stages - 1) * G;
-        // ring slot nring last served block ob - 2G (its output phase ended two barriers ago); stage nstg served block ob - G
-        publish_src(nring, wnext);
-        __syncthreads(); // src/shift[nring] visible; everybody has finished reading stage nstg (block ob - G)
-        issue(nb, nstg, nring);
-        wnext = fetch_src(nb + G);                            // in flight under the output phase
-        asm volatile("cp.async.wait_group %0;" ::"n"(kG3Stages - 1) : "memory"); // this thread's chunks of block ob have landed ...
-        __syncthreads();                                      // ... and everybody else's
-        const uint32_t cnt = count_of(ob);
-        const uint32_t *slots = sm.slot[stg];
-        const uint32_t *shf = sm.shift[ring];
-        uint4 *dst = out + ob * kBlockVec4;
-        for (uint32_t i = tid; i < kBlockVec4; i += kGatherThreads) {
-            uint32_t q[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t wq = 4u * i + j;
-                if (wq < kEntriesWord) q[j] = wq == 0 ? (uint32_t)ob : cnt;                  // blockid, nreserved
-                else if (wq >= kTrailerWord) q[j] = wq == kTrailerWord ? 1u : cnt;            // valid=1/misc/pad, dummy
-                else {
-                    const uint32_t e = wq - kEntriesWord;
-                    const uint32_t rec = e / kRecWords;
-                    const uint32_t w = e - rec * kRecWords;
-                    q[j] = rec < cnt ? slots[rec * kG3SlotWords + w + shf[rec]] : 0u;
-                }
-            }
-            dst[i] = make_uint4(q[0], q[1], q[2], q[3]);
-        }
-        stg = (stg + 1) % kG3Stages;
-        ring = (ring + 1) % (kG3Stages + 1);
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
-
-static int gather_impl() { // 2 = software-pipelined (default), 1 = version 1
-    static int impl = [] {
-        const char *e = getenv("DBT_GATHER_IMPL");
-        return e ? atoi(e) : 2;
-    }();
-    return impl;
-}
-
 int gather_records(const void *d_in, const uint32_t *d_rows, const uint32_t *d_row_slot, uint64_t nrows_out, void *d_out,
                    cudaStream_t st, int max_ctas, uint32_t blockid0) {
     StageScope sc(ST_GATHER, st);
     if (nrows_out == 0) return 0;
     uint64_t nb = (nrows_out + kRpb - 1) / kRpb;
-    int grid = (int)std::min<uint64_t>(nb, max_ctas > 0 ? (uint64_t)max_ctas : 148 * 8 * 4);
-    if (gather_impl() == 3 && ((uintptr_t)d_in & 15) == 0) { // (the chunk windows stay inside the image only for aligned images)
-        constexpr size_t smem = sizeof(G3Smem);
-        if (first_use_on_device((const void *)gather3_kernel))
-            DBT_CUDA(cudaFuncSetAttribute(gather3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        grid = (int)std::min<uint64_t>(nb, max_ctas > 0 ? (uint64_t)max_ctas : 148 * 4);
-        gather3_kernel<<<grid, kGatherThreads, smem, st>>>((const uint32_t *)d_in, d_rows, d_row_slot, nrows_out, (uint4 *)d_out, nb);
-    } else if (gather_impl() >= 2) {
-        static const int minb = [] { const char *e = getenv("DBT_GATHER_MINB"); return e ? atoi(e) : 4; }(); // tuning hook
-        grid = (int)std::min<uint64_t>(nb, max_ctas > 0 ? (uint64_t)max_ctas : 148 * (uint64_t)minb); // persistent: the resident CTAs
-        if (minb == 5) gather2_kernel<5><<<grid, kGatherThreads, 0, st>>>((const uint32_t *)d_in, d_rows, d_row_slot, nrows_out, (uint4 *)d_out, nb);
-        else if (minb == 6) gather2_kernel<6><<<grid, kGatherThreads, 0, st>>>((const uint32_t *)d_in, d_rows, d_row_slot, nrows_out, (uint4 *)d_out, nb);
-        else gather2_kernel<4><<<grid, kGatherThreads, 0, st>>>((const uint32_t *)d_in, d_rows, d_row_slot, nrows_out, (uint4 *)d_out, nb);
-    } else
-        gather_kernel<<<grid, kGatherThreads, 0, st>>>((const uint32_t *)d_in, d_rows, d_row_slot, nrows_out, (uint4 *)d_out,
-                                                       nb);
+    int grid = (int)std::min<uint64_t>(nb, max_ctas > 0 ? (uint64_t)max_ctas : 148 * 5); // persistent: the resident CTAs
+    gather_kernel<<<grid, kGatherThreads, 0, st>>>((const uint32_t *)d_in, d_rows, d_row_slot, nrows_out, (uint4 *)d_out, nb);
     if (blockid0) { // a chunk of a larger image (out-of-core): renumber in a separate tiny pass -- an extra parameter in
-                    // gather_kernel itself changed its schedule and cost 6 % (profiles/r01_notes.md)
+                    // the round-1 gather_kernel itself changed its schedule and cost 6 % (profiles/r01_notes.md)
         blockid_add_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>((uint32_t *)d_out, nb, blockid0);
         count_launch();
     }
