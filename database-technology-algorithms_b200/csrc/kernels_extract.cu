@@ -526,9 +526,8 @@ int extract_keys(const void *d_image, uint64_t nblocks_img, uint64_t nrows, cons
     const bool ragged = d_row_slot != nullptr;
     const bool stream_ok = (!ragged || (d_blk_nres && d_blk_row_off)) && ((uintptr_t)d_image % 16 == 0) &&
                            getenv("DBT_EXTRACT_STRIDED") == nullptr;
-    static const bool sparse_on = [] { const char *e = getenv("DBT_EXTRACT_SPARSE"); return !e || atoi(e) != 0; }(); // A/B hook
-    const bool sparse = sparse_on && (field == '0' || field == '1');
-    if (d_byte_hist && (stream_ok || sparse) && nrows && (field == '0' || field == '1'))
+    const bool sparse = field == '0' || field == '1'; // the key is the record's first 8 bytes: strided 64-byte-fill reads
+    if (d_byte_hist && sparse && nrows)
         DBT_CUDA(cudaMemsetAsync(d_byte_hist, 0, 4 * 256 * 4, st));
     if (nrows && sparse) {
         const uint32_t *img = (const uint32_t *)d_image;
@@ -542,20 +541,15 @@ int extract_keys(const void *d_image, uint64_t nblocks_img, uint64_t nrows, cons
         const uint64_t nblocks = ragged ? nblocks_img : (nrows + kRpb - 1) / kRpb;
         const uint32_t *bn = ragged ? d_blk_nres : nullptr, *bo = ragged ? d_blk_row_off : nullptr;
         switch (field) {
-        case '0': DBT_TRY(launch_extract_stream<0>(img, nblocks, nrows, kw, bn, bo, d_w0, d_str, d_recid, d_stats, d_byte_hist, st)); break;
-        case '1': DBT_TRY(launch_extract_stream<1>(img, nblocks, nrows, kw, bn, bo, d_w0, d_str, d_recid, d_stats, d_byte_hist, st)); break;
         case '2': DBT_TRY(launch_extract_stream<2>(img, nblocks, nrows, kw, bn, bo, d_w0, d_str, d_recid, d_stats, d_byte_hist, st)); break;
         case '3': DBT_TRY(launch_extract_stream<3>(img, nblocks, nrows, kw, bn, bo, d_w0, d_str, d_recid, d_stats, d_byte_hist, st)); break;
         default: set_error("bad field"); return DBT_ERR_ARG;
         }
         count_launch();
-        if (hist_done && d_byte_hist && (field == '0' || field == '1')) *hist_done = 1;
     } else if (nrows) {
         int grid = (int)((nrows + 255) / 256);
         const uint32_t *img = (const uint32_t *)d_image;
         switch (field) {
-        case '0': extract_kernel<0><<<grid, 256, 0, st>>>(img, nrows, d_row_slot, kw, d_w0, d_str, d_recid, d_stats); break;
-        case '1': extract_kernel<1><<<grid, 256, 0, st>>>(img, nrows, d_row_slot, kw, d_w0, d_str, d_recid, d_stats); break;
         case '2': extract_kernel<2><<<grid, 256, 0, st>>>(img, nrows, d_row_slot, kw, d_w0, d_str, d_recid, d_stats); break;
         case '3': extract_kernel<3><<<grid, 256, 0, st>>>(img, nrows, d_row_slot, kw, d_w0, d_str, d_recid, d_stats); break;
         default: set_error("bad field"); return DBT_ERR_ARG;

@@ -312,50 +312,9 @@ __device__ __forceinline__ void tp_wait(const TpPipe &p, int sidx, uint32_t pari
                      : "memory");
 }
 
-template <int FIELD>
-__global__ void __launch_bounds__(kTpThreads)
-semijoin_count_kernel(const uint32_t *__restrict__ img, uint64_t nblocks, const uint32_t *__restrict__ bm, uint32_t base, uint32_t span,
-                      uint4 *__restrict__ masks /*[nblocks]: 100 match bits*/, uint32_t *__restrict__ counts /*[nblocks]*/) {
-    extern __shared__ __align__(128) unsigned char tp_raw[];
-    TpPipe pipe{reinterpret_cast<uint32_t(*)[kBlockWords]>(tp_raw),
-                reinterpret_cast<uint64_t *>(tp_raw + sizeof(uint32_t) * kBlockWords * kTpStages)};
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t first = blockIdx.x, step = gridDim.x;
-    const uint64_t mine = first < nblocks ? (nblocks - first + step - 1) / step : 0;
-    if (tid == 0) {
-        for (int i = 0; i < kTpStages; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sj_smem_u32(&pipe.mbar[i])), "r"(1));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (uint64_t k = 0; k < (uint64_t)(kTpStages - 1) && k < mine; ++k) tp_issue(pipe, img, first + k * step, (int)k);
-    }
-    __syncthreads();
-    __shared__ uint32_t s_mask[4];
-    for (uint64_t k = 0; k < mine; ++k) {
-        if (tid == 0 && k + kTpStages - 1 < mine) tp_issue(pipe, img, first + (k + kTpStages - 1) * step, (int)((k + kTpStages - 1) % kTpStages));
-        const int sidx = (int)(k % kTpStages);
-        tp_wait(pipe, sidx, (uint32_t)((k / kTpStages) & 1));
-        const uint32_t *blk = pipe.stage[sidx];
-        const uint32_t nres = min(blk[1], kRpb);
-        bool match = false;
-        if (tid < (int)nres) {
-            const uint32_t v = blk[kEntriesWord + tid * kRecWords + (FIELD == 0 ? 0 : 1)] - base;
-            match = (v <= span) && ((__ldg(bm + (v >> 5)) >> (v & 31)) & 1u);
-        }
-        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, match);
-        if (lane == 0) s_mask[warp] = ballot;
-        __syncthreads(); // (also: everyone is done with this stage before it is refilled)
-        if (tid == 0) {
-            const uint64_t b = first + k * step;
-            const uint4 m = make_uint4(s_mask[0], s_mask[1], s_mask[2], s_mask[3]);
-            masks[b] = m;
-            counts[b] = __popc(m.x) + __popc(m.y) + __popc(m.z) + __popc(m.w);
-        }
-        __syncthreads(); // s_mask is rewritten by the next block
-    }
-}
-
-// Pass 1 without the image: the key is in the record's first 8 bytes, and ld.global.nc.L2::64B (ld_sparse) fills 64 bytes per L2
-// miss instead of a 128-byte line, so testing the keys costs ~68 bytes of DRAM traffic per S row instead of the 140 the
-// streaming version reads (the nreserved word of the block header shares its 64 bytes with the first record).  Four blocks
+// Pass 1 does not need the image: the key is in the record's first 8 bytes, and ld.global.nc.L2::64B (ld_sparse) fills 64 bytes
+// per L2 miss instead of a 128-byte line, so testing the keys costs ~68 bytes of DRAM traffic per S row instead of the 140 a
+// streaming pass reads (round 2's first version: 9.1 ms per 400M rows; this one 4.8) (the nreserved word of the block header shares its 64 bytes with the first record).  Four blocks
 // (4 x 100 independent loads) per CTA step.
 constexpr int kCsBlocks = 4;
 template <int FIELD>
@@ -482,20 +441,12 @@ int semijoin_two_pass(const void *d_s_img, uint64_t nblocks_s, int field, const 
         }
         return 0;
     };
-    DBT_TRY(occupancy(f == 0 ? (const void *)semijoin_count_kernel<0> : (const void *)semijoin_count_kernel<1>, f));
     DBT_TRY(occupancy((const void *)semijoin_copy_kernel, 2));
     {
         StageScope sc(ST_HASH_PROBE, st);
-        static const bool sparse = [] { const char *e = getenv("DBT_SEMIJOIN_SPARSE"); return !e || atoi(e) != 0; }(); // A/B hook
-        const int grid = (int)std::min<uint64_t>(nblocks_s, (uint64_t)148 * per_sm[f]);
-        if (sparse) {
-            const int g = (int)std::min<uint64_t>((nblocks_s + kCsBlocks - 1) / kCsBlocks, (uint64_t)148 * 16);
-            if (f == 0) semijoin_count_sparse_kernel<0><<<g, kTpThreads, 0, st>>>((const uint32_t *)d_s_img, nblocks_s, d_bitmap, base, span, masks, counts);
-            else semijoin_count_sparse_kernel<1><<<g, kTpThreads, 0, st>>>((const uint32_t *)d_s_img, nblocks_s, d_bitmap, base, span, masks, counts);
-        } else if (f == 0)
-            semijoin_count_kernel<0><<<grid, kTpThreads, smem, st>>>((const uint32_t *)d_s_img, nblocks_s, d_bitmap, base, span, masks, counts);
-        else
-            semijoin_count_kernel<1><<<grid, kTpThreads, smem, st>>>((const uint32_t *)d_s_img, nblocks_s, d_bitmap, base, span, masks, counts);
+        const int g = (int)std::min<uint64_t>((nblocks_s + kCsBlocks - 1) / kCsBlocks, (uint64_t)148 * 16);
+        if (f == 0) semijoin_count_sparse_kernel<0><<<g, kTpThreads, 0, st>>>((const uint32_t *)d_s_img, nblocks_s, d_bitmap, base, span, masks, counts);
+        else semijoin_count_sparse_kernel<1><<<g, kTpThreads, 0, st>>>((const uint32_t *)d_s_img, nblocks_s, d_bitmap, base, span, masks, counts);
         count_launch();
         DBT_KERNEL_CHECK();
     }
