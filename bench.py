@@ -877,12 +877,12 @@ def extra_measurements(dbt, torch, dev, peak):
                 "probe_tuples_per_s": ns / (ms * 1e-3), "ms": ms, "nres": k, "selectivity": sel,
                 "stage_ms": {a: round(b[0], 3) for a, b in rep.items()},
                 "s_passes_hbm_frac_of_measured": (140 + 140 * sel) * ns / (probe_ms * 1e-3) / 1e9 / peak,
-                "s_passes_actual_bytes_frac_of_measured": (280 + 140 * sel) * ns / (probe_ms * 1e-3) / 1e9 / peak,
+                "s_passes_actual_bytes_frac_of_measured": (68 + 140 + 140 * sel) * ns / (probe_ms * 1e-3) / 1e9 / peak,
                 "note": "semi-join (reference semantics): S rows in S order whose key is in keys(R).  R: extraction + "
-                        "direct-address bitmap (L2-resident: keys(R) span < 2^29).  S: two streaming passes over the image "
-                        "(count per block, scan, copy the matching records to their final place): algorithmic 140 B read + "
-                        "140 B written per match; actual 280 B read (S is read twice, sequentially, instead of once "
-                        "sequentially + once as a random gather at 267 B per match)"}
+                        "direct-address bitmap (L2-resident: keys(R) span < 2^29).  S: a key pass (8 bytes per row through "
+                        "64-byte-fill loads: ~68 B of DRAM reads per row, ncu), the scan of the per-block match counts, and a "
+                        "streaming pass over the image that copies the matching records to their final place: algorithmic "
+                        "140 B read per S row + 140 B written per match; actual 68 + 140 B read per S row"}
             del d_r, d_s, d_o, ws
             torch.cuda.empty_cache()
         except Exception as e:  # noqa: BLE001

@@ -1,13 +1,16 @@
-"""CPU check of the bench contract on the committed line of the round's final run (profiles/r01_bench_line.json):
+"""CPU check of the bench contract on the committed lines of each round's final run (profiles/r0N_bench_line.json):
 the keys the driver and the judge read are present and consistent with each other."""
 import json
 import os
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_committed_bench_line_has_the_contract_keys():
-    with open(os.path.join(ROOT, "profiles", "r01_bench_line.json")) as f:
+@pytest.mark.parametrize("line", ["r01_bench_line.json", "r02_bench_line.json"])
+def test_committed_bench_line_has_the_contract_keys(line):
+    with open(os.path.join(ROOT, "profiles", line)) as f:
         d = json.load(f)
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "e2e", "roofline", "cpu_baseline", "clocks", "gpu_launches"):
