@@ -397,14 +397,14 @@ __device__ __forceinline__ void os2_process_tile(Os2Smem<THREADS, ITEMS> &sm, in
         const uint32_t d = (key[j] >> shift) & 0xFFu;
         bool valid = true;
         uint32_t peers;
-        if (RANK == 0 || (RANK == 2 && (j & 1))) {
+        if (RANK == 0) {
             if (!FULL) valid = li0 + j * 32 < nvalid;
             peers = __match_any_sync(0xFFFFFFFFu, valid ? d : 0x100u);
-        } else if (RANK >= 22 && RANK <= 25) {
+        } else if (RANK == 23) {
             // the hybrid below with the ballots written so that ptxas sets the bit predicates with one R2P and spends
             // VOTE + predicated NOT + OR per bit (3 instructions instead of the 6 it makes of `bit ? m : ~m`):
             // differing lanes are collected per bit and removed from the match mask at the end
-            constexpr int K = (RANK >= 22 && RANK <= 25) ? RANK - 20 : 3;
+            constexpr int K = 3; // (2: 0.496 ms per pass, 3: 0.498, 4: 0.570)
             if (!FULL) valid = li0 + j * 32 < nvalid;
             peers = __match_any_sync(0xFFFFFFFFu, valid ? (d & ((1u << K) - 1u)) : (1u << K));
             uint32_t mm[8 - K]; // lanes whose bit b differs from mine
@@ -422,10 +422,10 @@ __device__ __forceinline__ void os2_process_tile(Os2Smem<THREADS, ITEMS> &sm, in
             for (int t = 1; t + 1 < 8 - K; t += 2) asm("lop3.b32 %0, %0, %1, %2, 0xFE;" : "+r"(diff) : "r"(mm[t]), "r"(mm[t + 1]));
             if ((8 - K) % 2 == 0) asm("lop3.b32 %0, %0, %1, %2, 0x10;" : "+r"(peers) : "r"(diff), "r"(mm[8 - K - 1])); // a & ~(b | c)
             else peers &= ~diff;
-        } else if (RANK >= 13 && RANK <= 15) {
+        } else if (RANK == 13) {
             // hybrid: match.any on the low K bits (cost ~ number of distinct values: <= 2^K groups, ADU pipe)
             // and one ballot per remaining bit (ALU pipe): every item loads both pipes lightly
-            constexpr int K = (RANK >= 13 && RANK <= 15) ? RANK - 10 : 3; // (the other instantiations never run this branch)
+            constexpr int K = 3;
             if (!FULL) valid = li0 + j * 32 < nvalid;
             peers = __match_any_sync(0xFFFFFFFFu, valid ? (d & ((1u << K) - 1u)) : (1u << K));
 #pragma unroll
@@ -448,7 +448,7 @@ __device__ __forceinline__ void os2_process_tile(Os2Smem<THREADS, ITEMS> &sm, in
                 peers &= valid ? vm : ~vm;
             }
         }
-        if (RANK >= 22 && RANK <= 25) {
+        if (RANK == 23) {
             // every lane reads the group's counter itself (one broadcast LDS) before the group's first lane bumps it: no
             // leader election (BREV + FLO), no shuffle
             const uint32_t before = peers & lt;
@@ -544,8 +544,8 @@ __device__ __forceinline__ void os2_process_tile(Os2Smem<THREADS, ITEMS> &sm, in
     }
 }
 
-// RANK: 0 = match.any, 1 = 8 ballots, 2 = alternating (even items ballots, odd items match.any),
-//       10+K = match.any on the K low digit bits + (8-K) ballots (13 is the tuned default)
+// RANK: 23 = match.any on the 3 low digit bits + 5 hand-scheduled ballots (the default); kept for comparison runs
+// (DBT_ONESWEEP_RANK): 0 = match.any on the whole digit, 1 = 8 ballots, 13 = 23 as the compiler schedules `bit ? m : ~m`
 template <int THREADS, int ITEMS, bool HAS_VALS, bool IOTA_VALS, int RANK, typename S>
 __global__ void __launch_bounds__(THREADS, (THREADS * ITEMS <= 4096) ? 3 : ((THREADS * ITEMS <= 6144) ? 2 : 1))
 onesweep2_kernel(const uint32_t *__restrict__ kin, uint32_t *__restrict__ kout, const uint32_t *__restrict__ vin,
@@ -653,7 +653,7 @@ static int launch_onesweep_t(const uint32_t *kin, uint32_t *kout, const uint32_t
 
 struct Os2Cfg {
     int impl;  // 1 = version 1 (one tile per CTA), 2 = persistent pipelined
-    int rank;  // 0 match.any, 1 ballots, 2 mixed
+    int rank;  // 23 (default), or 0 / 1 / 13 for comparison runs
     int ctas_per_sm;
 };
 static Os2Cfg os2_cfg() {
@@ -685,24 +685,14 @@ static int launch_onesweep2_t(const uint32_t *kin, uint32_t *kout, const uint32_
     } while (0)
     if (iota) {
         if (rank == 0) DBT_LAUNCH_OS2(true, 0);
-        else if (rank == 2) DBT_LAUNCH_OS2(true, 2);
+        else if (rank == 1) DBT_LAUNCH_OS2(true, 1);
         else if (rank == 13) DBT_LAUNCH_OS2(true, 13);
-        else if (rank == 23) DBT_LAUNCH_OS2(true, 23);
-        else if (rank == 22) DBT_LAUNCH_OS2(true, 22);
-        else if (rank == 24) DBT_LAUNCH_OS2(true, 24);
-        else if (rank == 14) DBT_LAUNCH_OS2(true, 14);
-        else if (rank == 15) DBT_LAUNCH_OS2(true, 15);
-        else DBT_LAUNCH_OS2(true, 1);
+        else DBT_LAUNCH_OS2(true, 23);
     } else {
         if (rank == 0) DBT_LAUNCH_OS2(false, 0);
-        else if (rank == 2) DBT_LAUNCH_OS2(false, 2);
+        else if (rank == 1) DBT_LAUNCH_OS2(false, 1);
         else if (rank == 13) DBT_LAUNCH_OS2(false, 13);
-        else if (rank == 23) DBT_LAUNCH_OS2(false, 23);
-        else if (rank == 22) DBT_LAUNCH_OS2(false, 22);
-        else if (rank == 24) DBT_LAUNCH_OS2(false, 24);
-        else if (rank == 14) DBT_LAUNCH_OS2(false, 14);
-        else if (rank == 15) DBT_LAUNCH_OS2(false, 15);
-        else DBT_LAUNCH_OS2(false, 1);
+        else DBT_LAUNCH_OS2(false, 23);
     }
 #undef DBT_LAUNCH_OS2
     count_launch();
@@ -713,7 +703,6 @@ static int launch_onesweep2_t(const uint32_t *kin, uint32_t *kout, const uint32_
 static int tile_items() { // the smallest tile any kernel this build may pick uses (sizes the tile-state array)
     OnesweepCfg c = current_cfg();
     int t = c.threads * c.items;
-    if (os2_cfg().impl == 3) t = std::min(t, onesweep3_tile_items());
     return t;
 }
 
@@ -743,36 +732,21 @@ static int launch_onesweep_wide(const uint32_t *kin, uint32_t *kout, const uint3
 
 static int launch_onesweep(const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, uint32_t n,
                            int shift, const uint32_t *digit_base, uint32_t *state, uint32_t *ctr, bool has_vals,
-                           bool iota, bool two_nibbles, cudaStream_t st) {
+                           bool iota, cudaStream_t st) {
     OnesweepCfg c = current_cfg();
     const bool aligned = (((uintptr_t)kin | (uintptr_t)vin) & 15) == 0; // cp.async.bulk needs 16-byte aligned sources
-    if (os2_cfg().impl == 3 && has_vals && aligned)
-        return launch_onesweep3(kin, kout, vin, vout, n, shift, digit_base, state, ctr, iota, two_nibbles, st);
     if (os2_cfg().impl == 2 && has_vals && aligned) {
         int rk = os2_cfg().rank;
-        if (c.threads == 256 && c.items == 16)
+        if (c.threads == 256 && c.items == 16) // (three CTAs per SM: 0.61 ms per pass against 0.50; kept as the comparison point)
             return launch_onesweep2_t<256, 16>(kin, kout, vin, vout, n, shift, digit_base, state, ctr, iota, rk, st);
-        if (c.threads == 256 && c.items == 12)
-            return launch_onesweep2_t<256, 12>(kin, kout, vin, vout, n, shift, digit_base, state, ctr, iota, rk, st);
-        if (c.threads == 512 && c.items == 8)
-            return launch_onesweep2_t<512, 8>(kin, kout, vin, vout, n, shift, digit_base, state, ctr, iota, rk, st);
-        if (c.threads == 384 && c.items == 12)
-            return launch_onesweep2_t<384, 12>(kin, kout, vin, vout, n, shift, digit_base, state, ctr, iota, rk, st);
         if (c.threads == 256 && c.items == 24)
             return launch_onesweep2_t<256, 24>(kin, kout, vin, vout, n, shift, digit_base, state, ctr, iota, rk, st);
-        if (c.threads == 384 && c.items == 16)
-            return launch_onesweep2_t<384, 16>(kin, kout, vin, vout, n, shift, digit_base, state, ctr, iota, rk, st);
-        if (c.threads == 512 && c.items == 12)
-            return launch_onesweep2_t<512, 12>(kin, kout, vin, vout, n, shift, digit_base, state, ctr, iota, rk, st);
     }
 #define DBT_CFG(T, I)                \
     if (c.threads == T && c.items == I) \
         return launch_onesweep_t<T, I>(kin, kout, vin, vout, n, shift, digit_base, state, ctr, has_vals, iota, st);
     DBT_CFG(256, 24)
     DBT_CFG(256, 16)
-    DBT_CFG(256, 12)
-    DBT_CFG(384, 12)
-    DBT_CFG(512, 8)
 #undef DBT_CFG
     set_error("unsupported DBT_ONESWEEP_CFG");
     return DBT_ERR_ARG;
@@ -781,7 +755,7 @@ static int launch_onesweep(const uint32_t *kin, uint32_t *kout, const uint32_t *
 constexpr uint64_t kMaxSortElems = (1ull << 32) - (1ull << 16); // u32 row ids, and tile arithmetic that stays inside 32 bits
 
 size_t sort_ws_bytes(uint64_t n) {
-    uint64_t ntiles = (n + 2048 - 1) / 2048 + 1; // bound for the smallest tile any config uses (256x12 = 3072)
+    uint64_t ntiles = (n + 2048 - 1) / 2048 + 1; // bound for the smallest tile any config uses (256x16 = 4096)
     if (n >= (1ull << 30)) return pad256(((n + 6143) / 6144 + 1) * kRadix * 8) + pad256(4 * kRadix * 4) + 4 * 256 + 4096; // 64-bit states
     return pad256(ntiles * kRadix * 4) + pad256(4 * kRadix * 4) + 4 * 256 + 4096;
 }
@@ -847,13 +821,12 @@ int sort_pairs_masked(uint32_t *&keys, uint32_t *&keys_alt, uint32_t *&vals, uin
         StageScope sc(ST_ONESWEEP, st);
         DBT_CUDA(cudaMemsetAsync(state, 0, state_bytes, st));
         DBT_CUDA(cudaMemsetAsync(ctr, 0, 4, st));
-        const bool two_nibbles = ((varying_mask >> plan.shift[p]) & 0xF0u) != 0; // else the window's high nibble is constant
         if (wide)
             DBT_TRY(launch_onesweep_wide(keys, keys_alt, vals, vals_alt, (uint32_t)n, plan.shift[p], ghist + p * kRadix,
                                          (uint64_t *)state, ctr, true, iota_vals && p == 0, st));
         else
             DBT_TRY(launch_onesweep(keys, keys_alt, vals, vals_alt, (uint32_t)n, plan.shift[p], ghist + p * kRadix,
-                                    (uint32_t *)state, ctr, true, iota_vals && p == 0, two_nibbles, st));
+                                    (uint32_t *)state, ctr, true, iota_vals && p == 0, st));
         std::swap(keys, keys_alt);
         std::swap(vals, vals_alt);
     }

@@ -1,4 +1,4 @@
-// sort_common.cuh -- device helpers shared by the onesweep kernels (kernels_sort.cu, kernels_sort3.cu).
+// sort_common.cuh -- device helpers shared by the onesweep kernels (kernels_sort.cu).
 #pragma once
 #include "dbt_internal.cuh"
 
@@ -68,11 +68,5 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-
-// version 3 of the onesweep pass (kernels_sort3.cu); sources 16-byte aligned
-int onesweep3_tile_items();
-int launch_onesweep3(const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, uint32_t n, int shift,
-                     const uint32_t *digit_base, uint32_t *state, uint32_t *ctr, bool iota, bool two_nibbles,
-                     cudaStream_t st);
 
 } // namespace dbt
