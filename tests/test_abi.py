@@ -84,6 +84,16 @@ def test_product_never_touches_the_oracle():
     assert not offenders, offenders
 
 
+def test_integration_notes_only_name_symbols_the_header_declares():
+    """INTEGRATION.md is what a maintainer binds against: every dbt_* function it names is declared in include/dbt_b200.h."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    hdr = open(os.path.join(ROOT, "include", "dbt_b200.h")).read()
+    declared = set(re.findall(r"\bdbt_[a-z0-9_]+\b", hdr))
+    named = {t for t in re.findall(r"\bdbt_[a-z0-9_]+\b", doc) if not t.endswith("_")}  # (dbt_dist_* etc. are families, not names)
+    named -= {"dbt_main", "dbt_b200", "dbt_oracle", "dbt_status"}                         # a binary, the header, a file, an enum
+    assert not (named - declared), sorted(named - declared)
+
+
 def test_bench_reference_arm_prints_a_contract_line():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
                         "--ref-rows", "200000"], capture_output=True, text=True, timeout=300)
