@@ -301,6 +301,38 @@ def test_large_dedup_properties_and_cpu_spot_checks(dbt, orc):
     assert bool((img_out[:, 1] == 100).all()) and bool((img_out[:, 0] == torch.arange(nbo, device="cuda", dtype=torch.int32)).all())
 
 
+def test_baseline_config1_at_full_size(dbt, orc):
+    """BASELINE.json configs[1] as stated -- EliminateDuplicates field=num on 100M records, one GPU -- checked through
+    size-independent properties by the independent torch checker that bench.py uses for the multi-GPU runs
+    (bench_verify.check_dedup_u32: keys strictly ascending, every emitted row is the min-recid row of its key, every key
+    once, and a 64-bit multiset hash over all 140 bytes of the emitted records equal to that of the winning input rows)."""
+    import torch
+
+    if torch.cuda.mem_get_info()[0] < 80 * 2**30:
+        pytest.skip("needs ~60 GB of free device memory")
+    sys.path.insert(0, ROOT)
+    import bench_verify as V
+
+    n, U = 100_000_000, 90_000_000
+    nb = n // 100
+    d_in = H.dev_alloc(nb * H.BLOCK_BYTES)
+    d_out = H.dev_alloc(nb * H.BLOCK_BYTES)
+    dbt.check(dbt.lib().dbt_gen_syn(42, n, U, 0, 0, n, 0, d_in.data_ptr(), H.stream()))
+    wsb = dbt.dev_ws_bytes(dbt.OP_DEDUP, nb, 0, "1")
+    ws = H.dev_alloc(wsb)
+    rows, uniq = dbt.dev_dedup(d_in.data_ptr(), nb, "1", d_out.data_ptr(), ws.data_ptr(), wsb, H.stream())
+    assert (rows, uniq) == (n, U)
+    del ws
+    torch.cuda.empty_cache()
+    res = V.check_dedup_u32(d_in, n, d_out, uniq, 1)
+    assert res["keys_strictly_ascending"] and res["every_row_is_min_recid_of_its_key"] and res["record_multiset_hash_equal"], res
+    assert res["rows"] == U and res["distinct_keys_in_input"] == U, res
+    nbo = U // 100  # CANON headers of the packed output image
+    hdr = d_out[: nbo * H.BLOCK_BYTES].view(torch.int32).view(nbo, 3504)
+    assert bool((hdr[:, 1] == 100).all()) and bool((hdr[:, 0] == torch.arange(nbo, device="cuda", dtype=torch.int32)).all())
+    assert bool((hdr[:, 3502] == 1).all()) and bool((hdr[:, 3503] == 100).all())
+
+
 def test_driver_runs_the_reference_workflow(dbt, orc, tmp_path):
     """dbt_main = the reference main.cpp workflow (generate, MergeJoin, HashJoin on the side files)."""
     exe = os.path.join(os.path.dirname(dbt.LIB_PATH), "dbt_main")
