@@ -306,8 +306,12 @@ def test_baseline_config1_at_full_size(dbt, orc):
     size-independent properties by the independent torch checker that bench.py uses for the multi-GPU runs
     (bench_verify.check_dedup_u32: keys strictly ascending, every emitted row is the min-recid row of its key, every key
     once, and a 64-bit multiset hash over all 140 bytes of the emitted records equal to that of the winning input rows)."""
+    import gc
+
     import torch
 
+    gc.collect()
+    torch.cuda.empty_cache()  # (an earlier test's cached blocks are not "free" for mem_get_info)
     if torch.cuda.mem_get_info()[0] < 80 * 2**30:
         pytest.skip("needs ~60 GB of free device memory")
     sys.path.insert(0, ROOT)
@@ -331,6 +335,39 @@ def test_baseline_config1_at_full_size(dbt, orc):
     hdr = d_out[: nbo * H.BLOCK_BYTES].view(torch.int32).view(nbo, 3504)
     assert bool((hdr[:, 1] == 100).all()) and bool((hdr[:, 0] == torch.arange(nbo, device="cuda", dtype=torch.int32)).all())
     assert bool((hdr[:, 3502] == 1).all()) and bool((hdr[:, 3503] == 100).all())
+
+
+@pytest.mark.parametrize("kind,label", [(1, "uniform"), (4, "zipf1.1")])
+def test_baseline_config3_shard_at_full_size(dbt, orc, kind, label):
+    """BASELINE.json configs[3] (HashJoin field=num, R = 100M x S = 1B, uniform and Zipf(1.1) keys) at the size one of four
+    GPUs sees -- all of R, a quarter of S -- checked row by row (all 140 bytes, S file order) by bench_verify's torch
+    boolean-table filter; the full S streams through one GPU in bench.py, whose match count must agree with N-GPU runs."""
+    import gc
+
+    import torch
+
+    gc.collect()
+    torch.cuda.empty_cache()  # (an earlier test's cached blocks are not "free" for mem_get_info)
+    if torch.cuda.mem_get_info()[0] < 120 * 2**30:
+        pytest.skip("needs ~100 GB of free device memory")
+    sys.path.insert(0, ROOT)
+    import bench_verify as V
+
+    L = dbt.lib()
+    nr, ns, D = 100_000_000, 250_000_000, 100_000_000
+    nbr, nbs = nr // 100, ns // 100
+    cap = int(nbs * 0.78) + 64
+    d_r, d_s, d_o = H.dev_alloc(nbr * H.BLOCK_BYTES), H.dev_alloc(nbs * H.BLOCK_BYTES), H.dev_alloc(cap * H.BLOCK_BYTES)
+    dbt.check(L.dbt_gen_syn(7, nr, D, 1, 0, nr, 0, d_r.data_ptr(), H.stream()))
+    dbt.check(L.dbt_gen_syn(9, 1_000_000_000, D, kind, 0, ns, 0, d_s.data_ptr(), H.stream()))  # the first quarter of the 1B-row S
+    wsb = dbt.dev_ws_bytes(dbt.OP_HASHJOIN, nbr, nbs, "1")
+    ws = H.dev_alloc(wsb)
+    k = dbt.dev_hashjoin(d_r.data_ptr(), nbr, d_s.data_ptr(), nbs, "1", d_o.data_ptr(), cap, ws.data_ptr(), wsb, H.stream())
+    del ws
+    torch.cuda.empty_cache()
+    res = V.check_semijoin_u32(d_r, nr, d_s, ns, d_o, k, 1, D)
+    assert res["same_rows_in_s_order"] and res["rows"] == res["rows_expected"] == k, res
+    assert 0.6 * ns < k < 0.75 * ns  # selectivity 1 - 1/e for uniform keys over |R| values, a little more under Zipf(1.1)
 
 
 def test_driver_runs_the_reference_workflow(dbt, orc, tmp_path):
