@@ -306,16 +306,7 @@ def test_baseline_config1_at_full_size(dbt, orc):
     size-independent properties by the independent torch checker that bench.py uses for the multi-GPU runs
     (bench_verify.check_dedup_u32: keys strictly ascending, every emitted row is the min-recid row of its key, every key
     once, and a 64-bit multiset hash over all 140 bytes of the emitted records equal to that of the winning input rows)."""
-    import gc
-
-    import torch
-
-    gc.collect()
-    torch.cuda.empty_cache()  # (an earlier test's cached blocks are not "free" for mem_get_info)
-    if torch.cuda.mem_get_info()[0] < 80 * 2**30:
-        pytest.skip("needs ~60 GB of free device memory")
-    sys.path.insert(0, ROOT)
-    import bench_verify as V
+    torch, V = _fresh_device_memory(80)
 
     n, U = 100_000_000, 90_000_000
     nb = n // 100
@@ -342,16 +333,7 @@ def test_baseline_config3_shard_at_full_size(dbt, orc, kind, label):
     """BASELINE.json configs[3] (HashJoin field=num, R = 100M x S = 1B, uniform and Zipf(1.1) keys) at the size one of four
     GPUs sees -- all of R, a quarter of S -- checked row by row (all 140 bytes, S file order) by bench_verify's torch
     boolean-table filter; the full S streams through one GPU in bench.py, whose match count must agree with N-GPU runs."""
-    import gc
-
-    import torch
-
-    gc.collect()
-    torch.cuda.empty_cache()  # (an earlier test's cached blocks are not "free" for mem_get_info)
-    if torch.cuda.mem_get_info()[0] < 120 * 2**30:
-        pytest.skip("needs ~100 GB of free device memory")
-    sys.path.insert(0, ROOT)
-    import bench_verify as V
+    torch, V = _fresh_device_memory(120)
 
     L = dbt.lib()
     nr, ns, D = 100_000_000, 250_000_000, 100_000_000
@@ -368,6 +350,65 @@ def test_baseline_config3_shard_at_full_size(dbt, orc, kind, label):
     res = V.check_semijoin_u32(d_r, nr, d_s, ns, d_o, k, 1, D)
     assert res["same_rows_in_s_order"] and res["rows"] == res["rows_expected"] == k, res
     assert 0.6 * ns < k < 0.75 * ns  # selectivity 1 - 1/e for uniform keys over |R| values, a little more under Zipf(1.1)
+
+
+def _fresh_device_memory(gib):
+    import gc
+
+    import torch
+
+    gc.collect()
+    torch.cuda.empty_cache()  # (an earlier test's cached blocks are not "free" for mem_get_info)
+    if torch.cuda.mem_get_info()[0] < gib * 2**30:
+        pytest.skip(f"needs ~{gib} GB of free device memory")
+    sys.path.insert(0, ROOT)
+    import bench_verify as V
+
+    return torch, V
+
+
+@pytest.mark.parametrize("field,seed,U", [("2", 77, 1_000_000_000), ("1", 78, 1 << 32)])
+def test_baseline_config2_and_north_star_sort_shard_at_full_size(dbt, orc, field, seed, U):
+    """BASELINE.json configs[2] (MergeSort field=str, 1B records on 8 GPUs) and north_star's num-key MergeSort at the size
+    one of the eight GPUs sorts -- 125M records -- through bench_verify.check_sort: (key, recid) order over the whole output
+    and a 64-bit multiset hash over all 140 bytes of every record equal to the input's."""
+    torch, V = _fresh_device_memory(70)
+    n = 125_000_000
+    nb = n // 100
+    d_in, d_out = H.dev_alloc(nb * H.BLOCK_BYTES), H.dev_alloc(nb * H.BLOCK_BYTES)
+    dbt.check(dbt.lib().dbt_gen_syn(seed, 1_000_000_000, U, 1, 0, n, 0, d_in.data_ptr(), H.stream()))  # rank 0's shard of the 1B rows
+    wsb = dbt.dev_ws_bytes(dbt.OP_SORT, nb, 0, field)
+    ws = H.dev_alloc(wsb)
+    rows = dbt.dev_mergesort(d_in.data_ptr(), nb, field, d_out.data_ptr(), ws.data_ptr(), wsb, H.stream())
+    assert rows == n
+    del ws
+    torch.cuda.empty_cache()
+    key_fn = V.str_key64 if field == "2" else (lambda im, m: V.column(im, m, 1))
+    res = V.check_sort(d_in, n, d_out, rows, key_fn)
+    assert res["ordered_in_rank"] and res["record_multiset_hash_equal"] and res["rows"] == n, res
+
+
+def test_baseline_config4_shard_at_full_size(dbt, orc):
+    """BASELINE.json configs[4] (MergeJoin field=num+str, 2 x 500M records on 8 GPUs) at the size one of the eight GPUs
+    joins -- 2 x 62.5M records -- through bench_verify.check_mergejoin_composite: R's min-recid row of every (num, str) key
+    present in both relations, ascending, all 140 bytes (expectation from torch.sort / unique / isin of the key columns)."""
+    torch, V = _fresh_device_memory(70)
+    n = 62_500_000
+    nb = n // 100
+    U = int(0.3 * n)
+    d_r, d_s = H.dev_alloc(nb * H.BLOCK_BYTES), H.dev_alloc(nb * H.BLOCK_BYTES)
+    d_ur, d_us, d_o = (H.dev_alloc(nb * H.BLOCK_BYTES) for _ in range(3))
+    dbt.check(dbt.lib().dbt_gen_syn(21, n, U, 1, 0, n, 0, d_r.data_ptr(), H.stream()))
+    dbt.check(dbt.lib().dbt_gen_syn(21 ^ 0x5EED, n, U, 3, 0, n, 0, d_s.data_ptr(), H.stream()))
+    wsb = dbt.dev_ws_bytes(dbt.OP_MERGEJOIN, nb, nb, "3")
+    ws = H.dev_alloc(wsb)
+    info = dbt.dev_mergejoin(d_r.data_ptr(), nb, d_s.data_ptr(), nb, "3", d_ur.data_ptr(), d_us.data_ptr(), d_o.data_ptr(),
+                             ws.data_ptr(), wsb, H.stream())
+    del ws, d_ur, d_us
+    torch.cuda.empty_cache()
+    res = V.check_mergejoin_composite(d_r, n, d_s, n, d_o, info["nres"])
+    assert res["same_keys_and_recids_in_global_order"] and res["record_multiset_hash_equal"], res
+    assert res["rows"] == res["rows_expected"] == info["nres"] > 0, res
 
 
 def test_driver_runs_the_reference_workflow(dbt, orc, tmp_path):
