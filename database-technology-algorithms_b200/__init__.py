@@ -15,7 +15,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdbt_b200.so")
+LIB_PATH = os.environ.get("DBT_LIB") or os.path.join(HERE, "libdbt_b200.so")  # DBT_LIB: an A/B build of the same library
 
 BLOCK_BYTES = 14016
 RECORD_BYTES = 140
