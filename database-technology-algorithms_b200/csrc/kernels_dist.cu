@@ -84,7 +84,8 @@ int launch_gather_push(const void *d_in, const uint32_t *d_row_slot, const PushP
 // ---- streaming scatter ---------------------------------------------------------------------------------
 // The sender side of the pipelined sort used to be: key extraction (one full read of the image for 8 bytes per row),
 // a partition pass over the row ids, and one random 140-byte gather per row into per-owner block images (267 bytes
-// read per row, kernels_gather.cu) -- 58 GB of HBM traffic for a 14 GB shard.  When the routing key is a record
+// read per row with 128-byte fills, 204 with the 64-byte fills of round 2, kernels_gather.cu) -- 58 GB (now ~45 GB) of HBM
+// traffic for a 14 GB shard.  When the routing key is a record
 // word (recid / num), ONE streaming pass does it: blocks arrive in shared memory by cp.async.bulk (as in the
 // streaming semi-join), every live row finds its bucket among the splitters, takes the next free slot of the bucket's
 // image (shared-memory ranks inside the block, one global atomic per block and bucket) and is copied there by one warp.

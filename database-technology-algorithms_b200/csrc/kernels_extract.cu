@@ -214,12 +214,12 @@ extract_kernel(const uint32_t *__restrict__ img, uint64_t nrows, const uint32_t 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Streaming extraction for block-dense images (every block but the last full => row == slot).
-// ncu (profiles/r01_notes.md): DRAM serves 128-byte lines here, and rows are 140 bytes apart, so the
-// strided kernel above already pulls ~the whole image from DRAM (132 B per row) -- but as scattered
-// sector requests at 3 TB/s.  This kernel streams whole 14016-byte blocks into shared memory with
-// cp.async.bulk (TMA bulk copy, one instruction per block, 3 blocks in flight per CTA) and picks the
-// key words out of shared memory: same DRAM bytes, sequential, and almost no LSU work.
+// Streaming extraction for the str / num+str keys (fields '2', '3'; fields '0', '1' use the sparse kernel further down).
+// ncu (profiles/r01_notes.md): with the default 128-byte fills and rows 140 bytes apart, the strided kernel above pulls
+// ~the whole image from DRAM (132 B per row) as scattered sector requests at 3 TB/s.  This kernel streams whole
+// 14016-byte blocks into shared memory with cp.async.bulk (TMA bulk copy, one instruction per block, 3 blocks in flight
+// per CTA) and picks the key words out of shared memory: same DRAM bytes, sequential, and almost no LSU work.  (40 of a
+// row's 140 bytes are key: 64-byte fills would read ~100 B per row at the lower rate of sparse reads -- about even.)
 // ---------------------------------------------------------------------------------------------
 constexpr int kExThreads = 128;
 constexpr int kExStages = 3;

@@ -276,18 +276,19 @@ int semijoin_stream(const void *d_s_img, uint64_t nblocks_s, int field, const ui
 }
 
 // =====================================================================================================
-// Two streaming passes (the default): no chain, nothing to wait for.
+// Two passes (the default): no chain, nothing to wait for.
 //
-//   pass 1  streams S (cp.async.bulk, three blocks in flight per CTA), tests every live row's key against the bitmap
-//           and writes, per S block, the 100-bit match mask and the match count (20 bytes per 14 KB block);
+//   pass 1  tests every live row's key against the bitmap and writes, per S block, the 100-bit match mask and the match
+//           count (20 bytes per 14 KB block).  It reads 8 bytes per row through 64-byte-fill loads (~68 B of DRAM traffic
+//           per row); round 2's first version streamed the whole image for it (140 B per row: 9.1 vs 4.8 ms per 400M rows);
 //   scan    exclusive prefix of the per-block counts (the device-wide scan of kernels_gather.cu) = the output row of
 //           every block's first match, and the total -- so a result that does not fit is refused before a byte moves;
-//   pass 2  streams S again and copies every matching 140-byte record from shared memory to its final place in the
-//           packed output image (one warp per record: 35 consecutive words, consecutive matches are contiguous).
+//   pass 2  streams S (cp.async.bulk, three blocks in flight per CTA) and copies every matching 140-byte record from shared
+//           memory to its final place in the packed output image (one warp per record: 35 consecutive words, consecutive
+//           matches are contiguous).
 //
-// DRAM traffic 280 B per S row + 140 B per match against ~141 + 8 + 8 + 4 + (267 + 140) per match for the column path
-// (extraction, probe, compaction, random gather): S is read twice, but sequentially, and the scattered second read of
-// the gather (267 B per 140-byte row) is gone.
+// DRAM traffic 68 + 140 B per S row + 140 B per match, against ~68 + 8 + 8 + 4 + (204 + 140) per match for the column path
+// (extraction, probe, compaction, random gather): S's records are read sequentially, once, instead of as a gather.
 // =====================================================================================================
 constexpr int kTpThreads = 128;
 constexpr int kTpStages = 3;
