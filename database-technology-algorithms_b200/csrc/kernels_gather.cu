@@ -35,10 +35,10 @@ struct ScanWs {
 };
 
 #ifndef DBT_SCAN_THREADS
-#define DBT_SCAN_THREADS 512
+#define DBT_SCAN_THREADS 384 // x 3 CTAs per SM: 0.450 ms per 100M rows (512 x 2: 0.483, 256 x 4: 0.486, 1024 x 1: 0.495)
 #endif
 #ifndef DBT_SCAN_MINB
-#define DBT_SCAN_MINB 2
+#define DBT_SCAN_MINB 3
 #endif
 constexpr int kScanThreads = DBT_SCAN_THREADS;
 constexpr int kScanItems = 16; // two groups of 8 consecutive rows per thread
@@ -51,7 +51,7 @@ constexpr int kScanTile = kScanThreads * kScanItems;
 //          A tile's outputs are first compacted in shared memory and then written coalesced; a tile that emits
 //          more than it holds (field-'3' multiplicities) writes directly.
 template <class CountFn, class EmitFn>
-__global__ void __launch_bounds__(kScanThreads, DBT_SCAN_MINB) // <= 64 registers: two 512-thread CTAs per SM (ncu: the compaction variant took 110)
+__global__ void __launch_bounds__(kScanThreads, DBT_SCAN_MINB) // <= 56 registers: three 384-thread CTAs per SM
 scan_emit_kernel(uint64_t n, CountFn cnt, EmitFn emit, ScanWs ws, unsigned long long *total_out) {
     __shared__ uint64_t s_wsum[kScanThreads / 32];
     __shared__ uint64_t s_prefix;
