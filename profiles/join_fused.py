@@ -28,7 +28,7 @@ peak = 6539.9
 for kind, label in ((1, "uniform"), (4, "zipf1.1")):
     dbt.check(L.dbt_gen_syn(9, ns, D, kind, 0, ns, 0, d_s.data_ptr(), sp))
     ref = None
-    for fused in ("2", "1", "0"):
+    for fused in os.environ.get("JOIN_MODES", "2,1,0").split(","):
         os.environ["DBT_JOIN_FUSED"] = fused
         L.dbt_stage_timing_enable(1)
         times = []
